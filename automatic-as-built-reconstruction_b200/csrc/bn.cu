@@ -1,0 +1,344 @@
+// bn.cu - BatchNormalization fused with (Leaky)ReLU over the active rows.
+//
+// Reference: SparseConvNet/sparseconvnet/SCN/CPU/BatchNormalization.cpp:13-107 (math) and
+// CUDA/BatchNormalization.cu:14-184 (which runs on <= 16 thread blocks).  Here: a full-grid
+// statistics pass with 128-bit coalesced loads and per-thread fp32 / cross-thread fp64
+// accumulation, a one-block-per-128-channels finalize, and a vectorised elementwise apply.
+#include "common.cuh"
+#include "../../include/scn_b200.h"
+
+namespace scn {
+
+constexpr int BN_T = 256;
+
+// ---- statistics: q0 = sum a, q1 = sum b over rows, per channel ---------------------------
+// forward:  a = x,  b = x*x
+// backward: a = d,  b = (x-mean)*d   with d = dy * (y > 0 ? 1 : leak)
+template <bool BWD>
+__device__ __forceinline__ void bn_terms(float x, float y, float dy, float mean, float leak,
+                                         float &a, float &b) {
+  if (BWD) {
+    const float d = dy * (y > 0.f ? 1.f : leak);
+    a = d;
+    b = (x - mean) * d;
+  } else {
+    a = x;
+    b = x * x;
+  }
+}
+
+// vector path: C % 4 == 0 and 1024 % C == 0; thread owns one channel quad for all its rows
+template <bool BWD>
+__global__ void __launch_bounds__(BN_T)
+k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
+               const float *__restrict__ dY, const float *__restrict__ mean, float leak,
+               long long n, int C, double *__restrict__ part) {
+  __shared__ double red[2][BN_T * 4];
+  const int qpr = C >> 2;               // quads per row
+  const int rpb = BN_T / qpr;           // rows per block iteration (>= 1 since C <= 1024)
+  const int cq = threadIdx.x % qpr, rs = threadIdx.x / qpr;
+  float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
+  float4 mu = make_float4(0, 0, 0, 0);
+  if (BWD) mu = reinterpret_cast<const float4 *>(mean)[cq];
+  if (rs < rpb) {
+    for (long long r = (long long)blockIdx.x * rpb + rs; r < n; r += (long long)gridDim.x * rpb) {
+      const long long o = r * qpr + cq;
+      const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + o);
+      float4 y = x, d = x;
+      if (BWD) {
+        y = __ldg(reinterpret_cast<const float4 *>(Yo) + o);
+        d = __ldg(reinterpret_cast<const float4 *>(dY) + o);
+      }
+      float a, b;
+      bn_terms<BWD>(x.x, y.x, d.x, mu.x, leak, a, b); s0.x += a; s1.x += b;
+      bn_terms<BWD>(x.y, y.y, d.y, mu.y, leak, a, b); s0.y += a; s1.y += b;
+      bn_terms<BWD>(x.z, y.z, d.z, mu.z, leak, a, b); s0.z += a; s1.z += b;
+      bn_terms<BWD>(x.w, y.w, d.w, mu.w, leak, a, b); s0.w += a; s1.w += b;
+    }
+  }
+  const int t4 = threadIdx.x * 4;
+  red[0][t4] = s0.x; red[0][t4 + 1] = s0.y; red[0][t4 + 2] = s0.z; red[0][t4 + 3] = s0.w;
+  red[1][t4] = s1.x; red[1][t4 + 1] = s1.y; red[1][t4 + 2] = s1.z; red[1][t4 + 3] = s1.w;
+  __syncthreads();
+  // thread c (< C) sums the rpb row-slots of channel c: element index = rs*C + c
+  for (int c = threadIdx.x; c < C; c += BN_T) {
+    double a = 0, b = 0;
+    for (int j = 0; j < rpb; ++j) { a += red[0][j * C + c]; b += red[1][j * C + c]; }
+    part[((long long)blockIdx.x * 2 + 0) * C + c] = a;
+    part[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+  }
+}
+
+// generic path: block (32,8); x = channel, y = row slot
+template <bool BWD>
+__global__ void __launch_bounds__(BN_T)
+k_bn_stats_gen(const float *__restrict__ X, const float *__restrict__ Yo,
+               const float *__restrict__ dY, const float *__restrict__ mean, float leak,
+               long long n, int C, double *__restrict__ part) {
+  __shared__ double red[2][8][33];
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  double s0 = 0, s1 = 0;
+  if (c < C) {
+    const float mu = BWD ? mean[c] : 0.f;
+    for (long long r = (long long)blockIdx.x * 8 + threadIdx.y; r < n; r += (long long)gridDim.x * 8) {
+      const float x = X[r * C + c];
+      float a, b;
+      bn_terms<BWD>(x, BWD ? Yo[r * C + c] : 0.f, BWD ? dY[r * C + c] : 0.f, mu, leak, a, b);
+      s0 += a;
+      s1 += b;
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = s0;
+  red[1][threadIdx.y][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0, b = 0;
+    for (int j = 0; j < 8; ++j) { a += red[0][j][threadIdx.x]; b += red[1][j][threadIdx.x]; }
+    part[((long long)blockIdx.x * 2 + 0) * C + c] = a;
+    part[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+  }
+}
+
+// ---- finalize --------------------------------------------------------------------------
+// forward train (CPU/BatchNormalization.cpp:19-40): coef = [scale, shift]
+__global__ void k_bn_fwd_finalize(const double *__restrict__ part, int gx, long long n, int C,
+                                  float *save_mean, float *save_invstd, float *running_mean,
+                                  float *running_var, const float *weight, const float *bias,
+                                  float eps, float momentum, float *__restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sum = 0, sq = 0;
+  for (int g = 0; g < gx; ++g) {
+    sum += part[((long long)g * 2 + 0) * C + c];
+    sq += part[((long long)g * 2 + 1) * C + c];
+  }
+  const double mean = sum / (double)n;
+  const double s = sq - mean * mean * (double)n;  // sum of squared deviations
+  running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
+  running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(s / (double)(n - 1));
+  const float invstd = powf((float)(s / (double)n) + eps, -0.5f);
+  save_mean[c] = (float)mean;
+  save_invstd[c] = invstd;
+  const float w = invstd * (weight ? weight[c] : 1.f);
+  coef[c] = w;
+  coef[C + c] = -(float)mean * w + (bias ? bias[c] : 0.f);
+}
+
+// forward eval (:41-46): statistics are the running buffers as passed
+__global__ void k_bn_eval_coef(int C, float *save_mean, float *save_invstd,
+                               const float *running_mean, const float *running_var,
+                               const float *weight, const float *bias, float eps,
+                               float *__restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = running_mean[c];
+  const float invstd = powf(running_var[c] + eps, -0.5f);
+  save_mean[c] = mean;
+  save_invstd[c] = invstd;
+  const float w = invstd * (weight ? weight[c] : 1.f);
+  coef[c] = w;
+  coef[C + c] = -mean * w + (bias ? bias[c] : 0.f);
+}
+
+// backward (:86-106): coef = [gradMean, k, invstd*gamma]
+__global__ void k_bn_bwd_finalize(const double *__restrict__ part, int gx, long long n, int C,
+                                  const float *save_invstd, const float *weight, float *d_weight,
+                                  float *d_bias, float *__restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double gsum = 0, dotp = 0;
+  for (int g = 0; g < gx; ++g) {
+    gsum += part[((long long)g * 2 + 0) * C + c];
+    dotp += part[((long long)g * 2 + 1) * C + c];
+  }
+  const float invstd = save_invstd[c];
+  if (d_bias) d_bias[c] = (float)gsum;
+  if (d_weight) d_weight[c] = (float)dotp * invstd;
+  coef[c] = (float)(gsum / (double)n);
+  coef[C + c] = (float)dotp * invstd * invstd / (float)n;
+  coef[2 * C + c] = invstd * (weight ? weight[c] : 1.f);
+}
+
+// ---- apply -----------------------------------------------------------------------------
+__device__ __forceinline__ float lrelu(float v, float leak) { return v > 0.f ? v : v * leak; }
+
+template <bool VEC>
+__global__ void __launch_bounds__(BN_T)
+k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, const float *__restrict__ coef,
+               float leak, long long total, int C) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    const long long nq = total >> 2;
+    for (; i < nq; i += st) {
+      const int c = (int)((i << 2) % C);
+      const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + i);
+      const float4 w = *reinterpret_cast<const float4 *>(coef + c);
+      const float4 b = *reinterpret_cast<const float4 *>(coef + C + c);
+      float4 y;
+      y.x = lrelu(fmaf(x.x, w.x, b.x), leak);
+      y.y = lrelu(fmaf(x.y, w.y, b.y), leak);
+      y.z = lrelu(fmaf(x.z, w.z, b.z), leak);
+      y.w = lrelu(fmaf(x.w, w.w, b.w), leak);
+      reinterpret_cast<float4 *>(Y)[i] = y;
+    }
+  } else {
+    for (; i < total; i += st) {
+      const int c = (int)(i % C);
+      Y[i] = lrelu(fmaf(X[i], coef[c], coef[C + c]), leak);
+    }
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(BN_T)
+k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
+               const float *__restrict__ dY, float *__restrict__ dX,
+               const float *__restrict__ mean, const float *__restrict__ coef, float leak,
+               long long total, int C) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    const long long nq = total >> 2;
+    for (; i < nq; i += st) {
+      const int c = (int)((i << 2) % C);
+      const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + i);
+      const float4 y = __ldg(reinterpret_cast<const float4 *>(Yo) + i);
+      const float4 d = __ldg(reinterpret_cast<const float4 *>(dY) + i);
+      const float4 mu = *reinterpret_cast<const float4 *>(mean + c);
+      const float4 gm = *reinterpret_cast<const float4 *>(coef + c);
+      const float4 kk = *reinterpret_cast<const float4 *>(coef + C + c);
+      const float4 sc = *reinterpret_cast<const float4 *>(coef + 2 * C + c);
+      float4 o;
+      o.x = (d.x * (y.x > 0.f ? 1.f : leak) - gm.x - (x.x - mu.x) * kk.x) * sc.x;
+      o.y = (d.y * (y.y > 0.f ? 1.f : leak) - gm.y - (x.y - mu.y) * kk.y) * sc.y;
+      o.z = (d.z * (y.z > 0.f ? 1.f : leak) - gm.z - (x.z - mu.z) * kk.z) * sc.z;
+      o.w = (d.w * (y.w > 0.f ? 1.f : leak) - gm.w - (x.w - mu.w) * kk.w) * sc.w;
+      reinterpret_cast<float4 *>(dX)[i] = o;
+    }
+  } else {
+    for (; i < total; i += st) {
+      const int c = (int)(i % C);
+      const float d = dY[i] * (Yo[i] > 0.f ? 1.f : leak);
+      dX[i] = (d - coef[c] - (X[i] - mean[c]) * coef[C + c]) * coef[2 * C + c];
+    }
+  }
+}
+
+static bool vec_ok(long long n, int C, const void *a, const void *b, const void *c, const void *d) {
+  auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+  return C % 4 == 0 && C <= 1024 && 1024 % C == 0 && al(a) && al(b) && al(c) && al(d);
+}
+
+static int stats_grid(long long n, int rows_per_iter) {
+  long long g = (n + (long long)rows_per_iter * 4 - 1) / ((long long)rows_per_iter * 4);
+  const long long cap = (long long)num_sms() * 4;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int apply_grid(long long work) {
+  long long g = (work + BN_T - 1) / BN_T;
+  const long long cap = (long long)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace scn
+
+using namespace scn;
+
+extern "C" {
+
+int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *save_invstd,
+                          float *running_mean, float *running_var, const float *weight,
+                          const float *bias, float eps, float momentum, int train, float leakiness,
+                          int64_t n, int64_t C64, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = (int)C64;
+  SCN_CHECK(C > 0 && save_mean && save_invstd && running_mean && running_var, "bad BN arguments");
+  if (n == 0) return 0;
+  SCN_CHECK(in && out, "null feature pointer");
+  const bool vec = vec_ok(n, C, in, out, in, out);
+  float *coef = nullptr;
+  SCN_TRY(dev_alloc_t(&coef, (size_t)3 * C, s));
+  if (train) {
+    int gx;
+    double *part = nullptr;
+    if (vec) {
+      gx = stats_grid(n, BN_T / (C / 4));
+      SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
+      k_bn_stats_vec<false><<<gx, BN_T, 0, s>>>(in, nullptr, nullptr, nullptr, 0.f, n, C, part);
+    } else {
+      gx = stats_grid(n, 8);
+      SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
+      k_bn_stats_gen<false><<<dim3(gx, cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, nullptr, nullptr,
+                                                                        nullptr, 0.f, n, C, part);
+    }
+    SCN_LAUNCHED();
+    k_bn_fwd_finalize<<<cdiv(C, 128), 128, 0, s>>>(part, gx, n, C, save_mean, save_invstd,
+                                                   running_mean, running_var, weight, bias, eps,
+                                                   momentum, coef);
+    SCN_LAUNCHED();
+    dev_free(part, s);
+  } else {
+    k_bn_eval_coef<<<cdiv(C, 128), 128, 0, s>>>(C, save_mean, save_invstd, running_mean,
+                                                running_var, weight, bias, eps, coef);
+    SCN_LAUNCHED();
+  }
+  const long long total = (long long)n * C;
+  if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, 0, s>>>(in, out, coef, leakiness, total, C);
+  else k_bn_fwd_apply<false><<<apply_grid(total), BN_T, 0, s>>>(in, out, coef, leakiness, total, C);
+  SCN_LAUNCHED();
+  dev_free(coef, s);
+  return 0;
+}
+
+int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const float *d_out,
+                           const float *save_mean, const float *save_invstd, const float *weight,
+                           float *d_weight, float *d_bias, float leakiness, int64_t n, int64_t C64,
+                           void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = (int)C64;
+  SCN_CHECK(C > 0 && save_mean && save_invstd, "bad BN arguments");
+  if (n == 0) {
+    if (d_weight) SCN_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)C * 4, s));
+    if (d_bias) SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)C * 4, s));
+    return 0;
+  }
+  SCN_CHECK(in && d_in && out && d_out, "null feature pointer");
+  const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0);
+  float *coef = nullptr;
+  double *part = nullptr;
+  SCN_TRY(dev_alloc_t(&coef, (size_t)3 * C, s));
+  int gx;
+  if (vec) {
+    gx = stats_grid(n, BN_T / (C / 4));
+    SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
+    k_bn_stats_vec<true><<<gx, BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, part);
+  } else {
+    gx = stats_grid(n, 8);
+    SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
+    k_bn_stats_gen<true><<<dim3(gx, cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, out, d_out, save_mean,
+                                                                     leakiness, n, C, part);
+  }
+  SCN_LAUNCHED();
+  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, s>>>(part, gx, n, C, save_invstd, weight, d_weight,
+                                                 d_bias, coef);
+  SCN_LAUNCHED();
+  const long long total = (long long)n * C;
+  if (vec)
+    k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, 0, s>>>(in, out, d_out, d_in, save_mean, coef,
+                                                             leakiness, total, C);
+  else
+    k_bn_bwd_apply<false><<<apply_grid(total), BN_T, 0, s>>>(in, out, d_out, d_in, save_mean, coef,
+                                                          leakiness, total, C);
+  SCN_LAUNCHED();
+  dev_free(part, s);
+  dev_free(coef, s);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// common.cu - error state, stream-ordered allocation, device-wide scan and radix sort.
+#include "common.cuh"
+#include <stdarg.h>
+#include <mutex>
+#include "../../include/scn_b200.h"
+
+namespace scn {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static std::once_flag g_pool_once;
+static int g_num_sms = 0;
+
+static void init_pool() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ULL;  // never trim: the per-step Metadata rebuild reuses it
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+int num_sms() {
+  std::call_once(g_pool_once, init_pool);
+  return g_num_sms > 0 ? g_num_sms : 148;
+}
+
+int dev_alloc(void **p, size_t bytes, cudaStream_t s) {
+  std::call_once(g_pool_once, init_pool);
+  *p = nullptr;
+  SCN_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, s));
+  return 0;
+}
+
+void dev_free(void *p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+
+int64_t *host_scratch(size_t n) {
+  static thread_local int64_t *buf = nullptr;
+  static thread_local size_t cap = 0;
+  if (n > cap) {
+    if (buf) cudaFreeHost(buf);
+    cap = n < 4096 ? 4096 : n;
+    if (cudaMallocHost((void **)&buf, cap * sizeof(int64_t)) != cudaSuccess) {
+      buf = nullptr;
+      cap = 0;
+    }
+  }
+  return buf;
+}
+
+// ---------------------------------------------------------------------------------------
+// exclusive scan: 512 threads x 8 items per block, recursive over block sums
+// ---------------------------------------------------------------------------------------
+constexpr int SCAN_T = 512, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_block(const int32_t *in, int32_t *out,
+             int32_t *__restrict__ block_sums, long long n_in, long long n_out) {
+  __shared__ int32_t warp_tot[SCAN_T / 32];
+  const long long base = (long long)blockIdx.x * SCAN_B + (long long)threadIdx.x * SCAN_I;
+  int32_t v[SCAN_I];
+  int32_t tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_I; ++i) {
+    long long g = base + i;
+    v[i] = (g < n_in) ? in[g] : 0;
+    tsum += v[i];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int32_t w = (lane < SCAN_T / 32) ? warp_tot[lane] : 0;
+    int32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < SCAN_T / 32) warp_tot[lane] = wi - w;  // exclusive warp offsets
+    if (lane == SCAN_T / 32 - 1 && block_sums) block_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  int32_t run = warp_tot[wid] + inc - tsum;
+#pragma unroll
+  for (int i = 0; i < SCAN_I; ++i) {
+    long long g = base + i;
+    if (g < n_out) out[g] = run;
+    run += v[i];
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_add(int32_t *__restrict__ out, const int32_t *__restrict__ block_off, long long n_out) {
+  const int32_t add = block_off[blockIdx.x];
+  const long long base = (long long)blockIdx.x * SCAN_B + (long long)threadIdx.x * SCAN_I;
+#pragma unroll
+  for (int i = 0; i < SCAN_I; ++i) {
+    long long g = base + i;
+    if (g < n_out) out[g] += add;
+  }
+}
+
+int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s) {
+  const long long n_out = n + 1;
+  const int nb = cdiv(n_out, SCAN_B);
+  if (nb == 1) {
+    k_scan_block<<<1, SCAN_T, 0, s>>>(in, out, nullptr, n, n_out);
+    SCN_LAUNCHED();
+    return 0;
+  }
+  int32_t *bs = nullptr;
+  SCN_TRY(dev_alloc_t(&bs, (size_t)nb + 1, s));
+  k_scan_block<<<nb, SCAN_T, 0, s>>>(in, out, bs, n, n_out);
+  SCN_LAUNCHED();
+  int r = exclusive_scan_i32(bs, bs, nb, s);
+  if (r) { dev_free(bs, s); return r; }
+  k_scan_add<<<nb, SCAN_T, 0, s>>>(out, bs, n_out);
+  SCN_LAUNCHED();
+  dev_free(bs, s);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits; every warp owns one contiguous chunk
+// ---------------------------------------------------------------------------------------
+constexpr int RS_WARPS = 8, RS_CHUNK = 2048;
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_rs_hist(const uint32_t *__restrict__ keys, int32_t *__restrict__ H, long long n, int shift,
+          int n_chunks) {
+  __shared__ int32_t hist[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * RS_WARPS + w;
+  for (int d = lane; d < 256; d += 32) hist[w][d] = 0;
+  __syncwarp();
+  if (chunk < n_chunks) {
+    const long long b = (long long)chunk * RS_CHUNK;
+    for (int it = 0; it < RS_CHUNK; it += 32) {
+      long long g = b + it + lane;
+      if (g < n) atomicAdd(&hist[w][(keys[g] >> shift) & 255], 1);
+    }
+  }
+  __syncwarp();
+  if (chunk < n_chunks)
+    for (int d = lane; d < 256; d += 32) H[(long long)d * n_chunks + chunk] = hist[w][d];
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals,
+             uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out,
+             const int32_t *__restrict__ Hs, long long n, int shift, int n_chunks) {
+  __shared__ int32_t cnt[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * RS_WARPS + w;
+  if (chunk >= n_chunks) return;
+  for (int d = lane; d < 256; d += 32) cnt[w][d] = Hs[(long long)d * n_chunks + chunk];
+  __syncwarp();
+  const long long b = (long long)chunk * RS_CHUNK;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int it = 0; it < RS_CHUNK; it += 32) {
+    long long g = b + it + lane;
+    const bool valid = g < n;
+    uint32_t key = valid ? keys[g] : 0u;
+    int32_t val = valid ? vals[g] : 0;
+    const int d = valid ? (int)((key >> shift) & 255) : 256 + lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & lt);
+    if (valid) {
+      const int pos = cnt[w][d] + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+    __syncwarp();
+    if (valid && rank == 0) cnt[w][d] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s) {
+  if (n <= 1 || bits <= 0) return 0;
+  const int passes = (bits + 7) / 8;
+  const int n_chunks = cdiv(n, RS_CHUNK);
+  const int nb = cdiv(n_chunks, RS_WARPS);
+  uint32_t *k2 = nullptr;
+  int32_t *v2 = nullptr, *H = nullptr;
+  SCN_TRY(dev_alloc_t(&k2, (size_t)n, s));
+  SCN_TRY(dev_alloc_t(&v2, (size_t)n, s));
+  SCN_TRY(dev_alloc_t(&H, (size_t)256 * n_chunks + 1, s));
+  uint32_t *ka = keys, *kb = k2;
+  int32_t *va = vals, *vb = v2;
+  for (int p = 0; p < passes; ++p) {
+    k_rs_hist<<<nb, RS_WARPS * 32, 0, s>>>(ka, H, n, p * 8, n_chunks);
+    SCN_LAUNCHED();
+    SCN_TRY(exclusive_scan_i32(H, H, (long long)256 * n_chunks, s));
+    k_rs_scatter<<<nb, RS_WARPS * 32, 0, s>>>(ka, va, kb, vb, H, n, p * 8, n_chunks);
+    SCN_LAUNCHED();
+    uint32_t *tk = ka; ka = kb; kb = tk;
+    int32_t *tv = va; va = vb; vb = tv;
+  }
+  if (ka != keys) {
+    SCN_CUDA(cudaMemcpyAsync(keys, ka, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    SCN_CUDA(cudaMemcpyAsync(vals, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  dev_free(k2, s);
+  dev_free(v2, s);
+  dev_free(H, s);
+  return 0;
+}
+
+__global__ void k_scale(float *y, float a, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += st) y[i] *= a;
+}
+
+}  // namespace scn
+
+extern "C" {
+const char *scn_last_error(void) { return scn::g_err; }
+int scn_version(void) { return 100; }
+int scn_n_rulebook_bits(void) { return 32; }
+int64_t scn_launch_count(void) { return scn::g_launches.load(); }
+int scn_scale_inplace(float *y, float alpha, int64_t n, void *stream) {
+  if (n <= 0) return 0;
+  int nb = scn::cdiv(n, 256);
+  int cap = scn::num_sms() * 8;
+  if (nb > cap) nb = cap;
+  scn::k_scale<<<nb, 256, 0, (cudaStream_t)stream>>>(y, alpha, n);
+  SCN_LAUNCHED();
+  return 0;
+}
+}

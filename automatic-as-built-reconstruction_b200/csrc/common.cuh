@@ -1,0 +1,91 @@
+// common.cuh - shared plumbing of libscn_b200: error reporting, stream-ordered device
+// memory, launch counting, and the small device primitives (scan, warp reductions) every
+// kernel file uses.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+
+namespace scn {
+
+// ---- errors ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define SCN_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      scn::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                     cudaGetErrorString(_e));                                           \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define SCN_CHECK(cond, ...)                                                            \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      scn::set_error(__VA_ARGS__);                                                      \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define SCN_TRY(expr)                                                                   \
+  do {                                                                                  \
+    int _r = (expr);                                                                    \
+    if (_r) return _r;                                                                  \
+  } while (0)
+
+// count + check a kernel launch
+#define SCN_LAUNCHED()                                                                  \
+  do {                                                                                  \
+    scn::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+    SCN_CUDA(cudaGetLastError());                                                       \
+  } while (0)
+
+// ---- stream-ordered device memory -------------------------------------------------------
+// cudaMallocAsync on the device's default pool with the release threshold raised, so the
+// rebuild-every-step Metadata never goes back to the driver after the first iteration.
+int dev_alloc(void **p, size_t bytes, cudaStream_t s);
+void dev_free(void *p, cudaStream_t s);
+
+template <typename T>
+inline int dev_alloc_t(T **p, size_t n, cudaStream_t s) {
+  return dev_alloc((void **)p, (n ? n : 1) * sizeof(T), s);
+}
+
+// pinned host scratch for count read-backs (per thread)
+int64_t *host_scratch(size_t n_int64);
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+int num_sms();
+
+// ---- device-wide exclusive scan of int32 ----------------------------------------------
+// out[i] = sum_{j<i} in[j]; out has n+1 entries (out[n] = total). in may alias out.
+int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s);
+
+// ---- stable LSD radix sort of (key uint32, value int32), keys limited to `bits` ----------
+int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s);
+
+// ---- device helpers ------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return k;
+}
+#endif
+
+}  // namespace scn

@@ -1,0 +1,31 @@
+// conv.cuh - interfaces shared by the FFMA (conv.cu) and tcgen05 (conv_tc.cu) convolution paths
+#pragma once
+#include "metadata.cuh"
+
+namespace scn {
+
+struct TileView {            // device view of a TileBook, passed by value to kernels
+  int identity;
+  int n_tiles;
+  const int32_t *perm;
+  const uint32_t *tile_mask;
+  const int32_t *tile_off;
+  const int32_t *entries;
+};
+
+TileView make_view(const TileBook &tb);
+
+// Y[stationary] = bias + sum_k X[partner_k] @ W[k]; W is [K,Cin,Cout] row-major fp32.
+int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
+           const TileBook &tb, int precision, cudaStream_t s);
+
+// tensor-core variants. Return 0 = done, >0 = shape/precision not handled (caller uses the FFMA
+// kernels), <0 = -(error) with scn_last_error set.
+int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
+              long long n_rows, const TileView &tv, int K, int precision, cudaStream_t s);
+int weight_grad_tc(const float *X, const float *dY, float *dW, int Cin, int Cout, RuleBook *rb,
+                   int xcol, int ycol, int precision, cudaStream_t s);
+
+int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, cudaStream_t s);
+
+}  // namespace scn

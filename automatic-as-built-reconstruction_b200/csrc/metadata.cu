@@ -1,0 +1,1066 @@
+// metadata.cu - the integer core on the GPU: coordinate packing, hash-grid insert/lookup,
+// input-layer numbering, submanifold / strided rulebooks, tile books, SparseToDense rules.
+//
+// Reference semantics reproduced (all under SparseConvNet/sparseconvnet/SCN/Metadata/):
+//   IOLayersRules.h:19-125            input layer: site id = order of first occurrence
+//   SubmanifoldConvolutionRules.h:13-87  k = row-major offset (last dim fastest), pairs (in,out)
+//   ConvolutionRules.h:12-105, RectangularRegions.h:97-119  strided rules + output grid
+//   ConvolutionRules.h:110-151        SparseToDense linear offsets
+//   Metadata.cpp:149-168              getSpatialLocations
+// The reference numbers conv-created sites in sparsehash iteration order (unpinned); here the
+// order is first touch in input-row order, made batch-contiguous ascending like the reference's
+// per-sample loop (ConvolutionRules.h:80-88).
+#include "metadata.cuh"
+#include "../../include/scn_b200.h"
+#include <algorithm>
+#include <mutex>
+
+namespace scn {
+
+static bool g_tile_grouping = true;
+
+// ---------------------------------------------------------------------------------------
+// hash grid
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_key(int x, int y, int z, int b) {
+  return ((uint64_t)(uint32_t)b << 48) | ((uint64_t)(uint32_t)x << 32) |
+         ((uint64_t)(uint32_t)y << 16) | (uint64_t)(uint32_t)z;
+}
+__device__ __forceinline__ bool coord_ok(int x, int y, int z) {
+  return ((unsigned)x | (unsigned)y | (unsigned)z) < 65536u;
+}
+__device__ __forceinline__ uint32_t hash_insert(uint64_t *hk, uint32_t mask, uint64_t key) {
+  uint32_t slot = (uint32_t)mix64(key) & mask;
+  while (true) {
+    unsigned long long prev =
+        atomicCAS((unsigned long long *)&hk[slot], (unsigned long long)EMPTY_KEY,
+                  (unsigned long long)key);
+    if (prev == EMPTY_KEY || prev == key) return slot;
+    slot = (slot + 1) & mask;
+  }
+}
+__device__ __forceinline__ int hash_find(const uint64_t *__restrict__ hk,
+                                         const int32_t *__restrict__ hv, uint32_t mask,
+                                         uint64_t key) {
+  uint32_t slot = (uint32_t)mix64(key) & mask;
+  while (true) {
+    const uint64_t k = hk[slot];
+    if (k == key) return hv[slot];
+    if (k == EMPTY_KEY) return -1;
+    slot = (slot + 1) & mask;
+  }
+}
+
+static uint32_t table_capacity(int64_t n) {
+  uint64_t c = 64;
+  while (c < (uint64_t)(2 * n + 2)) c <<= 1;
+  return (uint32_t)c;
+}
+
+static int grid_alloc_table(Grid *g, int64_t n_keys, int fill_val_byte, cudaStream_t s) {
+  g->hcap = table_capacity(n_keys);
+  SCN_TRY(dev_alloc_t(&g->hkeys, g->hcap, s));
+  SCN_TRY(dev_alloc_t(&g->hvals, g->hcap, s));
+  SCN_CUDA(cudaMemsetAsync(g->hkeys, 0xFF, (size_t)g->hcap * 8, s));
+  SCN_CUDA(cudaMemsetAsync(g->hvals, fill_val_byte, (size_t)g->hcap * 4, s));
+  return 0;
+}
+
+static void grid_free(Grid *g, cudaStream_t s) {
+  dev_free(g->coords, s);
+  dev_free(g->hkeys, s);
+  dev_free(g->hvals, s);
+  delete g;
+}
+
+static void tilebook_free(TileBook &tb, cudaStream_t s) {
+  dev_free(tb.perm, s);
+  dev_free(tb.tile_mask, s);
+  dev_free(tb.tile_off, s);
+  dev_free(tb.entries, s);
+  tb = TileBook();
+}
+
+static void rulebook_free(RuleBook *rb, cudaStream_t s) {
+  dev_free(rb->pairs, s);
+  dev_free(rb->t_out, s);
+  dev_free(rb->t_in, s);
+  dev_free(rb->dw_work, s);
+  tilebook_free(rb->tb_out, s);
+  tilebook_free(rb->tb_in, s);
+  delete rb;
+}
+
+static bool same3(const int64_t *a, const int64_t *b) {
+  return a[0] == b[0] && a[1] == b[1] && a[2] == b[2];
+}
+
+Grid *find_grid(scn_metadata *m, const int64_t *ss) {
+  for (Grid *g : m->grids)
+    if (same3(g->ss, ss)) return g;
+  return nullptr;
+}
+
+static void metadata_clear(scn_metadata *m, cudaStream_t s) {
+  for (Grid *g : m->grids) grid_free(g, s);
+  m->grids.clear();
+  for (RuleBook *rb : m->rulebooks) rulebook_free(rb, s);
+  m->rulebooks.clear();
+  dev_free(m->input.point_row, s);
+  dev_free(m->input.csr_off, s);
+  dev_free(m->input.members, s);
+  dev_free(m->input.stat, s);
+  m->input = InputRules();
+  m->batch_size = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// input layer (IOLayersRules.h:19-125)
+// ---------------------------------------------------------------------------------------
+// stat[0] error flag, stat[1] max batch index, stat[2] "batch column not ascending"
+__global__ void k_in_insert(const int64_t *__restrict__ coords, long long n, int ncols,
+                            uint64_t *hk, int32_t *hv, uint32_t mask, int32_t *pslot,
+                            int32_t *stat, int take_max) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t *c = coords + i * ncols;
+  const long long x = c[0], y = c[1], z = c[2], b = (ncols == 4) ? c[3] : 0;
+  if (x < 0 || y < 0 || z < 0 || x > 65535 || y > 65535 || z > 65535 || b < 0 || b > 32767) {
+    atomicOr(&stat[0], 1);
+    pslot[i] = 0;
+    return;
+  }
+  if (ncols == 4) {
+    atomicMax(&stat[1], (int)b);
+    if (i > 0 && coords[(i - 1) * ncols + 3] > b) atomicOr(&stat[2], 1);
+  }
+  const uint32_t slot = hash_insert(hk, mask, pack_key((int)x, (int)y, (int)z, (int)b));
+  pslot[i] = (int32_t)slot;
+  if (take_max) atomicMax(&hv[slot], (int)i);
+  else atomicMin(&hv[slot], (int)i);
+}
+
+__global__ void k_in_flag(const int32_t *__restrict__ pslot, const int32_t *__restrict__ hv,
+                          int32_t *__restrict__ flag, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (hv[pslot[i]] == (int)i) ? 1 : 0;
+}
+
+// first occurrences take their rank as site id, publish coordinates, and relabel the table
+__global__ void k_in_assign(const int64_t *__restrict__ coords, long long n, int ncols,
+                            const int32_t *__restrict__ rank, const int32_t *__restrict__ pslot,
+                            int32_t *hv, int32_t *__restrict__ site_coords) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = rank[i];
+  if (rank[i + 1] == r) return;  // not a first occurrence
+  const int64_t *c = coords + i * ncols;
+  int4 v = make_int4((int)c[0], (int)c[1], (int)c[2], ncols == 4 ? (int)c[3] : 0);
+  reinterpret_cast<int4 *>(site_coords)[r] = v;
+  hv[pslot[i]] = r;
+}
+
+__global__ void k_in_rows(const int32_t *__restrict__ pslot, const int32_t *__restrict__ hv,
+                          int32_t *__restrict__ prow, int32_t *cnt, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = hv[pslot[i]];
+  prow[i] = r;
+  atomicAdd(&cnt[r], 1);
+}
+
+__global__ void k_in_fill(const int32_t *__restrict__ prow, const int32_t *__restrict__ csr_off,
+                          int32_t *cursor, int32_t *__restrict__ members, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = prow[i];
+  const int pos = atomicAdd(&cursor[r], 1);
+  members[csr_off[r] + pos] = (int)i;
+}
+
+// point lists come out of the atomics in arbitrary order; the reference lists them in
+// ascending point order (IOLayersRules.h:92) - restore that (lists are 1-3 long in practice)
+__global__ void k_in_sort_members(const int32_t *__restrict__ csr_off, int32_t *members,
+                                  long long n_rows, int32_t *max_active) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int b = csr_off[r], e = csr_off[r + 1];
+  for (int i = b + 1; i < e; ++i) {
+    const int v = members[i];
+    int j = i - 1;
+    while (j >= b && members[j] > v) { members[j + 1] = members[j]; --j; }
+    members[j + 1] = v;
+  }
+  if (e - b > 1) atomicMax(max_active, e - b);
+}
+
+__global__ void k_iota(int32_t *a, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int)i;
+}
+
+__global__ void k_in_mode0(const int64_t *__restrict__ coords, long long n, int ncols,
+                           int32_t *__restrict__ site_coords) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t *c = coords + i * ncols;
+  reinterpret_cast<int4 *>(site_coords)[i] =
+      make_int4((int)c[0], (int)c[1], (int)c[2], ncols == 4 ? (int)c[3] : 0);
+}
+
+static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t *coords,
+                               int64_t n, int ncols, int on_device, int64_t batch_size,
+                               int mode, cudaStream_t s, int64_t *n_active_out) {
+  SCN_CHECK(m->dim == 3, "only dimension 3 is implemented (Metadata_3)");
+  SCN_CHECK(ncols == 3 || ncols == 4, "coords must have 3 or 4 columns, got %d", ncols);
+  SCN_CHECK(mode >= 0 && mode <= 4, "InputLayer mode %d not in 0..4", mode);
+  SCN_CHECK(n >= 0 && n < (1LL << 30), "too many input points: %lld", (long long)n);
+  metadata_clear(m, s);
+  m->last_stream = s;
+  Grid *g = new Grid();
+  memcpy(g->ss, ss, sizeof(g->ss));
+  m->grids.push_back(g);
+  InputRules &ir = m->input;
+  ir.mode = mode;
+  ir.n_points = n;
+  if (n == 0) {
+    SCN_TRY(grid_alloc_table(g, 0, 0x7F, s));
+    SCN_TRY(dev_alloc_t(&g->coords, 4, s));
+    SCN_TRY(dev_alloc_t(&ir.point_row, 1, s));
+    SCN_TRY(dev_alloc_t(&ir.csr_off, 1, s));
+    SCN_CUDA(cudaMemsetAsync(ir.csr_off, 0, 4, s));
+    SCN_TRY(dev_alloc_t(&ir.members, 1, s));
+    ir.built = true;
+    m->batch_size = batch_size;
+    *n_active_out = 0;
+    return 0;
+  }
+  const int64_t *dcoords = coords;
+  int64_t *staged = nullptr;
+  if (!on_device) {
+    SCN_TRY(dev_alloc_t(&staged, (size_t)n * ncols, s));
+    SCN_CUDA(cudaMemcpyAsync(staged, coords, (size_t)n * ncols * 8, cudaMemcpyHostToDevice, s));
+    dcoords = staged;
+  }
+  int32_t *pslot = nullptr, *stat = nullptr, *rank = nullptr;
+  SCN_TRY(dev_alloc_t(&pslot, (size_t)n, s));
+  SCN_TRY(dev_alloc_t(&stat, 8, s));
+  SCN_CUDA(cudaMemsetAsync(stat, 0, 32, s));
+  SCN_TRY(grid_alloc_table(g, n, mode == 0 ? 0x80 : 0x7F, s));
+  const int T = 256, nb = cdiv(n, T);
+  k_in_insert<<<nb, T, 0, s>>>(dcoords, n, ncols, g->hkeys, g->hvals, g->hcap - 1, pslot, stat,
+                               mode == 0);
+  SCN_LAUNCHED();
+  int64_t *hs = host_scratch(16);
+  SCN_CHECK(hs, "pinned host scratch allocation failed");
+  int32_t *hs32 = (int32_t *)hs;
+  if (mode == 0) {
+    // guaranteed-unique mode: rows are the points themselves (IOLayersRules.h:29-58)
+    SCN_CUDA(cudaMemcpyAsync(hs32, stat, 16, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaStreamSynchronize(s));
+    SCN_CHECK(hs32[0] == 0, "InputLayer: coordinate outside [0,65535] or batch outside [0,32767]");
+    g->n_active = n;
+    SCN_TRY(dev_alloc_t(&g->coords, (size_t)n * 4, s));
+    k_in_mode0<<<nb, T, 0, s>>>(dcoords, n, ncols, g->coords);
+    SCN_LAUNCHED();
+    SCN_TRY(dev_alloc_t(&ir.point_row, (size_t)n, s));
+    SCN_TRY(dev_alloc_t(&ir.members, (size_t)n, s));
+    SCN_TRY(dev_alloc_t(&ir.csr_off, (size_t)n + 1, s));
+    k_iota<<<nb, T, 0, s>>>(ir.point_row, n);
+    SCN_LAUNCHED();
+    k_iota<<<nb, T, 0, s>>>(ir.members, n);
+    SCN_LAUNCHED();
+    k_iota<<<cdiv(n + 1, T), T, 0, s>>>(ir.csr_off, n + 1);
+    SCN_LAUNCHED();
+    ir.n_active = n;
+    ir.max_active = 1;
+  } else {
+    SCN_TRY(dev_alloc_t(&rank, (size_t)n + 1, s));
+    k_in_flag<<<nb, T, 0, s>>>(pslot, g->hvals, rank, n);
+    SCN_LAUNCHED();
+    SCN_TRY(exclusive_scan_i32(rank, rank, n, s));
+    SCN_CUDA(cudaMemcpyAsync(hs32, stat, 16, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaMemcpyAsync(hs32 + 4, rank + n, 4, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaStreamSynchronize(s));  // the one documented read-back of this call
+    SCN_CHECK(hs32[0] == 0, "InputLayer: coordinate outside [0,65535] or batch outside [0,32767]");
+    const int64_t na = hs32[4];
+    g->n_active = na;
+    ir.n_active = na;
+    SCN_TRY(dev_alloc_t(&g->coords, (size_t)na * 4, s));
+    k_in_assign<<<nb, T, 0, s>>>(dcoords, n, ncols, rank, pslot, g->hvals, g->coords);
+    SCN_LAUNCHED();
+    int32_t *cnt = nullptr;
+    SCN_TRY(dev_alloc_t(&ir.point_row, (size_t)n, s));
+    SCN_TRY(dev_alloc_t(&ir.csr_off, (size_t)na + 1, s));
+    SCN_TRY(dev_alloc_t(&ir.members, (size_t)n, s));
+    SCN_TRY(dev_alloc_t(&cnt, (size_t)na + 2, s));
+    SCN_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)na + 2) * 4, s));
+    k_in_rows<<<nb, T, 0, s>>>(pslot, g->hvals, ir.point_row, cnt, n);
+    SCN_LAUNCHED();
+    SCN_TRY(exclusive_scan_i32(cnt, ir.csr_off, na, s));
+    SCN_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)na + 2) * 4, s));
+    k_in_fill<<<nb, T, 0, s>>>(ir.point_row, ir.csr_off, cnt, ir.members, n);
+    SCN_LAUNCHED();
+    int32_t *mx = cnt + na + 1;  // zeroed above, untouched by k_in_fill
+    k_in_sort_members<<<cdiv(na, T), T, 0, s>>>(ir.csr_off, ir.members, na, mx);
+    SCN_LAUNCHED();
+    SCN_CUDA(cudaMemcpyAsync(stat + 4, mx, 4, cudaMemcpyDeviceToDevice, s));
+    ir.max_active = -1;  // stat[4] on the device; fetched lazily (scn_input_rulebook_header)
+    dev_free(cnt, s);
+    dev_free(rank, s);
+  }
+  g->batch_sorted = (hs32[2] == 0);
+  const int64_t bs_seen = (ncols == 4) ? (int64_t)hs32[1] + 1 : 1;
+  m->batch_size = std::max<int64_t>(batch_size, bs_seen);
+  ir.built = true;
+  ir.stat = stat;  // owned by the InputRules from here on
+  dev_free(pslot, s);
+  dev_free(staged, s);
+  *n_active_out = g->n_active;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// rulebook tables
+// ---------------------------------------------------------------------------------------
+struct Filter3 { int size[3]; int stride[3]; int out_size[3]; };
+
+// T[k*n+s] = row of the site at coords(s)+delta_k, or -1 (SubmanifoldConvolutionRules.h:13-45)
+__global__ void k_sub_table(const int32_t *__restrict__ coords, long long n, Filter3 f, int K,
+                            const uint64_t *__restrict__ hk, const int32_t *__restrict__ hv,
+                            uint32_t mask, int32_t *__restrict__ T) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * K) return;
+  const int k = (int)(idx / n);
+  const long long s = idx - (long long)k * n;
+  const int4 c = reinterpret_cast<const int4 *>(coords)[s];
+  const int iz = k % f.size[2], iy = (k / f.size[2]) % f.size[1], ix = k / (f.size[2] * f.size[1]);
+  const int x = c.x + ix - f.size[0] / 2, y = c.y + iy - f.size[1] / 2, z = c.z + iz - f.size[2] / 2;
+  int r = -1;
+  if (x == c.x && y == c.y && z == c.z) r = (int)s;
+  else if (coord_ok(x, y, z)) r = hash_find(hk, hv, mask, pack_key(x, y, z, c.w));
+  T[idx] = r;
+}
+
+__global__ void k_flag_table(const int32_t *__restrict__ T, int32_t *__restrict__ flag,
+                             long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) flag[i] = T[i] >= 0 ? 1 : 0;
+}
+
+// meta[k] = first pair of offset k, meta[K] = total pairs
+__global__ void k_pair_offsets(const int32_t *__restrict__ pos, long long n, int K,
+                               int32_t *__restrict__ meta) {
+  int k = threadIdx.x;
+  if (k <= K) meta[k] = pos[(long long)k * n];
+}
+
+__global__ void k_emit_pairs(const int32_t *__restrict__ T, const int32_t *__restrict__ pos,
+                             long long n, long long total, int32_t *__restrict__ pairs) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int t = T[idx];
+  if (t < 0) return;
+  const int p = pos[idx];
+  reinterpret_cast<int2 *>(pairs)[p] = make_int2(t, (int)(idx % n));
+}
+
+// T_in[k*n_in + in] = out for every pair (each in row occurs at most once per offset)
+__global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t *__restrict__ poff,
+                               int K, long long n_in, int32_t *__restrict__ t_in) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= poff[K]) return;
+  int k = 0;
+  while (k + 1 < K && poff[k + 1] <= p) ++k;
+  const int2 pr = reinterpret_cast<const int2 *>(pairs)[p];
+  t_in[(long long)k * n_in + pr.x] = pr.y;
+}
+
+// ---------------------------------------------------------------------------------------
+// tile books
+// ---------------------------------------------------------------------------------------
+__global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
+                            uint32_t *__restrict__ mask, int32_t *__restrict__ idx) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  uint32_t m = 0;
+  for (int k = 0; k < K; ++k)
+    if (T[(long long)k * n + r] >= 0) m |= (1u << k);
+  mask[r] = m;
+  idx[r] = (int)r;
+}
+
+// one block per tile: pad the permutation, OR the row masks
+__global__ void __launch_bounds__(TILE_M)
+k_tile_masks(const uint32_t *__restrict__ sorted_mask, const int32_t *__restrict__ sorted_idx,
+             long long n, int32_t *__restrict__ perm, uint32_t *__restrict__ tile_mask,
+             int32_t *__restrict__ tile_pop) {
+  __shared__ uint32_t wm[TILE_M / 32];
+  const long long slot = (long long)blockIdx.x * TILE_M + threadIdx.x;
+  uint32_t m = 0;
+  int row = -1;
+  if (slot < n) { m = sorted_mask[slot]; row = sorted_idx[slot]; }
+  perm[slot] = row;
+  m = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t u = 0;
+#pragma unroll
+    for (int i = 0; i < TILE_M / 32; ++i) u |= wm[i];
+    tile_mask[blockIdx.x] = u;
+    tile_pop[blockIdx.x] = __popc(u);
+  }
+}
+
+__global__ void __launch_bounds__(TILE_M)
+k_fill_entries(const int32_t *__restrict__ T, long long n, const int32_t *__restrict__ perm,
+               const uint32_t *__restrict__ tile_mask, const int32_t *__restrict__ tile_off,
+               int32_t *__restrict__ entries) {
+  const int row = perm[(long long)blockIdx.x * TILE_M + threadIdx.x];
+  uint32_t m = tile_mask[blockIdx.x];
+  long long e = tile_off[blockIdx.x];
+  while (m) {
+    const int k = __ffs(m) - 1;
+    m &= m - 1;
+    entries[e * TILE_M + threadIdx.x] = row >= 0 ? T[(long long)k * n + row] : -1;
+    ++e;
+  }
+}
+
+// Phase 1 (no host knowledge needed): masks, grouping, per-tile offsets. meta_slot receives
+// the entry total.  Phase 2 after the read-back: allocate + fill the entry lists.
+static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows,
+                           int64_t n_partner, int32_t *meta_slot, cudaStream_t s) {
+  tb.K = K;
+  tb.n_rows = n_rows;
+  tb.n_partner = n_partner;
+  tb.n_tiles = cdiv(n_rows, TILE_M);
+  if (tb.n_tiles == 0) {
+    SCN_CUDA(cudaMemsetAsync(meta_slot, 0, 4, s));
+    return 0;
+  }
+  uint32_t *mask = nullptr;
+  int32_t *idx = nullptr, *pop = nullptr;
+  SCN_TRY(dev_alloc_t(&mask, (size_t)n_rows, s));
+  SCN_TRY(dev_alloc_t(&idx, (size_t)n_rows, s));
+  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, idx);
+  SCN_LAUNCHED();
+  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(mask, idx, n_rows, K, s));
+  SCN_TRY(dev_alloc_t(&tb.perm, (size_t)tb.n_tiles * TILE_M, s));
+  SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
+  SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
+  SCN_TRY(dev_alloc_t(&pop, (size_t)tb.n_tiles + 1, s));
+  k_tile_masks<<<tb.n_tiles, TILE_M, 0, s>>>(mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
+  SCN_LAUNCHED();
+  SCN_TRY(exclusive_scan_i32(pop, tb.tile_off, tb.n_tiles, s));
+  SCN_CUDA(cudaMemcpyAsync(meta_slot, tb.tile_off + tb.n_tiles, 4, cudaMemcpyDeviceToDevice, s));
+  dev_free(mask, s);
+  dev_free(idx, s);
+  dev_free(pop, s);
+  return 0;
+}
+
+static int tilebook_phase2(TileBook &tb, const int32_t *T, int64_t n_entries, cudaStream_t s) {
+  tb.n_entries = n_entries;
+  SCN_TRY(dev_alloc_t(&tb.entries, (size_t)n_entries * TILE_M, s));
+  if (tb.n_tiles > 0 && n_entries > 0) {
+    k_fill_entries<<<tb.n_tiles, TILE_M, 0, s>>>(T, tb.n_rows, tb.perm, tb.tile_mask, tb.tile_off,
+                                                 tb.entries);
+    SCN_LAUNCHED();
+  }
+  tb.built = true;
+  return 0;
+}
+
+// pairs + tb_out from t_out with a single read-back
+static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
+  const int K = rb->K;
+  const int64_t n = rb->n_out;
+  const long long total = (long long)K * n;
+  SCN_CHECK(total < (1LL << 31), "rulebook table too large (%lld entries)", total);
+  int32_t *pos = nullptr, *meta = nullptr;
+  SCN_TRY(dev_alloc_t(&pos, (size_t)total + 1, s));
+  SCN_TRY(dev_alloc_t(&meta, (size_t)K + 4, s));
+  if (total > 0) {
+    k_flag_table<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, total);
+    SCN_LAUNCHED();
+  }
+  SCN_TRY(exclusive_scan_i32(pos, pos, total, s));
+  k_pair_offsets<<<1, 64, 0, s>>>(pos, n, K, meta);
+  SCN_LAUNCHED();
+  SCN_TRY(tilebook_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s));
+  int64_t *hs = host_scratch(64);
+  int32_t *h32 = (int32_t *)hs;
+  SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)(K + 2) * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back: pair counts + entry total
+  for (int k = 0; k <= K; ++k) rb->pair_off[k] = h32[k];
+  for (int k = 0; k < K; ++k) rb->counts[k] = h32[k + 1] - h32[k];
+  rb->total_pairs = h32[K];
+  SCN_TRY(dev_alloc_t(&rb->pairs, (size_t)rb->total_pairs * 2, s));
+  if (total > 0) {
+    k_emit_pairs<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, n, total, rb->pairs);
+    SCN_LAUNCHED();
+  }
+  SCN_TRY(tilebook_phase2(rb->tb_out, rb->t_out, h32[K + 1], s));
+  dev_free(pos, s);
+  dev_free(meta, s);
+  return 0;
+}
+
+static int build_t_in(RuleBook *rb, cudaStream_t s) {
+  if (rb->t_in) return 0;
+  const long long total = (long long)rb->K * rb->n_in;
+  SCN_TRY(dev_alloc_t(&rb->t_in, (size_t)total, s));
+  SCN_CUDA(cudaMemsetAsync(rb->t_in, 0xFF, (size_t)(total ? total : 1) * 4, s));
+  if (rb->total_pairs > 0) {
+    int32_t *poff = nullptr;
+    SCN_TRY(dev_alloc_t(&poff, (size_t)rb->K + 1, s));
+    int32_t h[MAX_K + 1];
+    for (int k = 0; k <= rb->K; ++k) h[k] = (int32_t)rb->pair_off[k];
+    // pageable source: the copy is staged before return, so the stack array may die
+    SCN_CUDA(cudaMemcpyAsync(poff, h, (size_t)(rb->K + 1) * 4, cudaMemcpyHostToDevice, s));
+    k_scatter_t_in<<<cdiv(rb->total_pairs, 256), 256, 0, s>>>(rb->pairs, poff, rb->K, rb->n_in,
+                                                             rb->t_in);
+    SCN_LAUNCHED();
+    dev_free(poff, s);
+  }
+  return 0;
+}
+
+int ensure_tilebook(RuleBook *rb, bool stationary_out, cudaStream_t s) {
+  TileBook &tb = stationary_out ? rb->tb_out : rb->tb_in;
+  if (tb.built) return 0;
+  if (rb->identity) {
+    tb.identity = true;
+    tb.K = 1;
+    tb.n_rows = rb->n_out;
+    tb.n_partner = rb->n_in;
+    tb.n_tiles = cdiv(rb->n_out, TILE_M);
+    tb.built = true;
+    return 0;
+  }
+  SCN_CHECK(!stationary_out, "internal: tb_out must be built with the rulebook");
+  SCN_TRY(build_t_in(rb, s));
+  int32_t *meta = nullptr;
+  SCN_TRY(dev_alloc_t(&meta, 4, s));
+  SCN_TRY(tilebook_phase1(tb, rb->t_in, rb->K, rb->n_in, rb->n_out, meta, s));
+  int32_t *h32 = (int32_t *)host_scratch(16);
+  SCN_CUDA(cudaMemcpyAsync(h32, meta, 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back (first backward use only)
+  SCN_TRY(tilebook_phase2(tb, rb->t_in, h32[0], s));
+  dev_free(meta, s);
+  return 0;
+}
+
+int ensure_dw_work(RuleBook *rb, cudaStream_t s) {
+  if (rb->dw_work || rb->total_pairs == 0) return 0;
+  long long chunk = (rb->total_pairs + 4LL * num_sms() - 1) / (4LL * num_sms());
+  chunk = (chunk + 31) / 32 * 32;
+  chunk = std::min<long long>(std::max<long long>(chunk, 256), 8192);
+  std::vector<DwWork> w;
+  for (int k = 0; k < rb->K; ++k) {
+    int slot = 0;
+    for (long long st = 0; st < rb->counts[k]; st += chunk) {
+      DwWork d;
+      d.k = k;
+      d.start = (int32_t)(rb->pair_off[k] + st);
+      d.len = (int32_t)std::min<long long>(chunk, rb->counts[k] - st);
+      d.slot = slot++;
+      w.push_back(d);
+    }
+  }
+  rb->n_dw_work = (int)w.size();
+  rb->dw_chunk = (int)chunk;
+  SCN_TRY(dev_alloc_t(&rb->dw_work, w.size(), s));
+  SCN_CUDA(cudaMemcpyAsync(rb->dw_work, w.data(), w.size() * sizeof(DwWork),
+                           cudaMemcpyHostToDevice, s));
+  SCN_CUDA(cudaStreamSynchronize(s));  // host vector dies at return
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// submanifold rulebook
+// ---------------------------------------------------------------------------------------
+static RuleBook *find_rulebook(scn_metadata *m, int kind, const int64_t *in_ss,
+                               const int64_t *filter, const int64_t *stride) {
+  for (RuleBook *rb : m->rulebooks)
+    if (rb->kind == kind && same3(rb->in_ss, in_ss) && same3(rb->filter, filter) &&
+        (kind == 0 || same3(rb->stride, stride)))
+      return rb;
+  return nullptr;
+}
+
+int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *filter,
+                             cudaStream_t s, RuleBook **out) {
+  m->last_stream = s;
+  if (RuleBook *rb = find_rulebook(m, 0, ss, filter, nullptr)) { *out = rb; return 0; }
+  Grid *g = find_grid(m, ss);
+  SCN_CHECK(g, "no active sites at spatial size [%lld,%lld,%lld]", (long long)ss[0],
+            (long long)ss[1], (long long)ss[2]);
+  const int64_t K64 = filter[0] * filter[1] * filter[2];
+  SCN_CHECK(filter[0] > 0 && filter[1] > 0 && filter[2] > 0 && K64 <= MAX_K,
+            "filter volume %lld not in 1..%d", (long long)K64, MAX_K);
+  RuleBook *rb = new RuleBook();
+  rb->kind = 0;
+  memcpy(rb->in_ss, ss, 24); memcpy(rb->out_ss, ss, 24); memcpy(rb->filter, filter, 24);
+  rb->stride[0] = rb->stride[1] = rb->stride[2] = 1;
+  rb->K = (int)K64;
+  rb->n_in = rb->n_out = g->n_active;
+  memset(rb->counts, 0, sizeof(rb->counts));
+  memset(rb->pair_off, 0, sizeof(rb->pair_off));
+  m->rulebooks.push_back(rb);
+  if (rb->K == 1) {
+    // 1x1x1: pairs are (i,i); no hashing, no lists (the reference still probes, same result)
+    rb->identity = true;
+    rb->counts[0] = g->n_active;
+    rb->pair_off[1] = g->n_active;
+    rb->total_pairs = g->n_active;
+    SCN_TRY(ensure_tilebook(rb, true, s));
+    *out = rb;
+    return 0;
+  }
+  const long long total = (long long)rb->K * g->n_active;
+  SCN_CHECK(total < (1LL << 31), "submanifold table too large");
+  SCN_TRY(dev_alloc_t(&rb->t_out, (size_t)total, s));
+  if (total > 0) {
+    Filter3 f;
+    for (int d = 0; d < 3; ++d) { f.size[d] = (int)filter[d]; f.stride[d] = 1; f.out_size[d] = (int)ss[d]; }
+    k_sub_table<<<cdiv(total, 256), 256, 0, s>>>(g->coords, g->n_active, f, rb->K, g->hkeys,
+                                                 g->hvals, g->hcap - 1, rb->t_out);
+    SCN_LAUNCHED();
+  }
+  SCN_TRY(finish_rulebook(rb, s));
+  *out = rb;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// strided convolution rulebook + output grid (ConvolutionRules.h:12-105)
+// ---------------------------------------------------------------------------------------
+struct Region { int lb[3], cnt[3]; };
+__device__ __forceinline__ Region out_region(const int4 c, const Filter3 &f) {
+  Region r;
+  const int in[3] = {c.x, c.y, c.z};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // RectangularRegions.h:111-119 (C++ truncating division, computed in 64 bit)
+    long long lb = ((long long)in[d] - f.size[d] + f.stride[d]) / f.stride[d];
+    if (lb < 0) lb = 0;
+    long long ub = in[d] / f.stride[d];
+    if (ub > f.out_size[d] - 1) ub = f.out_size[d] - 1;
+    r.lb[d] = (int)lb;
+    r.cnt[d] = (int)(ub - lb + 1);
+  }
+  return r;
+}
+
+// jj enumerates the (at most R = Rx*Ry*Rz) output cells of input i, last dim fastest
+__device__ __forceinline__ bool region_cell(const Region &r, int jj, const int R3[3], int j[3]) {
+  const int jz = jj % R3[2], jy = (jj / R3[2]) % R3[1], jx = jj / (R3[2] * R3[1]);
+  if (jx >= r.cnt[0] || jy >= r.cnt[1] || jz >= r.cnt[2]) return false;
+  j[0] = r.lb[0] + jx; j[1] = r.lb[1] + jy; j[2] = r.lb[2] + jz;
+  return true;
+}
+
+struct R3s { int v[3]; };
+
+__global__ void k_conv_insert(const int32_t *__restrict__ coords, long long n_in, Filter3 f,
+                              R3s R3, int R, uint64_t *hk, int32_t *hv, uint32_t mask,
+                              int32_t *__restrict__ pslot) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_in * R) return;
+  const long long i = idx / R;
+  const int jj = (int)(idx - i * R);
+  const int4 c = reinterpret_cast<const int4 *>(coords)[i];
+  const Region r = out_region(c, f);
+  int j[3];
+  if (!region_cell(r, jj, R3.v, j)) { pslot[idx] = -1; return; }
+  const uint32_t slot = hash_insert(hk, mask, pack_key(j[0], j[1], j[2], c.w));
+  pslot[idx] = (int32_t)slot;
+  atomicMin(&hv[slot], (int)idx);
+}
+
+__global__ void k_conv_flag(const int32_t *__restrict__ pslot, const int32_t *__restrict__ hv,
+                            int32_t *__restrict__ flag, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int sl = pslot[idx];
+  flag[idx] = (sl >= 0 && hv[sl] == (int)idx) ? 1 : 0;
+}
+
+__global__ void k_conv_assign(const int32_t *__restrict__ coords, long long n_in, Filter3 f,
+                              R3s R3, int R, const int32_t *__restrict__ rank,
+                              const int32_t *__restrict__ pslot, int32_t *hv,
+                              int32_t *__restrict__ out_coords) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_in * R) return;
+  const int r0 = rank[idx];
+  if (rank[idx + 1] == r0) return;
+  const long long i = idx / R;
+  const int jj = (int)(idx - i * R);
+  const int4 c = reinterpret_cast<const int4 *>(coords)[i];
+  const Region r = out_region(c, f);
+  int j[3];
+  region_cell(r, jj, R3.v, j);
+  reinterpret_cast<int4 *>(out_coords)[r0] = make_int4(j[0], j[1], j[2], c.w);
+  hv[pslot[idx]] = r0;
+}
+
+// relabel rows by a permutation new_of_old (batch-contiguity fix-up)
+__global__ void k_relabel_table(int32_t *hv, uint32_t cap, const uint64_t *__restrict__ hk,
+                                const int32_t *__restrict__ new_of_old) {
+  uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl < cap && hk[sl] != EMPTY_KEY) hv[sl] = new_of_old[hv[sl]];
+}
+__global__ void k_batch_keys(const int32_t *__restrict__ coords, long long n,
+                             uint32_t *__restrict__ key, int32_t *__restrict__ idx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = (uint32_t)coords[i * 4 + 3];
+  idx[i] = (int)i;
+}
+__global__ void k_permute_coords(const int32_t *__restrict__ src, const int32_t *__restrict__ old_of_new,
+                                 int32_t *__restrict__ dst, int32_t *__restrict__ new_of_old,
+                                 long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = old_of_new[i];
+  reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(src)[o];
+  new_of_old[o] = (int)i;
+}
+
+__global__ void k_conv_tables(const int32_t *__restrict__ coords, long long n_in, long long n_out,
+                              Filter3 f, R3s R3, int R, const int32_t *__restrict__ pslot,
+                              const int32_t *__restrict__ hv, int32_t *__restrict__ t_out,
+                              int32_t *__restrict__ t_in) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_in * R) return;
+  const int sl = pslot[idx];
+  if (sl < 0) return;
+  const long long i = idx / R;
+  const int jj = (int)(idx - i * R);
+  const int4 c = reinterpret_cast<const int4 *>(coords)[i];
+  const Region r = out_region(c, f);
+  int j[3];
+  region_cell(r, jj, R3.v, j);
+  // offset of the input inside the output's window (RectangularRegions.h:31-38)
+  const int ox = c.x - j[0] * f.stride[0], oy = c.y - j[1] * f.stride[1], oz = c.z - j[2] * f.stride[2];
+  const int k = (ox * f.size[1] + oy) * f.size[2] + oz;
+  const int o = hv[sl];
+  t_out[(long long)k * n_out + o] = (int)i;
+  t_in[(long long)k * n_in + i] = o;
+}
+
+int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_ss,
+                      const int64_t *filter, const int64_t *stride, cudaStream_t s,
+                      RuleBook **out) {
+  m->last_stream = s;
+  if (RuleBook *rb = find_rulebook(m, 1, in_ss, filter, stride)) { *out = rb; return 0; }
+  Grid *gi = find_grid(m, in_ss);
+  SCN_CHECK(gi, "no active sites at spatial size [%lld,%lld,%lld]", (long long)in_ss[0],
+            (long long)in_ss[1], (long long)in_ss[2]);
+  const int64_t K64 = filter[0] * filter[1] * filter[2];
+  SCN_CHECK(K64 >= 1 && K64 <= MAX_K, "filter volume %lld not in 1..%d", (long long)K64, MAX_K);
+  Filter3 f;
+  R3s R3;
+  int R = 1;
+  for (int d = 0; d < 3; ++d) {
+    SCN_CHECK(filter[d] > 0 && stride[d] > 0 && out_ss[d] > 0, "bad filter/stride/output size");
+    f.size[d] = (int)filter[d]; f.stride[d] = (int)stride[d]; f.out_size[d] = (int)out_ss[d];
+    R3.v[d] = (int)((filter[d] + stride[d] - 1) / stride[d]);
+    R *= R3.v[d];
+  }
+  const int64_t n_in = gi->n_active;
+  const long long total = (long long)n_in * R;
+  SCN_CHECK(total < (1LL << 30), "strided rulebook too large");
+  // (re)create the output grid (ConvolutionRules.h:66-70 clears it)
+  for (size_t i = 0; i < m->grids.size(); ++i)
+    if (same3(m->grids[i]->ss, out_ss) && m->grids[i] != gi) {
+      grid_free(m->grids[i], s);
+      m->grids.erase(m->grids.begin() + i);
+      break;
+    }
+  SCN_CHECK(!same3(in_ss, out_ss), "convolution input and output spatial sizes coincide");
+  Grid *go = new Grid();
+  memcpy(go->ss, out_ss, 24);
+  m->grids.push_back(go);
+  RuleBook *rb = new RuleBook();
+  rb->kind = 1;
+  memcpy(rb->in_ss, in_ss, 24); memcpy(rb->out_ss, out_ss, 24);
+  memcpy(rb->filter, filter, 24); memcpy(rb->stride, stride, 24);
+  rb->K = (int)K64;
+  rb->n_in = n_in;
+  memset(rb->counts, 0, sizeof(rb->counts));
+  memset(rb->pair_off, 0, sizeof(rb->pair_off));
+  m->rulebooks.push_back(rb);
+
+  SCN_TRY(grid_alloc_table(go, total, 0x7F, s));
+  int32_t *pslot = nullptr, *rank = nullptr;
+  SCN_TRY(dev_alloc_t(&pslot, (size_t)total, s));
+  SCN_TRY(dev_alloc_t(&rank, (size_t)total + 1, s));
+  int64_t n_out = 0;
+  if (total > 0) {
+    k_conv_insert<<<cdiv(total, 256), 256, 0, s>>>(gi->coords, n_in, f, R3, R, go->hkeys,
+                                                   go->hvals, go->hcap - 1, pslot);
+    SCN_LAUNCHED();
+    k_conv_flag<<<cdiv(total, 256), 256, 0, s>>>(pslot, go->hvals, rank, total);
+    SCN_LAUNCHED();
+    SCN_TRY(exclusive_scan_i32(rank, rank, total, s));
+    int32_t *h32 = (int32_t *)host_scratch(16);
+    SCN_CUDA(cudaMemcpyAsync(h32, rank + total, 4, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back: nActive of the new scale
+    n_out = h32[0];
+  }
+  go->n_active = n_out;
+  rb->n_out = n_out;
+  SCN_TRY(dev_alloc_t(&go->coords, (size_t)n_out * 4, s));
+  if (total > 0) {
+    k_conv_assign<<<cdiv(total, 256), 256, 0, s>>>(gi->coords, n_in, f, R3, R, rank, pslot,
+                                                   go->hvals, go->coords);
+    SCN_LAUNCHED();
+  }
+  if (!gi->batch_sorted && n_out > 1) {
+    // input rows interleave samples: stable-sort the new sites by sample index so that this
+    // scale is batch-contiguous ascending, as the reference's per-sample loop guarantees
+    uint32_t *bk = nullptr;
+    int32_t *old_of_new = nullptr, *new_of_old = nullptr, *c2 = nullptr;
+    SCN_TRY(dev_alloc_t(&bk, (size_t)n_out, s));
+    SCN_TRY(dev_alloc_t(&old_of_new, (size_t)n_out, s));
+    SCN_TRY(dev_alloc_t(&new_of_old, (size_t)n_out, s));
+    SCN_TRY(dev_alloc_t(&c2, (size_t)n_out * 4, s));
+    k_batch_keys<<<cdiv(n_out, 256), 256, 0, s>>>(go->coords, n_out, bk, old_of_new);
+    SCN_LAUNCHED();
+    SCN_TRY(radix_sort_pairs(bk, old_of_new, n_out, 16, s));
+    k_permute_coords<<<cdiv(n_out, 256), 256, 0, s>>>(go->coords, old_of_new, c2, new_of_old, n_out);
+    SCN_LAUNCHED();
+    k_relabel_table<<<cdiv(go->hcap, 256), 256, 0, s>>>(go->hvals, go->hcap, go->hkeys, new_of_old);
+    SCN_LAUNCHED();
+    dev_free(go->coords, s);
+    go->coords = c2;
+    dev_free(bk, s);
+    dev_free(old_of_new, s);
+    dev_free(new_of_old, s);
+  }
+  go->batch_sorted = true;
+  const long long t_out_n = (long long)rb->K * n_out, t_in_n = (long long)rb->K * n_in;
+  SCN_TRY(dev_alloc_t(&rb->t_out, (size_t)t_out_n, s));
+  SCN_TRY(dev_alloc_t(&rb->t_in, (size_t)t_in_n, s));
+  SCN_CUDA(cudaMemsetAsync(rb->t_out, 0xFF, (size_t)(t_out_n ? t_out_n : 1) * 4, s));
+  SCN_CUDA(cudaMemsetAsync(rb->t_in, 0xFF, (size_t)(t_in_n ? t_in_n : 1) * 4, s));
+  if (total > 0) {
+    k_conv_tables<<<cdiv(total, 256), 256, 0, s>>>(gi->coords, n_in, n_out, f, R3, R, pslot,
+                                                   go->hvals, rb->t_out, rb->t_in);
+    SCN_LAUNCHED();
+  }
+  dev_free(pslot, s);
+  dev_free(rank, s);
+  SCN_TRY(finish_rulebook(rb, s));
+  *out = rb;
+  return 0;
+}
+
+}  // namespace scn
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace scn;
+
+extern "C" {
+
+int scn_set_tile_grouping(int enabled) {
+  g_tile_grouping = enabled != 0;
+  return 0;
+}
+
+int scn_metadata_create(int dimension, scn_metadata_t **out) {
+  SCN_CHECK(out, "null output pointer");
+  SCN_CHECK(dimension == 3, "only Metadata_3 (dimension 3) is implemented, got %d", dimension);
+  *out = new scn_metadata();
+  (*out)->dim = dimension;
+  return 0;
+}
+
+void scn_metadata_destroy(scn_metadata_t *m) {
+  if (!m) return;
+  metadata_clear(m, m->last_stream);
+  delete m;
+}
+
+int scn_metadata_clear(scn_metadata_t *m, void *stream) {
+  SCN_CHECK(m, "null metadata");
+  metadata_clear(m, (cudaStream_t)stream);
+  return 0;
+}
+
+int scn_get_nactive(scn_metadata_t *m, const int64_t *ss, int64_t *n_active) {
+  SCN_CHECK(m && ss && n_active, "null argument");
+  Grid *g = find_grid(m, ss);
+  *n_active = g ? g->n_active : -1;
+  return 0;
+}
+
+int scn_get_batch_size(scn_metadata_t *m, int64_t *batch_size) {
+  SCN_CHECK(m && batch_size, "null argument");
+  *batch_size = m->batch_size;
+  return 0;
+}
+
+int scn_get_spatial_locations_device(scn_metadata_t *m, const int64_t *ss, int32_t *out_dev,
+                                     void *stream) {
+  SCN_CHECK(m && ss, "null argument");
+  Grid *g = find_grid(m, ss);
+  SCN_CHECK(g, "no active sites at that spatial size");
+  if (g->n_active)
+    SCN_CUDA(cudaMemcpyAsync(out_dev, g->coords, (size_t)g->n_active * 16,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int scn_get_spatial_locations(scn_metadata_t *m, const int64_t *ss, int64_t *out_host,
+                              void *stream) {
+  SCN_CHECK(m && ss, "null argument");
+  Grid *g = find_grid(m, ss);
+  SCN_CHECK(g, "no active sites at that spatial size");
+  if (g->n_active == 0) return 0;
+  std::vector<int32_t> tmp((size_t)g->n_active * 4);
+  SCN_CUDA(cudaMemcpyAsync(tmp.data(), g->coords, tmp.size() * 4, cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  SCN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (size_t i = 0; i < tmp.size(); ++i) out_host[i] = tmp[i];
+  return 0;
+}
+
+int scn_input_layer_prepare(scn_metadata_t *m, const int64_t *spatial_size, const int64_t *coords,
+                            int64_t n_points, int n_cols, int coords_on_device,
+                            int64_t batch_size, int mode, void *stream, int64_t *n_active) {
+  SCN_CHECK(m && spatial_size && n_active && (coords || n_points == 0), "null argument");
+  return input_layer_prepare(m, spatial_size, coords, n_points, n_cols, coords_on_device,
+                             batch_size, mode, (cudaStream_t)stream, n_active);
+}
+
+int scn_input_rulebook_header(scn_metadata_t *m, int64_t header[4], void *stream) {
+  SCN_CHECK(m && m->input.built, "input layer not prepared");
+  InputRules &ir = m->input;
+  if (ir.max_active < 0) {
+    int32_t *h32 = (int32_t *)host_scratch(16);
+    SCN_CUDA(cudaMemcpyAsync(h32, ir.stat + 4, 4, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    SCN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    ir.max_active = std::max(1, h32[0]);
+    if (ir.mode == 1 || ir.mode == 2) ir.max_active = 1;
+  }
+  header[0] = ir.mode;
+  header[1] = ir.n_points ? ir.max_active : 0;
+  header[2] = ir.n_points;
+  header[3] = ir.n_active;
+  return 0;
+}
+
+int scn_input_rulebook_copy(scn_metadata_t *m, int32_t *out_host, void *stream) {
+  int64_t hd[4];
+  SCN_TRY(scn_input_rulebook_header(m, hd, stream));
+  InputRules &ir = m->input;
+  if (ir.mode == 0 || ir.n_active == 0) return 0;
+  std::vector<int32_t> off((size_t)ir.n_active + 1), mem((size_t)ir.n_points);
+  cudaStream_t s = (cudaStream_t)stream;
+  SCN_CUDA(cudaMemcpyAsync(off.data(), ir.csr_off, off.size() * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaMemcpyAsync(mem.data(), ir.members, mem.size() * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  const int64_t w = 1 + hd[1];
+  memset(out_host, 0, (size_t)(ir.n_active * w) * 4);
+  for (int64_t r = 0; r < ir.n_active; ++r) {
+    int32_t *row = out_host + r * w;
+    const int b = off[r], e = off[r + 1];
+    if (ir.mode == 1) { row[0] = 1; row[1] = mem[b]; }          // IOLayersRules.h:100-105 front()
+    else if (ir.mode == 2) { row[0] = 1; row[1] = mem[e - 1]; }  // :106-111 back()
+    else { row[0] = e - b; for (int i = b; i < e; ++i) row[1 + i - b] = mem[i]; }
+  }
+  return 0;
+}
+
+int scn_submanifold_rulebook_prepare(scn_metadata_t *m, const int64_t *ss, const int64_t *filter,
+                                     void *stream, int64_t *counts_host) {
+  SCN_CHECK(m && ss && filter, "null argument");
+  RuleBook *rb = nullptr;
+  SCN_TRY(get_submanifold_rulebook(m, ss, filter, (cudaStream_t)stream, &rb));
+  if (counts_host)
+    for (int k = 0; k < rb->K; ++k) counts_host[k] = rb->counts[k];
+  return 0;
+}
+
+int scn_conv_rulebook_prepare(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
+                              const int64_t *filter, const int64_t *stride, void *stream,
+                              int64_t *n_out_active, int64_t *counts_host) {
+  SCN_CHECK(m && in_ss && out_ss && filter && stride, "null argument");
+  RuleBook *rb = nullptr;
+  SCN_TRY(get_conv_rulebook(m, in_ss, out_ss, filter, stride, (cudaStream_t)stream, &rb));
+  if (n_out_active) *n_out_active = rb->n_out;
+  if (counts_host)
+    for (int k = 0; k < rb->K; ++k) counts_host[k] = rb->counts[k];
+  return 0;
+}
+
+static int copy_pairs(RuleBook *rb, int64_t offset, int32_t *pairs_host, cudaStream_t s) {
+  SCN_CHECK(offset >= 0 && offset < rb->K, "offset %lld outside filter volume %d",
+            (long long)offset, rb->K);
+  const int64_t c = rb->counts[offset];
+  if (c == 0) return 0;
+  if (rb->identity) {
+    for (int64_t i = 0; i < c; ++i) { pairs_host[2 * i] = (int32_t)i; pairs_host[2 * i + 1] = (int32_t)i; }
+    return 0;
+  }
+  SCN_CUDA(cudaMemcpyAsync(pairs_host, rb->pairs + 2 * rb->pair_off[offset], (size_t)c * 8,
+                           cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int scn_submanifold_rulebook_copy(scn_metadata_t *m, const int64_t *ss, const int64_t *filter,
+                                  int64_t offset, int32_t *pairs_host, void *stream) {
+  RuleBook *rb = nullptr;
+  SCN_TRY(get_submanifold_rulebook(m, ss, filter, (cudaStream_t)stream, &rb));
+  return copy_pairs(rb, offset, pairs_host, (cudaStream_t)stream);
+}
+
+int scn_conv_rulebook_copy(scn_metadata_t *m, const int64_t *in_ss, const int64_t *filter,
+                           const int64_t *stride, int64_t offset, int32_t *pairs_host,
+                           void *stream) {
+  RuleBook *rb = find_rulebook(m, 1, in_ss, filter, stride);
+  SCN_CHECK(rb, "convolution rulebook has not been prepared");
+  return copy_pairs(rb, offset, pairs_host, (cudaStream_t)stream);
+}
+
+int scn_sparse_to_dense_rules_copy(scn_metadata_t *m, const int64_t *ss, int32_t *rules_host,
+                                   int32_t *sample_host, void *stream) {
+  Grid *g = find_grid(m, ss);
+  SCN_CHECK(g, "no active sites at that spatial size");
+  if (g->n_active == 0) return 0;
+  std::vector<int32_t> c((size_t)g->n_active * 4);
+  SCN_CUDA(cudaMemcpyAsync(c.data(), g->coords, c.size() * 4, cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  SCN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int64_t r = 0; r < g->n_active; ++r) {
+    rules_host[2 * r] = (int32_t)r;
+    rules_host[2 * r + 1] = (int32_t)((c[4 * r] * ss[1] + c[4 * r + 1]) * ss[2] + c[4 * r + 2]);
+    sample_host[r] = c[4 * r + 3];
+  }
+  return 0;
+}
+
+int scn_rulebook_stats(scn_metadata_t *m, int kind, const int64_t *in_ss, const int64_t *filter,
+                       const int64_t *stride, int64_t stats[3]) {
+  SCN_CHECK(m && in_ss && filter && stats, "null argument");
+  RuleBook *rb = find_rulebook(m, kind == 0 ? 0 : 1, in_ss, filter, stride);
+  SCN_CHECK(rb, "rulebook not prepared");
+  const bool out_side = (kind == 0 || kind == 1 || kind == 4);
+  TileBook &tb = out_side ? rb->tb_out : rb->tb_in;
+  SCN_CHECK(tb.built, "tile book not built yet");
+  stats[0] = rb->total_pairs;
+  stats[1] = tb.identity ? (int64_t)tb.n_tiles * TILE_M : tb.n_entries * TILE_M;
+  stats[2] = tb.n_tiles;
+  return 0;
+}
+
+}  // extern "C"

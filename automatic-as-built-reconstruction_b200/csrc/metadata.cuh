@@ -1,0 +1,92 @@
+// metadata.cuh - device-resident Metadata<3>: per-scale hash grids, rulebooks, tile books.
+// Mirrors the role of SparseConvNet/sparseconvnet/SCN/Metadata/Metadata.h:44-163, but every
+// grid, rulebook and gather list lives in HBM; the host object only owns pointers and counts.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace scn {
+
+constexpr int TILE_M = 128;       // output rows per gather-GEMM tile
+constexpr int MAX_K = 32;         // filter volume limit (tile masks are 32-bit)
+constexpr uint64_t EMPTY_KEY = ~0ULL;
+
+struct Grid {                     // one spatial scale (Metadata.h:28-34 SparseGrids)
+  int64_t ss[3] = {0, 0, 0};
+  int64_t n_active = 0;
+  int32_t *coords = nullptr;      // [n_active,4] x,y,z,batch
+  uint64_t *hkeys = nullptr;      // open-addressing table: packed key
+  int32_t *hvals = nullptr;       //                        site row
+  uint32_t hcap = 0;              // power of two
+  bool batch_sorted = true;       // rows are batch-contiguous ascending
+};
+
+// Output-stationary gather lists: tiles of TILE_M "stationary" rows; for every kernel offset
+// active in the tile, TILE_M partner rows (-1 = none).
+struct TileBook {
+  bool built = false;
+  bool identity = false;          // 1x1x1 filter: partner(row) = row, no lists kept
+  int K = 0;
+  int64_t n_rows = 0;             // stationary rows
+  int64_t n_partner = 0;          // rows of the gathered side
+  int n_tiles = 0;
+  int64_t n_entries = 0;
+  int32_t *perm = nullptr;        // [n_tiles*TILE_M] stationary row per slot (-1 pad)
+  uint32_t *tile_mask = nullptr;  // [n_tiles] union of active offsets
+  int32_t *tile_off = nullptr;    // [n_tiles+1] first entry of the tile
+  int32_t *entries = nullptr;     // [n_entries*TILE_M] partner rows
+};
+
+struct DwWork { int32_t k, start, len, slot; };  // one partial-dW work item
+
+struct RuleBook {                 // Metadata.h:35 RuleBook + its derived gather lists
+  int kind = 0;                   // 0 submanifold, 1 strided convolution
+  int64_t in_ss[3], out_ss[3], filter[3], stride[3];
+  int K = 0;
+  int64_t n_in = 0, n_out = 0;
+  bool identity = false;
+  int64_t counts[MAX_K];          // pairs per offset
+  int64_t pair_off[MAX_K + 1];    // host copy of the prefix
+  int64_t total_pairs = 0;
+  int32_t *pairs = nullptr;       // [total_pairs,2] (in,out), offsets contiguous, sorted by out
+  int32_t *t_out = nullptr;       // [K,n_out] in-row feeding out-row at offset k (-1 none)
+  int32_t *t_in = nullptr;        // [K,n_in]  out-row fed by in-row at offset k (-1 none)
+  TileBook tb_out;                // stationary = out rows, gathers in rows
+  TileBook tb_in;                 // stationary = in rows, gathers out rows
+  DwWork *dw_work = nullptr;      // device work list for the weight gradient
+  int n_dw_work = 0;
+  int dw_chunk = 0;
+};
+
+struct InputRules {               // IOLayersRules.h:10-15, kept as CSR instead of a padded table
+  bool built = false;
+  int mode = 0;
+  int64_t n_points = 0, n_active = 0, max_active = 0;
+  int32_t *point_row = nullptr;   // [n_points] site of each point
+  int32_t *csr_off = nullptr;     // [n_active+1]
+  int32_t *members = nullptr;     // [n_points] point ids grouped by site, ascending
+  int32_t *stat = nullptr;        // device ints: [0] error [1] max batch [2] unsorted [4] maxActive
+};
+
+}  // namespace scn
+
+struct scn_metadata {
+  int dim = 3;
+  std::vector<scn::Grid *> grids;
+  std::vector<scn::RuleBook *> rulebooks;
+  scn::InputRules input;
+  int64_t batch_size = 0;
+  cudaStream_t last_stream = 0;
+};
+
+namespace scn {
+Grid *find_grid(scn_metadata *m, const int64_t *ss);
+int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *filter,
+                             cudaStream_t s, RuleBook **out);
+int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_ss,
+                      const int64_t *filter, const int64_t *stride, cudaStream_t s,
+                      RuleBook **out);
+// make sure tb_out / tb_in exists (tb_in builds t_in lazily for submanifold rulebooks)
+int ensure_tilebook(RuleBook *rb, bool stationary_out, cudaStream_t s);
+int ensure_dw_work(RuleBook *rb, cudaStream_t s);
+}  // namespace scn

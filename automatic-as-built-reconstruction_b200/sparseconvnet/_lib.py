@@ -1,0 +1,136 @@
+"""ctypes binding of libscn_b200.so (the C-ABI in include/scn_b200.h).
+
+The product path is CUDA only: if the shared library is missing this module raises at import
+time - there is no CPU or eager-PyTorch fallback behind it.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8,
+                    c_void_p)
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libscn_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "sparseconvnet (B200): %s not found. Build it with "
+        "`python __graft_entry__.py build` (or csrc/build.sh); there is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+PRECISIONS = {"fp32": 0, "bf16": 1, "tf32x3": 2}
+_precision = PRECISIONS[os.environ.get("SCN_B200_PRECISION", "fp32")]
+
+
+def set_conv_precision(name):
+    """'fp32' (exact FFMA, parity mode), 'bf16' or 'tf32x3' (tcgen05 tensor cores)."""
+    global _precision
+    _precision = PRECISIONS[name]
+
+
+def get_conv_precision():
+    return {v: k for k, v in PRECISIONS.items()}[_precision]
+
+
+def precision():
+    return _precision
+
+
+I64P = POINTER(c_int64)
+_sig = {
+    "scn_last_error": (c_char_p, []),
+    "scn_version": (c_int, []),
+    "scn_n_rulebook_bits": (c_int, []),
+    "scn_metadata_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "scn_metadata_destroy": (None, [c_void_p]),
+    "scn_metadata_clear": (c_int, [c_void_p, c_void_p]),
+    "scn_get_nactive": (c_int, [c_void_p, I64P, I64P]),
+    "scn_get_batch_size": (c_int, [c_void_p, I64P]),
+    "scn_get_spatial_locations": (c_int, [c_void_p, I64P, c_void_p, c_void_p]),
+    "scn_get_spatial_locations_device": (c_int, [c_void_p, I64P, c_void_p, c_void_p]),
+    "scn_quantize_points": (c_int, [c_void_p, c_int64, c_double, I64P, c_int64, c_void_p, c_void_p,
+                                    I64P, c_void_p]),
+    "scn_input_layer_prepare": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_int, c_int, c_int64,
+                                        c_int, c_void_p, I64P]),
+    "scn_input_layer_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "scn_input_layer_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "scn_output_layer_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "scn_output_layer_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "scn_input_rulebook_header": (c_int, [c_void_p, I64P, c_void_p]),
+    "scn_input_rulebook_copy": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "scn_submanifold_rulebook_prepare": (c_int, [c_void_p, I64P, I64P, c_void_p, I64P]),
+    "scn_conv_rulebook_prepare": (c_int, [c_void_p, I64P, I64P, I64P, I64P, c_void_p, I64P, I64P]),
+    "scn_submanifold_rulebook_copy": (c_int, [c_void_p, I64P, I64P, c_int64, c_void_p, c_void_p]),
+    "scn_conv_rulebook_copy": (c_int, [c_void_p, I64P, I64P, I64P, c_int64, c_void_p, c_void_p]),
+    "scn_sparse_to_dense_rules_copy": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_void_p]),
+    "scn_submanifold_conv_forward": (c_int, [c_void_p, I64P, I64P, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_int64, c_int64, c_int, c_void_p,
+                                             POINTER(c_double)]),
+    "scn_submanifold_conv_backward": (c_int, [c_void_p, I64P, I64P, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                              c_void_p]),
+    "scn_nin_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                c_int, c_void_p, POINTER(c_double)]),
+    "scn_nin_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "scn_batchnorm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_float, c_float, c_int, c_float, c_int64,
+                                      c_int64, c_void_p]),
+    "scn_batchnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64,
+                                       c_void_p]),
+    "scn_sparse_to_dense_forward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
+                                            c_void_p]),
+    "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
+                                             c_void_p]),
+    "scn_scale_inplace": (c_int, [c_void_p, c_float, c_int64, c_void_p]),
+    "scn_launch_count": (c_int64, []),
+    "scn_rulebook_stats": (c_int, [c_void_p, c_int, I64P, I64P, I64P, I64P]),
+    "scn_set_tile_grouping": (c_int, [c_int]),
+}
+for _name in ("scn_conv_forward", "scn_deconv_forward"):
+    _sig[_name] = (c_int, [c_void_p, I64P, I64P, I64P, I64P, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_int64, c_int64, c_int, c_void_p, POINTER(c_double)])
+for _name in ("scn_conv_backward", "scn_deconv_backward"):
+    _sig[_name] = (c_int, [c_void_p, I64P, I64P, I64P, I64P, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p])
+
+EXPORTS = sorted(_sig)
+for _name, (_res, _args) in _sig.items():
+    _f = getattr(lib, _name)  # AttributeError here = header / library mismatch
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("libscn_b200: " + lib.scn_last_error().decode("utf-8", "replace"))
+
+
+def i64x3(t):
+    """torch LongTensor / list of 3 ints -> ctypes int64[3]"""
+    if isinstance(t, torch.Tensor):
+        t = t.tolist()
+    return (c_int64 * 3)(int(t[0]), int(t[1]), int(t[2]))
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """device/host pointer of an optional tensor (None or empty -> NULL)"""
+    if t is None or t.numel() == 0:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def require_cuda_f32(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("sparseconvnet (B200): %s must be a CUDA tensor - this build has no "
+                           "CPU path (got device %s)" % (what, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError("sparseconvnet (B200): %s must be float32, got %s" % (what, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()

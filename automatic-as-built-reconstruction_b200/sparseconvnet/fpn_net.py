@@ -1,0 +1,124 @@
+"""FPN_Net - the sparse3d backbone graph (reference: SparseConvNet/sparseconvnet/fpn_net.py:13-265).
+
+Same constructor signature, same sub-module attribute names (layers_in_0, layers_in, layers_out,
+linear, convs_pro2d, m_downs, m_shortcuts, m_ups, m_mergeds => identical state_dict keys) and the
+same forward dataflow: 9-scale residual encoder, 1x1x1 shortcuts to nPlaneM, 8 deconvolution
+top-down steps with 3^3 merge convs (all 8 are executed, as in the reference), and the
+[1,1,Z] z-collapse convolutions that make the 2-D RPN maps.  Debug printing / pdb hooks of the
+reference are not reproduced.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+import sparseconvnet as scn
+
+CHECK_NAN = False  # the reference syncs on isnan(weight) every forward (fpn_net.py:141-145)
+
+
+class FPN_Net(torch.nn.Module):
+    def __init__(self, full_scale, dimension, raw_elements, reps, nPlanesF, nPlaneM, residual_blocks,
+                 fpn_scales_from_top, roi_scales_from_top, downsample, rpn_map_sizes,
+                 rpn_3d_2d_selector, leakiness=0, voxel_scale=None, bn_momentum=0.9,
+                 track_running_stats=True):
+        nn.Module.__init__(self)
+        self.bn_momentum = bn_momentum
+        self.track_running_stats = track_running_stats
+        self.dimension = dimension
+        self.down_kernels, self.down_strides = downsample[0], downsample[1]
+        self.fpn_scales_from_top = fpn_scales_from_top
+        self.roi_scales_from_top = roi_scales_from_top
+        n_scales = len(nPlanesF)
+        assert len(self.down_kernels) == n_scales - 1 == len(self.down_strides), \
+            "nPlanesF len = %d, kernels num = %d" % (n_scales, len(self.down_kernels))
+        assert all(len(k) == 3 for k in self.down_kernels) and all(len(s) == 3 for s in self.down_strides)
+        self._merge = "add"
+        in_channels = sum({"xyz": 3, "color": 3, "normal": 3}[e] for e in raw_elements)
+        bn = dict(momentum=bn_momentum, track_running_stats=track_running_stats)
+
+        self.layers_in_0 = scn.Sequential(scn.InputLayer(dimension, full_scale, mode=4))
+        self.layers_in = scn.Sequential(
+            scn.InputLayer(dimension, full_scale, mode=4),
+            scn.SubmanifoldConvolution(dimension, in_channels, nPlanesF[0], 3, False))
+        self.layers_out = scn.Sequential(scn.BatchNormReLU(nPlanesF[0], **bn), scn.OutputLayer(dimension))
+        self.linear = nn.Linear(nPlanesF[0], 20)
+        self.voxel_scale = voxel_scale
+        self.rpn_map_sizes = np.array(rpn_map_sizes)
+        self.rpn_3d_2d_selector = rpn_3d_2d_selector
+
+        self.convs_pro2d = nn.ModuleList(
+            scn.Convolution(dimension, nPlaneM, nPlaneM, [1, 1, int(z)], [1, 1, 1], False)
+            for z in self.rpn_map_sizes[:, -1])
+
+        def bn_act(c):
+            return scn.BatchNormLeakyReLU(c, leakiness=leakiness, **bn)
+
+        def block(m, a, b):
+            if residual_blocks:
+                m.add(scn.ConcatTable()
+                      .add(scn.Identity() if a == b else scn.NetworkInNetwork(a, b, False))
+                      .add(scn.Sequential()
+                           .add(bn_act(a)).add(scn.SubmanifoldConvolution(dimension, a, b, 3, False))
+                           .add(bn_act(b)).add(scn.SubmanifoldConvolution(dimension, b, b, 3, False)))
+                      ).add(scn.AddTable())
+            else:
+                m.add(scn.Sequential().add(bn_act(a))
+                      .add(scn.SubmanifoldConvolution(dimension, a, b, 3, False)))
+            return {"kernel": [1, 1, 1], "stride": [1, 1, 1]}
+
+        def strided(layer, a, b, scale):
+            return scn.Sequential().add(bn_act(a)).add(
+                layer(dimension, a, b, self.down_kernels[scale], self.down_strides[scale], False))
+
+        self.m_downs, self.m_shortcuts = nn.ModuleList(), nn.ModuleList()
+        self.operations_down, self.operations_up = [], []
+        for k in range(n_scales):
+            m = scn.Sequential()
+            if k > 0:
+                m.add(strided(scn.Convolution, nPlanesF[k - 1], nPlanesF[k], k - 1))
+                self.operations_down.append({"kernel": self.down_kernels[k - 1],
+                                             "stride": self.down_strides[k - 1]})
+            for _ in range(reps):
+                op = block(m, nPlanesF[k], nPlanesF[k])
+                if k == 0:
+                    self.operations_down.append(op)
+            self.m_downs.append(m)
+            self.m_shortcuts.append(scn.SubmanifoldConvolution(dimension, nPlanesF[k], nPlaneM, 1, False))
+
+        self.m_ups, self.m_mergeds = nn.ModuleList(), nn.ModuleList()
+        for k in range(n_scales - 1, 0, -1):
+            up = strided(scn.Deconvolution, nPlaneM, nPlaneM, k - 1)
+            # the reference adds BN and Deconvolution directly to the Sequential (fpn_net.py:88-90):
+            # keys m_ups.<i>.0 (BN) and m_ups.<i>.1 (Deconvolution) - `strided` builds exactly that
+            self.m_ups.append(up)
+            self.operations_up.append({"kernel": self.down_kernels[k - 1],
+                                       "stride": self.down_strides[k - 1]})
+            self.m_mergeds.append(scn.SubmanifoldConvolution(dimension, nPlaneM, nPlaneM, 3, False))
+
+    def forward(self, net0):
+        if CHECK_NAN and not torch.isnan(self.layers_in[1].weight).sum() == 0:
+            raise FloatingPointError("FPN_Net: NaN in stem weights")
+        return self.forward_fpn(self.layers_in(net0))
+
+    def forward_fpn(self, net):
+        n_scales = len(self.m_downs)
+        downs = []
+        for m in self.m_downs:
+            net = m(net)
+            downs.append(net)
+        net = self.m_shortcuts[-1](net)
+        ups = [net]
+        for k in range(n_scales - 1):
+            j = n_scales - 2 - k
+            net = self.m_ups[k](net)
+            net = scn.add_feature_planes([net, self.m_shortcuts[j](downs[j])])
+            ups.append(self.m_mergeds[k](net))
+
+        rpn_maps_3d = [ups[i] for i in self.fpn_scales_from_top]
+        rpn_maps_2d = [self.convs_pro2d[i](rpn_maps_3d[i]) for i in range(len(rpn_maps_3d))]
+        both = rpn_maps_3d + rpn_maps_2d
+        rpn_maps = [both[i] for i in self.rpn_3d_2d_selector]
+        roi_maps = [ups[i] for i in self.roi_scales_from_top]
+        for i, t in enumerate(rpn_maps_3d):
+            assert torch.all(t.spatial_size == torch.tensor(self.rpn_map_sizes[i]))
+        return rpn_maps, roi_maps

@@ -1,0 +1,223 @@
+/*
+ * scn_b200.h - C-ABI of libscn_b200.so, the B200-native replacement for the SparseConvNet
+ * "SCN" extension on the sparse3d-backbone hot path.
+ *
+ * Every entry point is what the reference's pybind surface for this path would bind
+ * (reference: SparseConvNet/sparseconvnet/SCN/pybind.cpp, sparseconvnet.h,
+ * sparseconvnet_cuda.cpp).  Differences forced by a C ABI:
+ *   - no tensor types: raw DEVICE pointers (fp32 features / weights), plain sizes, and the
+ *     CUDA stream as a void* (cudaStream_t);
+ *   - the reference passes an empty output tensor and resize_()s it inside C++
+ *     (e.g. CUDA/Convolution.cpp:38); here the caller first asks for the row count
+ *     (scn_get_nactive / the *_prepare calls) and allocates the output itself;
+ *   - errors: every call returns 0 on success, non-zero on failure, and scn_last_error()
+ *     returns a thread-local message (reference: C asserts / ATen exceptions).
+ *
+ * Conventions: feature matrices are row-major [rows, planes] fp32, contiguous.
+ * Weights are [K, 1, nIn, nOut] fp32 exactly like the reference Parameter
+ * (submanifoldConvolution.py:24-26); K enumerates the filter box row-major with the LAST
+ * spatial dimension fastest (RectangularRegions.h:31-38).  `spatial_size`, `filter_size`,
+ * `filter_stride` are int64[3].  All launches go to `stream`; the only host synchronisations
+ * are the documented count read-backs inside the *_prepare / first-use rulebook builds and
+ * the explicit copy-out calls (scn_get_spatial_locations, scn_*_rulebook_*).
+ * There is NO CPU fallback anywhere in this library.
+ */
+#ifndef SCN_B200_H
+#define SCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scn_metadata scn_metadata_t;
+
+/* Precision of the convolution contraction (accumulation is always fp32). */
+enum {
+  SCN_PRECISION_FP32 = 0,   /* exact fp32 FFMA tiles (parity mode)                        */
+  SCN_PRECISION_BF16 = 1,   /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accum     */
+  SCN_PRECISION_TF32X3 = 2  /* 3xTF32 split on tcgen05: fp32-equivalent accuracy          */
+};
+
+/* ---- library ---------------------------------------------------------------------- */
+const char *scn_last_error(void);
+int scn_version(void);
+/* replaces pybind.cpp:234 n_rulebook_bits() */
+int scn_n_rulebook_bits(void);
+
+/* ---- Metadata<3> handle (replaces class Metadata_3, pybind.cpp:11-32,205;
+ *      Metadata/Metadata.h:44-163) --------------------------------------------------- */
+int scn_metadata_create(int dimension, scn_metadata_t **out);
+void scn_metadata_destroy(scn_metadata_t *m);
+/* Metadata::clear (Metadata.cpp:51-62) */
+int scn_metadata_clear(scn_metadata_t *m, void *stream);
+/* Metadata::getNActive (Metadata.cpp:64-67); -1 in *n_active if the scale does not exist */
+int scn_get_nactive(scn_metadata_t *m, const int64_t *spatial_size, int64_t *n_active);
+/* number of samples = grids[...].size() (CPU/SparseToDense.cpp:43) */
+int scn_get_batch_size(scn_metadata_t *m, int64_t *batch_size);
+/* Metadata::getSpatialLocations (Metadata.cpp:149-168): int64 [nActive,4] rows (x,y,z,batch)
+ * written to HOST memory `out_host` (the reference returns a CPU tensor). Synchronises. */
+int scn_get_spatial_locations(scn_metadata_t *m, const int64_t *spatial_size,
+                              int64_t *out_host, void *stream);
+/* same rows, int32 [nActive,4], left on the device (no sync) */
+int scn_get_spatial_locations_device(scn_metadata_t *m, const int64_t *spatial_size,
+                                     int32_t *out_dev, void *stream);
+
+/* ---- voxelisation front end (replaces the numpy quantiser in
+ *      data3d/suncg_utils/suncg_dataset.py:126-188 + collate data3d/data.py:25-37) ----
+ * xyz: DEVICE float64 [n,3] metres; computes a = xyz*scale in fp64, a -= min(a) per column
+ * (min taken over this sample), keeps rows with 0 <= a < full_scale, truncates to int64.
+ * coords_out: DEVICE int64 [n,4] (x,y,z,batch_idx) compacted in input order; keep_out:
+ * DEVICE uint8 [n] mask; n_kept read back to the host (one sync). */
+int scn_quantize_points(const double *xyz, int64_t n, double scale, const int64_t *full_scale,
+                        int64_t batch_idx, int64_t *coords_out, uint8_t *keep_out,
+                        int64_t *n_kept, void *stream);
+
+/* ---- InputLayer / OutputLayer (replaces InputLayer_updateOutput / _updateGradInput,
+ *      OutputLayer_updateOutput / _updateGradInput: pybind.cpp:154-170,
+ *      CPU/IOLayers.cpp:45-140, Metadata::inputLayer Metadata.cpp:406-417,
+ *      inputLayerRules IOLayersRules.h:19-125) ---------------------------------------
+ * coords: int64 [n_points, n_cols] (n_cols = 3 or 4, last column = batch index), in HOST
+ * memory when coords_on_device == 0 (the reference contract: ioLayers.py:60) or DEVICE
+ * memory otherwise.  Builds the scale-0 hash grid, numbers the active sites in order of
+ * first occurrence, builds the point->site CSR.  One host sync (returns *n_active). */
+int scn_input_layer_prepare(scn_metadata_t *m, const int64_t *spatial_size,
+                            const int64_t *coords, int64_t n_points, int n_cols,
+                            int coords_on_device, int64_t batch_size, int mode,
+                            void *stream, int64_t *n_active);
+/* out[site] = sum/mean/first/last of in[points of site]; in [n_points,planes], out [n_active,planes] */
+int scn_input_layer_forward(scn_metadata_t *m, const float *in_feats, float *out_feats,
+                            int64_t n_planes, void *stream);
+/* d_in [n_points,planes] (fully written), d_out [n_active,planes] */
+int scn_input_layer_backward(scn_metadata_t *m, float *d_in_feats, const float *d_out_feats,
+                             int64_t n_planes, void *stream);
+/* OutputLayer: out[point] = in[site(point)] (average=false, CPU/IOLayers.cpp:91-109) */
+int scn_output_layer_forward(scn_metadata_t *m, const float *in_feats, float *out_feats,
+                             int64_t n_planes, void *stream);
+int scn_output_layer_backward(scn_metadata_t *m, float *d_in_feats, const float *d_out_feats,
+                              int64_t n_planes, void *stream);
+/* header of the input rulebook: [mode, maxActive, nInputRows, nOutputRows] (IOLayersRules.h:10-15) */
+int scn_input_rulebook_header(scn_metadata_t *m, int64_t header[4], void *stream);
+/* reference-format table nOutputRows x (1+maxActive) int32 -> HOST */
+int scn_input_rulebook_copy(scn_metadata_t *m, int32_t *out_host, void *stream);
+
+/* ---- rulebooks (replaces Metadata::getSubmanifoldRuleBook Metadata.cpp:430-444,
+ *      ::getRuleBook :485-512, ::getSparseToDenseRuleBook :469-483;
+ *      SubmanifoldConvolutionRules.h:13-87, ConvolutionRules.h:12-151) ----------------
+ * *_prepare builds (or finds cached) the rulebook; counts_host receives the number of
+ * (in,out) pairs per kernel offset (K = prod(filter_size) entries).  One host sync on first
+ * build, none on a cache hit. */
+int scn_submanifold_rulebook_prepare(scn_metadata_t *m, const int64_t *spatial_size,
+                                     const int64_t *filter_size, void *stream,
+                                     int64_t *counts_host);
+/* strided convolution rulebook; creates the output grid as a side effect and returns its
+ * nActive (Metadata.cpp:497-507). Deconvolution uses the same rulebook with roles swapped
+ * (CPU/Deconvolution.cpp:15-16). */
+int scn_conv_rulebook_prepare(scn_metadata_t *m, const int64_t *in_spatial_size,
+                              const int64_t *out_spatial_size, const int64_t *filter_size,
+                              const int64_t *filter_stride, void *stream,
+                              int64_t *n_out_active, int64_t *counts_host);
+/* copy the pairs of one offset to HOST as int32 [count,2] = (in,out) like RuleBook (Metadata.h:35) */
+int scn_submanifold_rulebook_copy(scn_metadata_t *m, const int64_t *spatial_size,
+                                  const int64_t *filter_size, int64_t offset,
+                                  int32_t *pairs_host, void *stream);
+int scn_conv_rulebook_copy(scn_metadata_t *m, const int64_t *in_spatial_size,
+                           const int64_t *filter_size, const int64_t *filter_stride,
+                           int64_t offset, int32_t *pairs_host, void *stream);
+/* SparseToDense rules: int32 [nActive,2] = (row, linear offset (x*Y+y)*Z+z) and the per-row
+ * sample index int32 [nActive] -> HOST (ConvolutionRules.h:110-128) */
+int scn_sparse_to_dense_rules_copy(scn_metadata_t *m, const int64_t *spatial_size,
+                                   int32_t *rules_host, int32_t *sample_host, void *stream);
+
+/* ---- convolutions (replaces SubmanifoldConvolution_updateOutput/_backward
+ *      pybind.cpp:134-143, Convolution_* :54-65, Deconvolution_* :78-89;
+ *      CPU/Convolution.cpp:46-185, CPU/Deconvolution.cpp:8-77) ------------------------
+ * in [nIn,n_in_planes]; out [nOut,n_out_planes] (fully written: zero + bias + sum);
+ * bias may be NULL.  *macs receives sum_k pairs_k*nIn*nOut like the reference's return.
+ * backward: d_in fully written; d_weight [K,1,nIn,nOut] fully written (matmul_out
+ * overwrites, CPU/Convolution.cpp:110); d_bias (may be NULL) = column sums of d_out. */
+int scn_submanifold_conv_forward(scn_metadata_t *m, const int64_t *spatial_size,
+                                 const int64_t *filter_size, const float *in, float *out,
+                                 const float *weight, const float *bias, int64_t n_in_planes,
+                                 int64_t n_out_planes, int precision, void *stream, double *macs);
+int scn_submanifold_conv_backward(scn_metadata_t *m, const int64_t *spatial_size,
+                                  const int64_t *filter_size, const float *in, float *d_in,
+                                  const float *d_out, const float *weight, float *d_weight,
+                                  float *d_bias, int64_t n_in_planes, int64_t n_out_planes,
+                                  int precision, void *stream);
+int scn_conv_forward(scn_metadata_t *m, const int64_t *in_spatial_size,
+                     const int64_t *out_spatial_size, const int64_t *filter_size,
+                     const int64_t *filter_stride, const float *in, float *out,
+                     const float *weight, const float *bias, int64_t n_in_planes,
+                     int64_t n_out_planes, int precision, void *stream, double *macs);
+int scn_conv_backward(scn_metadata_t *m, const int64_t *in_spatial_size,
+                      const int64_t *out_spatial_size, const int64_t *filter_size,
+                      const int64_t *filter_stride, const float *in, float *d_in,
+                      const float *d_out, const float *weight, float *d_weight, float *d_bias,
+                      int64_t n_in_planes, int64_t n_out_planes, int precision, void *stream);
+/* in lives on the COARSE scale (in_spatial_size), out on the FINE scale (out_spatial_size) */
+int scn_deconv_forward(scn_metadata_t *m, const int64_t *in_spatial_size,
+                       const int64_t *out_spatial_size, const int64_t *filter_size,
+                       const int64_t *filter_stride, const float *in, float *out,
+                       const float *weight, const float *bias, int64_t n_in_planes,
+                       int64_t n_out_planes, int precision, void *stream, double *macs);
+int scn_deconv_backward(scn_metadata_t *m, const int64_t *in_spatial_size,
+                        const int64_t *out_spatial_size, const int64_t *filter_size,
+                        const int64_t *filter_stride, const float *in, float *d_in,
+                        const float *d_out, const float *weight, float *d_weight, float *d_bias,
+                        int64_t n_in_planes, int64_t n_out_planes, int precision, void *stream);
+
+/* ---- NetworkInNetwork (replaces NetworkInNetwork_updateOutput / _updateGradInput /
+ *      _accGradParameters, sparseconvnet.h:50-60, CPU/NetworkInNetwork.cpp:8-46) ------ */
+int scn_nin_forward(const float *in, float *out, const float *weight, const float *bias,
+                    int64_t n_rows, int64_t n_in_planes, int64_t n_out_planes, int precision,
+                    void *stream, double *macs);
+int scn_nin_backward(const float *in, float *d_in, const float *d_out, const float *weight,
+                     float *d_weight, float *d_bias, int64_t n_rows, int64_t n_in_planes,
+                     int64_t n_out_planes, int precision, void *stream);
+
+/* ---- BatchNormalization fused with (Leaky)ReLU (replaces BatchNormalization_updateOutput /
+ *      _backward, sparseconvnet.h:21-32, CPU/BatchNormalization.cpp:13-107) ------------
+ * train != 0: batch statistics (biased var for normalisation, unbiased for running_var),
+ * running stats updated in place with `momentum` weighting the OLD value.
+ * train == 0: normalise with running_mean / running_var as passed.
+ * weight / bias may be NULL.  Unlike the reference, d_out is NOT modified in place. */
+int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *save_invstd,
+                          float *running_mean, float *running_var, const float *weight,
+                          const float *bias, float eps, float momentum, int train,
+                          float leakiness, int64_t n_rows, int64_t n_planes, void *stream);
+int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const float *d_out,
+                           const float *save_mean, const float *save_invstd,
+                           const float *weight, float *d_weight, float *d_bias,
+                           float leakiness, int64_t n_rows, int64_t n_planes, void *stream);
+
+/* ---- SparseToDense (replaces SparseToDense_updateOutput / _updateGradInput,
+ *      pybind.cpp:124-133, CPU/SparseToDense.cpp:35-87) --------------------------------
+ * out: dense [batch, n_planes, X, Y, Z] fp32, fully written (zero-filled then scattered). */
+int scn_sparse_to_dense_forward(scn_metadata_t *m, const int64_t *spatial_size, const float *in,
+                                float *out, int64_t n_planes, int64_t batch_size, void *stream);
+int scn_sparse_to_dense_backward(scn_metadata_t *m, const int64_t *spatial_size, float *d_in,
+                                 const float *d_out, int64_t n_planes, int64_t batch_size,
+                                 void *stream);
+
+/* ---- elementwise helper used by the data-parallel gradient bucket ------------------- */
+/* y[i] *= alpha over n fp32 values (scale the all-reduced gradient bucket by 1/world) */
+int scn_scale_inplace(float *y, float alpha, int64_t n, void *stream);
+
+/* ---- instrumentation --------------------------------------------------------------- */
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+int64_t scn_launch_count(void);
+/* tile-book statistics of a cached rulebook: stats[0]=pairs, [1]=tile entries*128 (rows the
+ * tensor/FFMA tiles actually multiply), [2]=tiles.  kind: 0 submanifold, 1 conv, 2 deconv,
+ * 3 conv-dX (fine<-coarse), 4 deconv-dX */
+int scn_rulebook_stats(scn_metadata_t *m, int kind, const int64_t *in_spatial_size,
+                       const int64_t *filter_size, const int64_t *filter_stride,
+                       int64_t stats[3]);
+/* 0: tiles in natural row order, 1 (default): rows grouped by neighbour mask */
+int scn_set_tile_grouping(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCN_B200_H */
