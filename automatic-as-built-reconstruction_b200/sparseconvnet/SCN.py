@@ -356,3 +356,9 @@ def SparseToDense_updateGradInput(spatial_size, m, input_features, d_input_featu
         return
     check(lib.scn_sparse_to_dense_backward(m._h, i64x3(spatial_size), ptr(d_input_features), ptr(dy),
                                            input_features.size(1), dy.size(0), stream()))
+
+
+# ---- instrumentation -----------------------------------------------------------------------
+def launch_count():
+    """kernels launched by libscn_b200 since load (bench.py `gpu_launches`)"""
+    return int(lib.scn_launch_count())

@@ -1,0 +1,456 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI of libscn_b200.so
+via the sparseconvnet host package and is compared with the oracle (oracle/scn_oracle.py, pinned to
+the compiled reference) and with the golden vectors generated from the reference itself.
+
+Tolerances: integer work bit-exact (canonical pair sets, site sets, first-occurrence order);
+fp32 features / gradients: max|a-b| <= 1e-4 * max|b| (the north-star fp32 bound)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import scn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, b):
+    a = a.detach().cpu().double() if torch.is_tensor(a) else torch.as_tensor(a).double()
+    b = b.detach().cpu().double() if torch.is_tensor(b) else torch.as_tensor(b).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def scn():
+    import sparseconvnet
+    sparseconvnet.set_conv_precision("fp32")
+    return sparseconvnet
+
+
+def make_input(scn, coords, ss, feats=None, mode=4, C=4, seed=0):
+    torch.manual_seed(seed)
+    if feats is None:
+        feats = torch.randn(len(coords), C)
+    leaf = feats.cuda().requires_grad_(True)
+    t = scn.InputLayer(3, ss, mode)([torch.as_tensor(coords), leaf])
+    t.leaf = leaf
+    return t, feats
+
+
+def canon(pairs, rin, rout):
+    return O.canonical_pairs(pairs.numpy() if torch.is_tensor(pairs) else pairs, rin, rout)
+
+
+# ---------------------------------------------------------------------------------------------
+# integer path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["appendix_c", "cloud_rulebooks"])
+def test_rulebooks_match_reference_golden(scn, gold, name):
+    g = gold(name)
+    coords, ss = g["coords"], g["ss"].tolist()
+    t, _ = make_input(scn, coords, ss)
+    m = t.metadata
+    header, table = m.inputLayerRuleBook()
+    assert header == g["in_header"].tolist()
+    assert np.array_equal(table.numpy(), g["in_table"])
+    loc0 = m.getSpatialLocations(ss).numpy()
+    assert np.array_equal(loc0, g["loc0"])
+    r0 = O.canonical_rank(loc0, ss)
+    for k, r in enumerate(m.getSubmanifoldRuleBook(ss, [3, 3, 3])):
+        assert np.array_equal(canon(r, r0, r0), g["sub3_%d" % k]), k
+    ss1 = [s // 2 for s in ss]
+    rules = m.getRuleBook(ss, ss1, [2, 2, 2], [2, 2, 2])
+    loc1 = m.getSpatialLocations(ss1).numpy()
+    assert (np.diff(loc1[:, 3]) >= 0).all()
+    r1 = O.canonical_rank(loc1, ss1)
+    assert np.array_equal(loc1[np.argsort(r1)], g["loc1_sorted"])
+    for k, r in enumerate(rules):
+        assert np.array_equal(canon(r, r0, r1), g["conv2_%d" % k]), k
+    ssz = [ss1[0], ss1[1], 1]
+    rules = m.getRuleBook(ss1, ssz, [1, 1, ss1[2]], [1, 1, 1])
+    locz = m.getSpatialLocations(ssz).numpy()
+    rz = O.canonical_rank(locz, ssz)
+    assert np.array_equal(locz[np.argsort(rz)], g["locz_sorted"])
+    for k, r in enumerate(rules):
+        assert np.array_equal(canon(r, r1, rz), g["zc_%d" % k]), k
+    rows, sample = m.getSparseToDenseRuleBook(ss1)
+    got = np.stack([r1[rows[:, 0].numpy()], rows[:, 1].numpy(), sample.numpy()], 1)
+    assert np.array_equal(got[np.argsort(got[:, 0])], g["s2d"])
+    # overlapping 3/2 on a fresh metadata
+    keep, so, soo = g["odd_keep"], g["odd_ss"].tolist(), g["odd_out_ss"].tolist()
+    t2, _ = make_input(scn, coords[keep], so)
+    lo = t2.metadata.getSpatialLocations(so).numpy()
+    ro = O.canonical_rank(lo, so)
+    rules = t2.metadata.getRuleBook(so, soo, [3, 3, 3], [2, 2, 2])
+    lout = t2.metadata.getSpatialLocations(soo).numpy()
+    rout = O.canonical_rank(lout, soo)
+    assert np.array_equal(lout[np.argsort(rout)], g["odd_loc_out_sorted"])
+    for k, r in enumerate(rules):
+        assert np.array_equal(canon(r, ro, rout), g["conv3s2_%d" % k]), k
+
+
+def _check_vs_oracle(scn, coords, ss, chain=2):
+    t, _ = make_input(scn, coords, ss, C=1)
+    m = t.metadata
+    loc0, prow, header, table = O.input_layer_rules(coords, 4)
+    hd, tab = m.inputLayerRuleBook()
+    assert hd == header and np.array_equal(tab.numpy(), table)
+    assert np.array_equal(m.getSpatialLocations(ss).numpy(), loc0)
+    loc, cur = loc0, list(ss)
+    for _ in range(chain):
+        r0 = O.canonical_rank(loc, cur)
+        want = O.submanifold_rules(loc, cur, [3, 3, 3])
+        got = m.getSubmanifoldRuleBook(cur, [3, 3, 3])
+        for k in range(27):
+            assert np.array_equal(canon(got[k], r0, r0), canon(want[k], r0, r0)), (cur, k)
+        nxt = [s // 2 for s in cur]
+        oloc, orules = O.conv_rules(loc, cur, [2, 2, 2], [2, 2, 2], nxt)
+        grules = m.getRuleBook(cur, nxt, [2, 2, 2], [2, 2, 2])
+        gloc = m.getSpatialLocations(nxt).numpy()
+        assert (np.diff(gloc[:, 3]) >= 0).all()
+        ro, rg = O.canonical_rank(oloc, nxt), O.canonical_rank(gloc, nxt)
+        assert np.array_equal(oloc[np.argsort(ro)], gloc[np.argsort(rg)])
+        for k in range(8):
+            assert np.array_equal(canon(grules[k], r0, rg), canon(orules[k], r0, ro)), (cur, k)
+        loc, cur = gloc, nxt
+    return m
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (37, 1), (5000, 2), (60000, 3)])
+def test_rulebooks_random_clouds(scn, n, seed):
+    rng = np.random.RandomState(seed)
+    ss = [256, 128, 64]
+    c = np.concatenate([np.concatenate([(rng.rand(n, 3) * np.array([200, 100, 6])).astype(np.int64),
+                                        np.full((n, 1), b)], 1) for b in range(3)])
+    _check_vs_oracle(scn, c, ss)
+
+
+def test_unsorted_batch_column_is_made_batch_contiguous(scn):
+    rng = np.random.RandomState(5)
+    c = np.concatenate([(rng.rand(3000, 3) * 40).astype(np.int64), rng.randint(0, 4, (3000, 1))], 1)
+    _check_vs_oracle(scn, c, [64, 64, 64])
+
+
+def test_coords_on_device_and_three_columns(scn):
+    rng = np.random.RandomState(6)
+    c3 = (rng.rand(2000, 3) * 30).astype(np.int64)
+    feats = torch.randn(2000, 5)
+    a = scn.InputLayer(3, [32, 32, 32], 4)([torch.from_numpy(c3), feats.cuda()])
+    b = scn.InputLayer(3, [32, 32, 32], 4)([torch.from_numpy(c3).cuda(), feats.cuda()])
+    assert torch.equal(a.features, b.features)
+    assert torch.equal(a.get_spatial_locations(), b.get_spatial_locations())
+    assert (a.get_spatial_locations()[:, 3] == 0).all()
+
+
+def test_empty_input(scn):
+    t = scn.InputLayer(3, [16, 16, 16], 4)([torch.zeros(0, 4, dtype=torch.long), torch.zeros(0, 3).cuda()])
+    assert t.features.shape == (0, 3) and t.metadata.getNActive([16, 16, 16]) == 0
+    y = scn.SubmanifoldConvolution(3, 3, 5, 3, False).cuda()(t)
+    assert y.features.shape == (0, 5)
+
+
+def test_out_of_range_coordinate_raises(scn):
+    with pytest.raises(RuntimeError, match="coordinate"):
+        scn.InputLayer(3, [16, 16, 16], 4)([torch.tensor([[0, 0, -1, 0]]), torch.zeros(1, 3).cuda()])
+
+
+def test_full_size_building_counts(scn):
+    """BASELINE configs 1/2 input: the active-site and pair counts measured on the reference CPU
+    build during the survey must reproduce exactly."""
+    locs, feats = O.to_input([O.building(300000, seed=0)])
+    t = scn.InputLayer(3, [4096, 4096, 512], 4)([locs, feats.cuda()])
+    m = t.metadata
+    n_active = [278639, 227288, 123489, 38672, 9544, 2184, 486, 112, 16]
+    pairs3 = [583287, 1005844, 953703, 371244, 98504, 25274, 6620, 1672, 100]
+    ss = [4096, 4096, 512]
+    for s in range(9):
+        assert m.getNActive(ss) == n_active[s], s
+        assert sum(len(r) for r in m.getSubmanifoldRuleBook(ss, [3, 3, 3])) == pairs3[s], s
+        if s < 8:
+            nxt = [v // 2 for v in ss]
+            rules = m.getRuleBook(ss, nxt, [2, 2, 2], [2, 2, 2])
+            assert sum(len(r) for r in rules) == n_active[s]
+            ss = nxt
+    for ss4, want in (([256, 256, 32], 3060), ([128, 128, 16], 780), ([64, 64, 8], 195), ([32, 32, 4], 56)):
+        m.getRuleBook(ss4, [ss4[0], ss4[1], 1], [1, 1, ss4[2]], [1, 1, 1])
+        assert m.getNActive([ss4[0], ss4[1], 1]) == want
+    # scale 0 and 1 against the numpy oracle (bit-exact canonical pair sets)
+    loc0 = m.getSpatialLocations([4096, 4096, 512]).numpy()
+    oloc0, _, _, _ = O.input_layer_rules(locs.numpy(), 4)
+    assert np.array_equal(loc0, oloc0)
+    r0 = O.canonical_rank(loc0, [4096, 4096, 512])
+    want = O.submanifold_rules(loc0, [4096, 4096, 512], [3, 3, 3])
+    got = m.getSubmanifoldRuleBook([4096, 4096, 512], [3, 3, 3])
+    for k in range(27):
+        assert np.array_equal(canon(got[k], r0, r0), canon(want[k], r0, r0)), k
+
+
+def test_quantize_points(scn):
+    xyz = O.building(20000, seed=3) * np.array([1.0, 1.0, 4.0])     # z range 12 m -> some points clipped
+    want, keep = O.quantize_points(xyz, 50, [4096, 4096, 512], 2)
+    got, gkeep = scn.quantize_points(torch.from_numpy(xyz).cuda(), 50, [4096, 4096, 512], 2)
+    assert not keep.all()
+    assert np.array_equal(got.cpu().numpy(), want) and np.array_equal(gkeep.cpu().numpy(), keep)
+
+
+# ---------------------------------------------------------------------------------------------
+# layers vs the oracle
+# ---------------------------------------------------------------------------------------------
+def _cloud(n=4000, ext=(60, 50, 12), batch=2, seed=0):
+    rng = np.random.RandomState(seed)
+    return np.concatenate([np.concatenate([(rng.rand(n, 3) * np.array(ext)).astype(np.int64),
+                                           np.full((n, 1), b)], 1) for b in range(batch)])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_input_output_layer_modes(scn, mode):
+    c = _cloud(1500, (12, 12, 6))
+    if mode == 0:
+        c = np.unique(c, axis=0)
+    t, feats = make_input(scn, c, [16, 16, 8], mode=mode, C=9)
+    loc, prow, header, table = O.input_layer_rules(c, mode)
+    want = O.input_layer_forward(feats, header, table)
+    assert rel(t.features, want) <= 1e-6
+    out = scn.OutputLayer(3)(t)
+    if mode != 0:
+        assert rel(out, want[prow]) <= 1e-6 or mode in (1, 2)
+    g = torch.randn_like(t.features)
+    (gin,) = torch.autograd.grad(t.features, [t.leaf], g)
+    wf = feats.clone().requires_grad_(True)
+    O.input_layer_forward(wf, header, table).backward(g.cpu())
+    assert rel(gin, wf.grad) <= 1e-6
+
+
+CONV_SHAPES = [(9, 32), (32, 32), (64, 64), (128, 128), (32, 128), (5, 7), (16, 16), (256, 256), (128, 64)]
+
+
+@pytest.mark.parametrize("cin,cout", CONV_SHAPES)
+@pytest.mark.parametrize("fs", [3, 1])
+def test_submanifold_convolution(scn, cin, cout, fs):
+    ss = [64, 64, 16]
+    c = _cloud()
+    t, _ = make_input(scn, c, ss, C=cin)
+    conv = scn.SubmanifoldConvolution(3, cin, cout, fs, cin == 5).cuda()
+    if cin == 5:
+        conv.bias.data.normal_()
+    y = conv(t)
+    loc = t.get_spatial_locations().numpy()
+    rules = O.submanifold_rules(loc, ss, [fs] * 3)
+    x = t.features.detach().cpu()
+    w = conv.weight.detach().cpu()
+    b = conv.bias.detach().cpu() if cin == 5 else None
+    want = O.conv_forward(x, w, rules, len(loc), b)
+    assert rel(y.features, want) <= TOL
+    dy = torch.randn_like(y.features)
+    y.features.backward(dy)
+    dx, dw, db = O.conv_backward(x, dy.cpu(), w, rules)
+    assert rel(conv.weight.grad, dw) <= TOL
+    assert rel(t.leaf.grad, _input_grad(t, c, dx)) <= TOL
+    if cin == 5:
+        assert rel(conv.bias.grad, db) <= TOL
+
+
+def _input_grad(t, coords, dx_sites):
+    """push a site-level gradient through the oracle's input layer to the point features"""
+    loc, prow, header, table = O.input_layer_rules(coords, 4)
+    f = torch.zeros(len(coords), dx_sites.shape[1], requires_grad=True)
+    O.input_layer_forward(f, header, table).backward(dx_sites)
+    return f.grad
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 64), (128, 128), (9, 16), (64, 128), (256, 256)])
+def test_strided_convolution_and_deconvolution(scn, cin, cout):
+    ss, ss1 = [64, 64, 16], [32, 32, 8]
+    c = _cloud(seed=1)
+    t, _ = make_input(scn, c, ss, C=cin)
+    conv = scn.Convolution(3, cin, cout, 2, 2, False).cuda()
+    dec = scn.Deconvolution(3, cout, cin, 2, 2, False).cuda()
+    y = conv(t)
+    z = dec(y)
+    assert z.spatial_size.tolist() == ss and y.spatial_size.tolist() == ss1
+    loc0 = t.get_spatial_locations().numpy()
+    gloc1 = y.get_spatial_locations().numpy()
+    oloc1, rules = O.conv_rules(loc0, ss, [2, 2, 2], [2, 2, 2], ss1)
+    pg, po = np.argsort(O.canonical_rank(gloc1, ss1)), np.argsort(O.canonical_rank(oloc1, ss1))
+    assert np.array_equal(gloc1[pg], oloc1[po])
+    x, w, w2 = t.features.detach().cpu(), conv.weight.detach().cpu(), dec.weight.detach().cpu()
+    oy = O.conv_forward(x, w, rules, len(oloc1))
+    assert rel(y.features[pg], oy[po]) <= TOL
+    oz = O.conv_forward(oy, w2, rules, len(loc0), swap=True)
+    assert rel(z.features, oz) <= TOL
+    dz = torch.randn_like(z.features)
+    z.features.backward(dz)
+    ody, odw2, _ = O.conv_backward(oy, dz.cpu(), w2, rules, swap=True)
+    assert rel(dec.weight.grad, odw2) <= TOL
+    odx, odw, _ = O.conv_backward(x, ody, w, rules)
+    assert rel(conv.weight.grad, odw) <= TOL
+    assert rel(t.leaf.grad, _input_grad(t, c, odx)) <= TOL
+
+
+@pytest.mark.parametrize("Z", [4, 8, 16, 32])
+def test_z_collapse_convolution(scn, Z):
+    ss = [32, 32, Z]
+    c = _cloud(2500, (30, 30, Z), seed=Z)
+    t, _ = make_input(scn, c, ss, C=128)
+    conv = scn.Convolution(3, 128, 128, [1, 1, Z], [1, 1, 1], False).cuda()
+    y = conv(t)
+    assert y.spatial_size.tolist() == [32, 32, 1]
+    loc0, gl = t.get_spatial_locations().numpy(), y.get_spatial_locations().numpy()
+    ol, rules = O.conv_rules(loc0, ss, [1, 1, Z], [1, 1, 1], [32, 32, 1])
+    pg, po = np.argsort(O.canonical_rank(gl, [32, 32, 1])), np.argsort(O.canonical_rank(ol, [32, 32, 1]))
+    x, w = t.features.detach().cpu(), conv.weight.detach().cpu()
+    oy = O.conv_forward(x, w, rules, len(ol))
+    assert rel(y.features[pg], oy[po]) <= TOL
+    dy = torch.randn_like(y.features)
+    y.features.backward(dy)
+    ody = torch.zeros_like(oy)
+    ody[po] = dy.cpu()[pg]
+    odx, odw, _ = O.conv_backward(x, ody, w, rules)
+    assert rel(conv.weight.grad, odw) <= TOL
+
+
+def test_network_in_network(scn):
+    t, _ = make_input(scn, _cloud(), [64, 64, 16], C=32)
+    nin = scn.NetworkInNetwork(32, 48, True).cuda()
+    nin.bias.data.normal_()
+    y = nin(t)
+    x = t.features.detach().cpu().requires_grad_(True)
+    want = x @ nin.weight.detach().cpu() + nin.bias.detach().cpu()
+    assert rel(y.features, want) <= TOL
+    dy = torch.randn_like(y.features)
+    y.features.backward(dy)
+    assert rel(nin.weight.grad, x.detach().t() @ dy.cpu()) <= TOL
+    assert rel(nin.bias.grad, dy.cpu().sum(0)) <= TOL
+
+
+@pytest.mark.parametrize("C", [9, 32, 64, 128, 256, 20])
+@pytest.mark.parametrize("leak", [0.0, 0.333])
+@pytest.mark.parametrize("n", [1000, 70001])
+def test_batchnorm_train(scn, C, leak, n):
+    torch.manual_seed(C + n)
+    x = (torch.randn(n, C) * 3 + 1).cuda().requires_grad_(True)
+    bn = scn.BatchNormLeakyReLU(C, momentum=0.95, leakiness=leak).cuda().train()
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    t = scn.SparseConvNetTensor(x, scn.Metadata(3), torch.tensor([8, 8, 8]))
+    y = bn(t).features
+    rm, rv = torch.zeros(C), torch.ones(C)
+    oy, sm, si = O.bn_forward(x.detach().cpu(), bn.weight.detach().cpu(), bn.bias.detach().cpu(), rm, rv, 1e-4,
+                              0.95, True, leak)
+    assert rel(y, oy) <= TOL
+    assert rel(bn.running_mean, rm) <= TOL and rel(bn.running_var, rv) <= TOL
+    dy = torch.randn_like(y)
+    dy0 = dy.clone()
+    y.backward(dy)
+    assert torch.equal(dy, dy0)          # unlike the reference, grad_output is not clobbered
+    odx, odw, odb = O.bn_backward(x.detach().cpu(), oy, dy.cpu(), sm, si, bn.weight.detach().cpu(), leak)
+    assert rel(x.grad, odx) <= TOL and rel(bn.weight.grad, odw) <= 5 * TOL and rel(bn.bias.grad, odb) <= 5 * TOL
+
+
+@pytest.mark.parametrize("track", [True, False])
+def test_batchnorm_eval(scn, track):
+    torch.manual_seed(3)
+    x = (torch.randn(5000, 64) * 2 - 1).cuda()
+    bn = scn.BatchNormReLU(64, momentum=0.95, track_running_stats=track).cuda().eval()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2)
+    t = scn.SparseConvNetTensor(x, scn.Metadata(3), torch.tensor([8, 8, 8]))
+    y = bn(t).features
+    xc = x.cpu()
+    rm, rv = (bn.running_mean.cpu(), bn.running_var.cpu()) if track else (xc.mean(0), xc.var(0))
+    oy, _, _ = O.bn_forward(xc, bn.weight.detach().cpu(), bn.bias.detach().cpu(), rm, rv, 1e-4, 0.95, False, 0.0)
+    assert rel(y, oy) <= TOL
+
+
+def test_sparse_to_dense(scn):
+    ss = [32, 32, 8]
+    c = _cloud(3000, (30, 28, 8))
+    t, _ = make_input(scn, c, ss, C=16)
+    d = scn.SparseToDense(3, 16)(t)
+    loc = t.get_spatial_locations().numpy()
+    want = O.sparse_to_dense(t.features.detach().cpu(), loc, ss, 2)
+    assert d.shape == want.shape and torch.equal(d.cpu(), want)
+    g = torch.randn_like(d)
+    (gx,) = torch.autograd.grad(d, t.features, g)
+    lt = torch.from_numpy(loc)
+    assert torch.equal(gx.cpu(), g.cpu()[lt[:, 3], :, lt[:, 0], lt[:, 1], lt[:, 2]])
+    d2 = scn.tools_3d_2d.sparse_3d_to_dense_2d(t)
+    mx = (loc.max(0) + 1).tolist()
+    assert list(d2.shape) == [2, 16, mx[0], mx[1], mx[2]]
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-free oracle: dense equivalence on fully active grids
+# ---------------------------------------------------------------------------------------------
+def test_dense_equivalence(scn):
+    S, B, cin, cout = 8, 2, 16, 32
+    g = torch.stack(torch.meshgrid(torch.arange(S), torch.arange(S), torch.arange(S), indexing="ij"), -1).reshape(-1, 3)
+    c = torch.cat([torch.cat([g, torch.full((len(g), 1), b)], 1) for b in range(B)])
+    c = c[torch.randperm(len(c), generator=torch.Generator().manual_seed(0))]
+    order = torch.argsort(c[:, 3], stable=True)
+    c = c[order]
+    t, _ = make_input(scn, c.numpy(), [S] * 3, C=cin)
+    dense = scn.SparseToDense(3, cin)(t)
+    sub = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
+    w = sub.weight.detach().view(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
+    assert rel(scn.SparseToDense(3, cout)(sub(t)), F.conv3d(dense, w, padding=1)) <= TOL
+    conv = scn.Convolution(3, cin, cout, 2, 2, False).cuda()
+    w = conv.weight.detach().view(2, 2, 2, cin, cout).permute(4, 3, 0, 1, 2)
+    y = conv(t)
+    assert rel(scn.SparseToDense(3, cout)(y), F.conv3d(dense, w, stride=2)) <= TOL
+    dec = scn.Deconvolution(3, cout, cin, 2, 2, False).cuda()
+    w = dec.weight.detach().view(2, 2, 2, cout, cin).permute(3, 4, 0, 1, 2)
+    assert rel(scn.SparseToDense(3, cin)(dec(y)), F.conv_transpose3d(scn.SparseToDense(3, cout)(y), w, stride=2)) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# whole backbone vs the reference's own fpn_net.py (golden)
+# ---------------------------------------------------------------------------------------------
+def _small_net(scn, g):
+    net = scn.FPN_Net([512] * 3, 3, ["xyz", "color", "normal"], 1, [8] + [16] * 8, nPlaneM=16,
+                      residual_blocks=True, fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
+                      downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8],
+                      rpn_map_sizes=[[32] * 3, [16] * 3, [8] * 3, [4] * 3], voxel_scale=50,
+                      rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95, track_running_stats=False)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    assert sorted(sd) == sorted(net.state_dict())            # state_dict keys identical to the reference
+    net.load_state_dict(sd)
+    return net.cuda()
+
+
+def test_backbone_matches_reference_golden(scn, gold):
+    g = gold("small_net")
+    net = _small_net(scn, g).train()
+    rpn, roi = net([torch.from_numpy(g["locs"]), torch.from_numpy(g["feats"]).cuda()])
+    loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= TOL * float(g["loss"])
+    for i, m in enumerate(list(rpn) + list(roi)):
+        loc = m.get_spatial_locations().numpy()
+        assert (np.diff(loc[:, 3]) >= 0).all()
+        order = np.argsort(O.canonical_rank(loc, m.spatial_size.tolist()))
+        assert np.array_equal(loc[order], g["out%d_loc" % i])
+        assert rel(m.features.detach().cpu()[order], g["out%d_feat" % i]) <= TOL
+    n = 0
+    for k, p in net.named_parameters():
+        if "grad/" + k in g.files:
+            assert p.grad is not None, k
+            assert rel(p.grad, g["grad/" + k]) <= 3 * TOL, k
+            n += 1
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    assert n > 40
+    for k, v in net.state_dict().items():
+        if "running_" in k and "after/" + k in g.files:
+            assert rel(v, g["after/" + k]) <= TOL, k
+    ge = gold("small_net_eval")
+    net.eval()
+    with torch.no_grad():
+        rpn, roi = net([torch.from_numpy(g["locs"]), torch.from_numpy(g["feats"]).cuda()])
+    for i, m in enumerate(list(rpn) + list(roi)):
+        order = np.argsort(O.canonical_rank(m.get_spatial_locations().numpy(), m.spatial_size.tolist()))
+        assert rel(m.features.cpu()[order], ge["out%d_feat" % i]) <= TOL
