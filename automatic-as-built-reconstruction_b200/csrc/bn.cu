@@ -262,6 +262,7 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   if (n == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, out, in, out);
+  prof_begin(PROF_BN, s);
   float *coef = nullptr;
   SCN_TRY(dev_alloc_t(&coef, (size_t)3 * C, s));
   if (train) {
@@ -293,6 +294,7 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   else k_bn_fwd_apply<false><<<apply_grid(total), BN_T, 0, s>>>(in, out, coef, leakiness, total, C);
   SCN_LAUNCHED();
   dev_free(coef, s);
+  prof_end(PROF_BN, s, (train ? 3.0 : 2.0) * 4.0 * (double)n * C, 0);  // 3 n C s
   return 0;
 }
 
@@ -310,6 +312,7 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   }
   SCN_CHECK(in && d_in && out && d_out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0);
+  prof_begin(PROF_BN, s);
   float *coef = nullptr;
   double *part = nullptr;
   SCN_TRY(dev_alloc_t(&coef, (size_t)3 * C, s));
@@ -338,6 +341,7 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   SCN_LAUNCHED();
   dev_free(part, s);
   dev_free(coef, s);
+  prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;
 }
 

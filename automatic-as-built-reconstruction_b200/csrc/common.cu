@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <mutex>
+#include <vector>
 #include "../../include/scn_b200.h"
 
 namespace scn {
@@ -14,6 +15,34 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- profiling regions ----------------------------------------------------------------------
+bool g_prof_on = false;
+struct ProfSeg { int cls; cudaEvent_t a, b; double bytes, flops; };
+static std::vector<ProfSeg> g_prof_segs;
+static std::vector<cudaEvent_t> g_prof_open[PROF_N];
+static std::mutex g_prof_mu;
+
+void prof_begin_(int cls, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_prof_open[cls].push_back(e);
+}
+void prof_end_(int cls, cudaStream_t s, double bytes, double flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_open[cls].empty()) return;
+  ProfSeg sg;
+  sg.cls = cls;
+  sg.a = g_prof_open[cls].back();
+  g_prof_open[cls].pop_back();
+  cudaEventCreate(&sg.b);
+  cudaEventRecord(sg.b, s);
+  sg.bytes = bytes;
+  sg.flops = flops;
+  g_prof_segs.push_back(sg);
 }
 
 static std::once_flag g_pool_once;
@@ -239,6 +268,28 @@ const char *scn_last_error(void) { return scn::g_err; }
 int scn_version(void) { return 100; }
 int scn_n_rulebook_bits(void) { return 32; }
 int64_t scn_launch_count(void) { return scn::g_launches.load(); }
+int scn_prof_enable(int on) {
+  scn::g_prof_on = on != 0;
+  return 0;
+}
+int scn_prof_read(int cls, double out[4]) {
+  using namespace scn;
+  SCN_CHECK(cls >= 0 && cls < PROF_N && out, "bad profile class %d", cls);
+  SCN_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  out[0] = out[1] = out[2] = out[3] = 0;
+  std::vector<ProfSeg> keep;
+  for (auto &sg : g_prof_segs) {
+    if (sg.cls != cls) { keep.push_back(sg); continue; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sg.a, sg.b);
+    out[0] += 1; out[1] += ms; out[2] += sg.bytes; out[3] += sg.flops;
+    cudaEventDestroy(sg.a);
+    cudaEventDestroy(sg.b);
+  }
+  g_prof_segs.swap(keep);
+  return 0;
+}
 int scn_scale_inplace(float *y, float alpha, int64_t n, void *stream) {
   if (n <= 0) return 0;
   int nb = scn::cdiv(n, 256);

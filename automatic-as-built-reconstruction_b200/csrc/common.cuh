@@ -60,6 +60,18 @@ inline int dev_alloc_t(T **p, size_t n, cudaStream_t s) {
 // pinned host scratch for count read-backs (per thread)
 int64_t *host_scratch(size_t n_int64);
 
+// ---- optional per-kernel-class timing (bench.py roofline; off by default) --------------------
+// A profiled region is bracketed by CUDA events on the launching stream; scn_prof_read sums the
+// elapsed times and the ALGORITHMIC bytes / flops the callers attribute to each region.
+enum ProfClass { PROF_GEMM = 0, PROF_DW = 1, PROF_BN = 2, PROF_RULES = 3, PROF_IO = 4, PROF_N = 5 };
+extern bool g_prof_on;
+void prof_begin_(int cls, cudaStream_t s);
+void prof_end_(int cls, cudaStream_t s, double bytes, double flops);
+static inline void prof_begin(int cls, cudaStream_t s) { if (g_prof_on) prof_begin_(cls, s); }
+static inline void prof_end(int cls, cudaStream_t s, double bytes, double flops) {
+  if (g_prof_on) prof_end_(cls, s, bytes, flops);
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();
 

@@ -221,12 +221,21 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
            const TileBook &tb, int precision, cudaStream_t s) {
   if (tb.n_tiles == 0) return 0;
   const TileView tv = make_view(tb);
-  if (precision != SCN_PRECISION_FP32) {
-    int r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, s);
-    if (r <= 0) return -r;  // 0 = done, negative = error code; positive = shape not supported
+  prof_begin(PROF_GEMM, s);
+  int r = 1;
+  if (precision != SCN_PRECISION_FP32)
+    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, s);
+  if (r > 0) {  // 0 = done, negative = -(error); positive = shape not handled by the tensor path
+    r = Cout <= 32 ? launch_osgemm_ffma<32>(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, s)
+                   : launch_osgemm_ffma<64>(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, s);
+  } else {
+    r = -r;
   }
-  if (Cout <= 32) return launch_osgemm_ffma<32>(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, s);
-  return launch_osgemm_ffma<64>(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, s);
+  // algorithmic bytes: every feature row once, the weights once, 8 B per pair
+  const double bytes = 4.0 * ((double)tb.n_partner * Cin + (double)tb.n_rows * Cout) +
+                       4.0 * tb.K * Cin * Cout + (tb.identity ? 0.0 : 8.0 * tb.n_pairs);
+  prof_end(PROF_GEMM, s, bytes, 2.0 * tb.n_pairs * Cin * Cout);
+  return r;
 }
 
 // Wt[k][co][ci] = W[k][ci][co]
@@ -402,9 +411,13 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
     }
     first.v[K] = w;
   }
+  prof_begin(PROF_DW, s);
+  const double dw_bytes = 4.0 * ((double)rb->n_in * (xcol ? Cout : Cin) + (double)rb->n_out * (xcol ? Cin : Cout)) +
+                          4.0 * K * cc + (rb->identity ? 0.0 : 8.0 * rb->total_pairs);
+  const double dw_flops = 2.0 * rb->total_pairs * cc;
   if (precision != SCN_PRECISION_FP32 && n_work > 0) {
     int r = weight_grad_tc(X, dY, dW, Cin, Cout, rb, xcol, ycol, precision, s);
-    if (r <= 0) return -r;
+    if (r <= 0) { prof_end(PROF_DW, s, dw_bytes, dw_flops); return -r; }
   }
   float *partial = nullptr;
   if (n_work > 0) {
@@ -421,6 +434,7 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
   k_dw_reduce<<<grid, 256, 0, s>>>(partial, dW, first, cc);
   SCN_LAUNCHED();
   dev_free(partial, s);
+  prof_end(PROF_DW, s, dw_bytes, dw_flops);
   return 0;
 }
 

@@ -217,6 +217,7 @@ static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t
   SCN_CHECK(n >= 0 && n < (1LL << 30), "too many input points: %lld", (long long)n);
   metadata_clear(m, s);
   m->last_stream = s;
+  prof_begin(PROF_RULES, s);
   Grid *g = new Grid();
   memcpy(g->ss, ss, sizeof(g->ss));
   m->grids.push_back(g);
@@ -316,6 +317,7 @@ static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t
   ir.stat = stat;  // owned by the InputRules from here on
   dev_free(pslot, s);
   dev_free(staged, s);
+  prof_end(PROF_RULES, s, (double)n * ncols * 8 + 12.0 * g->n_active + 8.0 * n, 0);
   *n_active_out = g->n_active;
   return 0;
 }
@@ -503,6 +505,7 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
     SCN_LAUNCHED();
   }
   SCN_TRY(tilebook_phase2(rb->tb_out, rb->t_out, h32[K + 1], s));
+  rb->tb_out.n_pairs = rb->total_pairs;
   dev_free(pos, s);
   dev_free(meta, s);
   return 0;
@@ -537,6 +540,7 @@ int ensure_tilebook(RuleBook *rb, bool stationary_out, cudaStream_t s) {
     tb.n_rows = rb->n_out;
     tb.n_partner = rb->n_in;
     tb.n_tiles = cdiv(rb->n_out, TILE_M);
+    tb.n_pairs = rb->n_out;
     tb.built = true;
     return 0;
   }
@@ -549,6 +553,7 @@ int ensure_tilebook(RuleBook *rb, bool stationary_out, cudaStream_t s) {
   SCN_CUDA(cudaMemcpyAsync(h32, meta, 4, cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back (first backward use only)
   SCN_TRY(tilebook_phase2(tb, rb->t_in, h32[0], s));
+  tb.n_pairs = rb->total_pairs;
   dev_free(meta, s);
   return 0;
 }
@@ -622,6 +627,7 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
   }
   const long long total = (long long)rb->K * g->n_active;
   SCN_CHECK(total < (1LL << 31), "submanifold table too large");
+  prof_begin(PROF_RULES, s);
   SCN_TRY(dev_alloc_t(&rb->t_out, (size_t)total, s));
   if (total > 0) {
     Filter3 f;
@@ -631,6 +637,8 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
     SCN_LAUNCHED();
   }
   SCN_TRY(finish_rulebook(rb, s));
+  // algorithmic bytes: K probes x 12 B + one 12 B entry per site
+  prof_end(PROF_RULES, s, (double)g->n_active * (12.0 + 12.0 * rb->K), 0);
   *out = rb;
   return 0;
 }
@@ -795,6 +803,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   memset(rb->pair_off, 0, sizeof(rb->pair_off));
   m->rulebooks.push_back(rb);
 
+  prof_begin(PROF_RULES, s);
   SCN_TRY(grid_alloc_table(go, total, 0x7F, s));
   int32_t *pslot = nullptr, *rank = nullptr;
   SCN_TRY(dev_alloc_t(&pslot, (size_t)total, s));
@@ -856,6 +865,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   dev_free(pslot, s);
   dev_free(rank, s);
   SCN_TRY(finish_rulebook(rb, s));
+  prof_end(PROF_RULES, s, (double)n_in * (12.0 + 12.0 * R) + 12.0 * n_out, 0);
   *out = rb;
   return 0;
 }

@@ -31,6 +31,7 @@ struct TileBook {
   int64_t n_partner = 0;          // rows of the gathered side
   int n_tiles = 0;
   int64_t n_entries = 0;
+  int64_t n_pairs = 0;            // (in,out) pairs behind the lists (algorithmic-bytes accounting)
   int32_t *perm = nullptr;        // [n_tiles*TILE_M] stationary row per slot (-1 pad)
   uint32_t *tile_mask = nullptr;  // [n_tiles] union of active offsets
   int32_t *tile_off = nullptr;    // [n_tiles+1] first entry of the tile

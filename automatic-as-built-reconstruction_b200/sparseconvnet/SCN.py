@@ -362,3 +362,20 @@ def SparseToDense_updateGradInput(spatial_size, m, input_features, d_input_featu
 def launch_count():
     """kernels launched by libscn_b200 since load (bench.py `gpu_launches`)"""
     return int(lib.scn_launch_count())
+
+
+PROF_CLASSES = ("conv_gemm", "weight_grad", "batchnorm", "rulebook", "io")
+
+
+def prof_enable(on):
+    check(lib.scn_prof_enable(1 if on else 0))
+
+
+def prof_read():
+    """{class: dict(regions, ms, bytes, flops)} accumulated since the last read (synchronises)"""
+    out = {}
+    for i, name in enumerate(PROF_CLASSES):
+        v = (c_double * 4)()
+        check(lib.scn_prof_read(i, v))
+        out[name] = {"regions": int(v[0]), "ms": v[1], "bytes": v[2], "flops": v[3]}
+    return out

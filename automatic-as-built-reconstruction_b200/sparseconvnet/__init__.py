@@ -19,6 +19,7 @@ from . import (batchNormalization, convolution, deconvolution, identity, ioLayer
 from .fpn_net import FPN_Net  # noqa: E402
 from . import tools_3d_2d  # noqa: E402
 from .voxelize import quantize_points  # noqa: E402
+from .data_parallel import GradBucket, broadcast_parameters, shard_indices  # noqa: E402
 
 
 def _off_path(name):

@@ -1,0 +1,371 @@
+"""bench.py - the sparse3d backbone (FPN_Net) forward+backward on synthetic SUNCG-shaped buildings.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch: fresh Metadata (voxel hashing + every rulebook
+rebuilt, as in real training), FPN_Net forward, loss = sum(features^2) over the 6 rpn + 2 roi maps,
+backward (live graph only) and, for N > 1, the gradient all-reduce over NCCL.  Workload at N=1 is
+BASELINE.json configs[1]: one 300k-point building, batch 1 (SURVEY.md section 8d generator).
+Metric: active voxels/s (sum over samples of nActive at scale 0 / time), whole job over all GPUs.
+
+  value     inputs resident in HBM when the timed region starts
+  e2e       same step through the public API from pinned HOST buffers (coords + features H2D and a
+            D2H read of the loss inside the timed region)
+  roofline  conv gather-GEMM class: algorithmic bytes (SURVEY.md 8d formula) / CUDA-event time of
+            those launches, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the compiled reference CPU SparseConvNet (oracle/_ref) driving
+            the same graph on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "automatic-as-built-reconstruction_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FULL_SCALE = [4096, 4096, 512]
+PLANES = [32, 64, 64, 128, 128, 128, 256, 256, 256]
+RPN_SIZES = [[256, 256, 32], [128, 128, 16], [64, 64, 8], [32, 32, 4]]
+
+
+# ---- synthetic input (benchmark-input spec of SURVEY.md Appendix D.3; not product code) ---------
+def building(n, L=(19.0, 16.3, 3.0), floors=1, seed=0):
+    rng = np.random.RandomState(seed)
+    L = np.array(L)
+    pts = []
+    per = n // (6 * floors)
+    for f in range(floors):
+        z0 = f * L[2]
+        for z in (z0, z0 + L[2] - 1e-3):
+            p = rng.rand(per, 3) * L
+            p[:, 2] = z
+            pts.append(p)
+        k = got = 0
+        while got < 4 * per:
+            m = per // 2
+            p = rng.rand(m, 3) * L
+            p[:, 2] += z0
+            if k % 2 == 0:
+                p[:, 0] = (k // 2 % 5) * (L[0] - 1e-3) / 4
+            else:
+                p[:, 1] = (k // 2 % 5) * (L[1] - 1e-3) / 4
+            pts.append(p)
+            k += 1
+            got += m
+    p = np.concatenate(pts)
+    if len(p) < n:
+        p = np.concatenate([p, p[:n - len(p)]])
+    return p[:n]
+
+
+def to_input(xyz_list, scale=50, full=FULL_SCALE, seed=0):
+    torch.manual_seed(seed)
+    locs, feats = [], []
+    for b, xyz in enumerate(xyz_list):
+        a = xyz * scale
+        a -= a.min(0)
+        a = a[(a < np.array(full)[None]).all(1)]
+        l = torch.from_numpy(a).long()
+        locs.append(torch.cat([l, torch.full((len(l), 1), b, dtype=torch.long)], 1))
+        f = torch.randn(len(l), 9)
+        f[:, 0:3] = torch.from_numpy(a / scale).float()
+        feats.append(f)
+    return torch.cat(locs), torch.cat(feats)
+
+
+def make_batch(points, floors, batch, first_seed):
+    return to_input([building(points, floors=floors, seed=first_seed + i) for i in range(batch)])
+
+
+def n_active0(locs):
+    k = ((locs[:, 3] * 4096 + locs[:, 0]) * 4096 + locs[:, 1]) * 512 + locs[:, 2]
+    return int(torch.unique(k).numel())
+
+
+# ---- clocks ---------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- reference (CPU) arm -----------------------------------------------------------------------------
+def reference_state_dict():
+    """random-init weights of the full-size architecture, built without touching the GPU library"""
+    torch.manual_seed(0)
+    sd = {}
+
+    def conv(key, k, a, b):
+        sd[key + ".weight"] = torch.empty(k, 1, a, b).normal_(0, (2.0 / a / k) ** 0.5)
+
+    def bn(key, c):
+        sd[key + ".weight"], sd[key + ".bias"] = torch.ones(c), torch.zeros(c)
+        sd[key + ".running_mean"], sd[key + ".running_var"] = torch.zeros(c), torch.ones(c)
+
+    def block(key, c):
+        bn(key + ".1.0", c), conv(key + ".1.1", 27, c, c), bn(key + ".1.2", c), conv(key + ".1.3", 27, c, c)
+
+    conv("layers_in.1", 27, 9, PLANES[0])
+    for k, c in enumerate(PLANES):
+        if k == 0:
+            block("m_downs.0.0", c)
+        else:
+            bn("m_downs.%d.0.0" % k, PLANES[k - 1]), conv("m_downs.%d.0.1" % k, 8, PLANES[k - 1], c)
+            block("m_downs.%d.1" % k, c)
+        conv("m_shortcuts.%d" % k, 1, c, 128)
+    for k in range(8):
+        bn("m_ups.%d.0" % k, 128), conv("m_ups.%d.1" % k, 8, 128, 128), conv("m_mergeds.%d" % k, 27, 128, 128)
+    for i, s in enumerate(RPN_SIZES):
+        conv("convs_pro2d.%d" % i, s[2], 128, 128)
+    return sd
+
+
+def cpu_reference_step(sd, locs, feats):
+    """one fwd+bwd of the compiled reference CPU path (fresh Metadata); returns seconds"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_backbone as RB
+    net = RB.RefBackbone(sd, full_scale=FULL_SCALE, n_planes=PLANES, rpn_map_sizes=RPN_SIZES)
+    t0 = time.perf_counter()
+    rpn, roi = net.forward(locs, feats)
+    RB.backbone_loss(rpn, roi).backward()
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    points = args.points if (args.steps + args.warmup) <= 8 else min(args.points, 60000)
+    locs, feats = make_batch(points, args.floors, args.batch, 0)
+    na = n_active0(locs)
+    sd = reference_state_dict()
+    sample = "%d building(s) x %d points (nActive %d), fwd+bwd, fresh Metadata each step" % (args.batch, points, na)
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, locs, feats)
+    ts = [cpu_reference_step(sd, locs, feats) for _ in range(args.steps)]
+    sec = float(np.mean(ts))
+    val = na / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "active_voxels_per_sec", "value": val, "unit": "active voxels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "buildings_per_sec": args.batch / sec,
+        "config": workload_config(args, points),
+        "cpu_baseline": {"value": val, "unit": "active voxels/s", "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "active voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, points=None):
+    return {"workload": "FPN_Net sparse3d backbone fwd+bwd, %d x %dk-point synthetic building per GPU "
+                        "(BASELINE configs[1])" % (args.batch, (points or args.points) // 1000),
+            "per_gpu_batch": args.batch, "points_per_building": points or args.points, "floors": args.floors,
+            "full_scale": FULL_SCALE, "planes": PLANES, "precision": args.precision,
+            "parallelism": "dp%d" % args.gpus,
+            "l2": "256 MiB flush buffer written between steps; per-step activations (GBs) exceed the 126 MB L2"}
+
+
+# ---- B200 arm --------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import sparseconvnet as scn
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scn.set_conv_precision(args.precision)
+    torch.manual_seed(0)
+    net = scn.FPN_Net(FULL_SCALE, 3, ["xyz", "color", "normal"], 1, PLANES, nPlaneM=128, residual_blocks=True,
+                      fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
+                      downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8], rpn_map_sizes=RPN_SIZES, voxel_scale=50,
+                      rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95, track_running_stats=False)
+    net = net.to(dev).train()
+    scn.broadcast_parameters(net)
+    bucket = scn.GradBucket(net.parameters())
+    locs, feats = make_batch(args.points, args.floors, args.batch, rank * args.batch)   # weak scaling
+    na_local = n_active0(locs)
+    locs_pin, feats_pin = locs.pin_memory(), feats.pin_memory()
+    locs_dev, feats_dev = locs.to(dev), feats.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(coords, f):
+        bucket.zero()
+        rpn, roi = net([coords, f])
+        loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
+        loss.backward()
+        bucket.allreduce_mean()
+        return loss
+
+    def timed(n_steps, host_inputs):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = scn.SCN.launch_count()
+        a.record()
+        for _ in range(n_steps):
+            flush.fill_(1)
+            if host_inputs:
+                loss = step(locs_pin, feats_pin.to(dev, non_blocking=True))
+                loss.item()                                   # D2H read of the step's result
+            else:
+                step(locs_dev, feats_dev)
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), scn.SCN.launch_count() - l0
+
+    for _ in range(args.warmup):
+        step(locs_dev, feats_dev)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, launches = timed(args.steps, False)
+    clk = clocks.stop() if rank == 0 else None
+    step(locs_pin, feats_pin.to(dev, non_blocking=True))
+    ms_e2e, _ = timed(args.steps, True)
+
+    na_t = torch.tensor([na_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(na_t)
+    na_total = float(na_t.item())
+
+    # per-kernel-class roofline pass (CUDA events around each launch group, outside the headline timing)
+    scn.SCN.prof_enable(True)
+    scn.SCN.prof_read()
+    for _ in range(2):
+        flush.fill_(1)
+        step(locs_dev, feats_dev)
+    prof = scn.SCN.prof_read()
+    scn.SCN.prof_enable(False)
+
+    if rank == 0:
+        peaks = {}
+        src = "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            src = "measured"
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        g = prof["conv_gemm"]
+        ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("conv_gemm")
+        except (OSError, ValueError):
+            pass
+        classes = {k: {"launch_groups": v["regions"] // 2, "ms_per_step": v["ms"] / 2,
+                       "algorithmic_gb_per_step": v["bytes"] / 2 / 1e9,
+                       "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None,
+                       "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None}
+                   for k, v in prof.items()}
+        sec = ms * 1e-3 / args.steps
+        sec_e2e = ms_e2e * 1e-3 / args.steps
+        out = {
+            "metric": "active_voxels_per_sec", "value": na_total / sec, "unit": "active voxels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16": "bf16", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
+            "buildings_per_sec": args.batch * world / sec, "active_voxels_per_building": na_local / args.batch,
+            "config": workload_config(args),
+            "e2e": {"value": na_total / sec_e2e, "unit": "active voxels/s", "ms_per_step": sec_e2e * 1e3,
+                    "h2d_bytes_per_step": int(locs.numel() * 8 + feats.numel() * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "conv gather-GEMM (fwd + dX), all launches of a step",
+                         "achieved": ach, "peak": hbm_peak, "peak_source": src + " (sustained copy)",
+                         "unit": "GB/s", "frac": ach / hbm_peak if hbm_peak else None, "traffic": traffic,
+                         "launches_per_step": g["regions"] // 2, "ms_per_step": g["ms"] / 2},
+            "kernel_classes": classes,
+            "grad_allreduce_bytes": bucket.nbytes() if world > 1 else 0,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            torch.set_num_threads(cores)
+            sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+            t = cpu_reference_step(sd, locs, feats)
+            out["cpu_baseline"] = {"value": na_local / t, "unit": "active voxels/s", "cores": cores,
+                                   "kind": "reference", "seconds_per_step": t,
+                                   "sample": "1 step (same %d-point batch, nActive %d) fwd+bwd on the compiled "
+                                             "reference CPU SparseConvNet, fresh Metadata, no warm-up"
+                                             % (len(locs), na_local)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="buildings per GPU")
+    ap.add_argument("--points", type=int, default=300000)
+    ap.add_argument("--floors", type=int, default=1)
+    ap.add_argument("--precision", default=os.environ.get("SCN_B200_PRECISION", "fp32"),
+                    choices=["fp32", "bf16", "tf32x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -208,6 +208,12 @@ int scn_scale_inplace(float *y, float alpha, int64_t n, void *stream);
 /* ---- instrumentation --------------------------------------------------------------- */
 /* number of kernels this library has launched since load (bench.py "gpu_launches") */
 int64_t scn_launch_count(void);
+/* per-kernel-class timing for the roofline report: when enabled every region of class `cls`
+ * (0 conv gather-GEMM fwd/dX, 1 weight gradient, 2 batch-norm, 3 hash/rulebook build,
+ * 4 input/output/sparse-to-dense) is bracketed by CUDA events on its stream.  scn_prof_read
+ * synchronises, returns out = [regions, total ms, algorithmic bytes, flops] and clears them. */
+int scn_prof_enable(int on);
+int scn_prof_read(int cls, double out[4]);
 /* tile-book statistics of a cached rulebook: stats[0]=pairs, [1]=tile entries*128 (rows the
  * tensor/FFMA tiles actually multiply), [2]=tiles.  kind: 0 submanifold, 1 conv, 2 deconv,
  * 3 conv-dX (fine<-coarse), 4 deconv-dX */
