@@ -218,16 +218,25 @@ TileView make_view(const TileBook &tb) {
 
 // Y[stationary rows] = bias + sum_k X[partner_k] @ W[k]   (W: [K,Cin,Cout] row-major)
 int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
-           const TileBook &tb, int precision, cudaStream_t s) {
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s) {
   if (tb.n_tiles == 0) return 0;
   const TileView tv = make_view(tb);
   prof_begin(PROF_GEMM, s);
   int r = 1;
   if (precision != SCN_PRECISION_FP32)
-    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, s);
-  if (r > 0) {  // 0 = done, negative = -(error); positive = shape not handled by the tensor path
-    r = Cout <= 32 ? launch_osgemm_ffma<32>(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, s)
-                   : launch_osgemm_ffma<64>(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, s);
+    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s);
+  if (r > 0) {  // 0 = done, negative = -(error); positive = shape outside the tensor path (e.g. Cin = 9)
+    float *wt = nullptr;
+    r = 0;
+    if (transpose_w) {
+      r = dev_alloc_t(&wt, (size_t)tb.K * Cin * Cout, s);
+      if (!r) r = transpose_weights(W, wt, tb.K, Cout, Cin, s);   // W is [K][Cout=N][Cin=Kd] -> [K][Kd][N]
+    }
+    const float *w = transpose_w ? wt : W;
+    if (!r)
+      r = Cout <= 32 ? launch_osgemm_ffma<32>(X, w, bias, Y, Cin, Cout, tb.n_rows, tv, s)
+                     : launch_osgemm_ffma<64>(X, w, bias, Y, Cin, Cout, tb.n_rows, tv, s);
+    dev_free(wt, s);
   } else {
     r = -r;
   }
@@ -472,14 +481,7 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
                                 long long n_dout_rows, int precision, cudaStream_t s) {
   SCN_TRY(ensure_tilebook(rb, dx_stationary_out, s));
   TileBook &tb = dx_stationary_out ? rb->tb_out : rb->tb_in;
-  if (d_in) {
-    float *wt = nullptr;
-    SCN_TRY(dev_alloc_t(&wt, (size_t)rb->K * Cin * Cout, s));
-    SCN_TRY(transpose_weights(weight, wt, rb->K, Cin, Cout, s));
-    int r = osgemm(d_out, wt, nullptr, d_in, Cout, Cin, tb, precision, s);
-    dev_free(wt, s);
-    if (r) return r;
-  }
+  if (d_in) SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s));
   if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, s));
   SCN_TRY(bias_grad(d_out, d_bias, n_dout_rows, Cout, s));
   return 0;
@@ -502,7 +504,7 @@ int scn_submanifold_conv_forward(scn_metadata_t *m, const int64_t *ss, const int
   if (macs) *macs = macs_of(rb, cin, cout);
   if (rb->n_out == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, s);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, 0, s);
 }
 
 int scn_submanifold_conv_backward(scn_metadata_t *m, const int64_t *ss, const int64_t *filter,
@@ -531,7 +533,7 @@ int scn_conv_forward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out
   SCN_TRY(get_conv_rulebook(m, in_ss, out_ss, filter, stride, s, &rb));
   if (macs) *macs = macs_of(rb, cin, cout);
   if (rb->n_out == 0) return 0;
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, s);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, 0, s);
 }
 
 int scn_conv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
@@ -563,7 +565,7 @@ int scn_deconv_forward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *o
   if (macs) *macs = macs_of(rb, cin, cout);
   if (rb->n_in == 0) return 0;
   SCN_TRY(ensure_tilebook(rb, false, s));
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_in, precision, s);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_in, precision, 0, s);
 }
 
 int scn_deconv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
@@ -592,7 +594,7 @@ int scn_nin_forward(const float *in, float *out, const float *weight, const floa
   tb.identity = true; tb.built = true; tb.K = 1;
   tb.n_rows = tb.n_partner = n_rows;
   tb.n_tiles = cdiv(n_rows, TILE_M);
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, tb, precision, (cudaStream_t)stream);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, tb, precision, 0, (cudaStream_t)stream);
 }
 
 int scn_nin_backward(const float *in, float *d_in, const float *d_out, const float *weight,

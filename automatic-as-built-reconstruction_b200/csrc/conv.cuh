@@ -15,14 +15,16 @@ struct TileView {            // device view of a TileBook, passed by value to ke
 
 TileView make_view(const TileBook &tb);
 
-// Y[stationary] = bias + sum_k X[partner_k] @ W[k]; W is [K,Cin,Cout] row-major fp32.
-int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
-           const TileBook &tb, int precision, cudaStream_t s);
+// Y[stationary] = bias + sum_k X[partner_k] @ Wg[k]; Kd = reduction width (row width of X), N = row
+// width of Y.  transpose_w = 0: Wg[k] = W[k] with W [K,Kd,N]; transpose_w = 1: Wg[k] = W[k]^T with
+// W [K,N,Kd] (the dX pass reads the forward weights in place).
+int osgemm(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s);
 
 // tensor-core variants. Return 0 = done, >0 = shape/precision not handled (caller uses the FFMA
 // kernels), <0 = -(error) with scn_last_error set.
-int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
-              long long n_rows, const TileView &tv, int K, int precision, cudaStream_t s);
+int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
+              long long n_rows, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s);
 int weight_grad_tc(const float *X, const float *dY, float *dW, int Cin, int Cout, RuleBook *rb,
                    int xcol, int ycol, int precision, cudaStream_t s);
 

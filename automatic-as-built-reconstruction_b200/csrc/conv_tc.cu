@@ -1,10 +1,345 @@
-// conv_tc.cu - tcgen05 / TMEM gather-GEMM (bf16 and 3xTF32).  Placeholder until the tensor
-// core kernels land: reports "not handled" so callers use the exact-fp32 FFMA tiles.
+// conv_tc.cu - tcgen05 / TMEM gather-GEMM for the sparse convolutions (sm_100a only).
+//
+// Same contraction as conv.cu (reference: CPU/Convolution.cpp:46-185, CPU/Deconvolution.cpp:8-77)
+//   Y[stationary rows] = bias + sum_k X[partner_k rows] @ W[k]
+// executed on the 5th-generation tensor cores:
+//   * one CTA owns a tile of 128 stationary rows; the fp32 accumulator [128 x N] lives in TMEM;
+//   * for every kernel offset active in the tile and every 32-wide slice of the reduction dim, the
+//     128 partner rows are GATHERED straight from global memory into shared memory with 16-byte
+//     cp.async (zero-fill where a row has no partner) in the canonical K-major no-swizzle UMMA
+//     layout, while the matching weight slice - pre-packed into the same layout by k_pack_weights -
+//     arrives as one cp.async.bulk (TMA, mbarrier complete_tx);
+//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=Cout, K=8) on the staged slices and
+//     tcgen05.commit releases the stage; a 3-stage ring keeps gathers of step s+1/s+2 in flight
+//     while the tensor core works on step s;
+//   * epilogue: tcgen05.ld TMEM -> registers -> (+bias) -> each stationary row written exactly once.
+// fp32 features are fed unconverted (kind::tf32 reads the upper 19 bits); weights are rounded to
+// tf32 when packed.  Accumulation is fp32.
 #include "conv.cuh"
+#include "../../include/scn_b200.h"
 
 namespace scn {
-int osgemm_tc(const float *, const float *, const float *, float *, int, int, long long,
-              const TileView &, int, int, cudaStream_t) { return 1; }
-int weight_grad_tc(const float *, const float *, float *, int, int, RuleBook *, int, int, int,
-                   cudaStream_t) { return 1; }
+namespace tc {
+
+constexpr int KC = 32;                      // reduction elements per pipeline step
+constexpr int NCORE = KC / 4;               // 16-byte k-cores (4 tf32) per step
+constexpr int A_LBO = TILE_M * 16 + 16;     // bytes between k-cores of A (+16: bank spread for the gather)
+constexpr int A_STAGE = NCORE * A_LBO;      // 16512
+constexpr int NS = 3;                       // pipeline stages
+constexpr int NT = 256;                     // threads
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// leading byte offset>>4 [16,30), stride byte offset>>4 [32,46), version=1 [46,48), layout [61,64)=0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major (or MN-major
+// when the flags are set), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: W fp32 [K][Cin][Cout] -> Wp[k][chunk c][k-core j][n][4], the exact shared-memory
+// image of the K-major B operand.  transpose=0: reduction dim = Cin, n = Cout (forward);
+// transpose=1: reduction dim = Cout, n = Cin (dX = dY @ W[k]^T).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ Wp, int K, int Cin, int Cout,
+                               int transpose) {
+  const int Kd = transpose ? Cout : Cin, N = transpose ? Cin : Cout;
+  const long long per_k = (long long)Kd * N;
+  const long long total = (long long)K * per_k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i / per_k);
+    long long r = i - (long long)k * per_k;
+    // destination order inside offset k: chunk c, core j, column n, element t
+    const int c = (int)(r / ((long long)KC * N));
+    r -= (long long)c * KC * N;
+    const int j = (int)(r / (4 * N));
+    r -= (long long)j * 4 * N;
+    const int n = (int)(r >> 2), t = (int)(r & 3);
+    const int kk = c * KC + j * 4 + t;
+    const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
+    Wp[i] = to_tf32(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the gather-GEMM kernel
+// ---------------------------------------------------------------------------------------------
+struct Smem {
+  // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
+  int a, b, idx, perm, kofs, bars, tmem_slot, total;
+  __host__ __device__ Smem(int N, int K) {
+    a = 0;
+    b = a + NS * A_STAGE;
+    idx = b + NS * NCORE * N * 16;
+    perm = idx + K * TILE_M * 4;
+    kofs = perm + TILE_M * 4;
+    bars = kofs + 64;
+    tmem_slot = bars + (2 * NS + 1) * 8;
+    total = tmem_slot + 16;
+  }
+};
+
+__global__ void __launch_bounds__(NT)
+k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
+              float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const Smem L(N, K);
+  int32_t(*sIdx)[TILE_M] = reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.idx);
+  int32_t *sPerm = reinterpret_cast<int32_t *>(smem + L.perm);
+  int8_t *sK = reinterpret_cast<int8_t *>(smem + L.kofs);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
+  const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
+  const uint32_t bar_full = smem_u32(smem + L.bars);            // [NS] weight slice landed
+  const uint32_t bar_empty = bar_full + NS * 8;                 // [NS] MMAs that read the stage retired
+  const uint32_t bar_done = bar_empty + NS * 8;                 // accumulator complete
+  const int B_STAGE = NCORE * N * 16;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+
+  // ---- tile book-keeping ------------------------------------------------------------------
+  int nE;
+  if (tb.identity) {
+    nE = 1;
+    if (tid < TILE_M) {
+      const long long r = (long long)tile * TILE_M + tid;
+      const int v = r < n_rows ? (int)r : -1;
+      sPerm[tid] = v;
+      sIdx[0][tid] = v;
+    }
+    if (tid == 0) sK[0] = 0;
+  } else {
+    const uint32_t mask = tb.tile_mask[tile];
+    const int e0 = tb.tile_off[tile];
+    nE = __popc(mask);
+    if (tid < TILE_M) sPerm[tid] = tb.perm[(long long)tile * TILE_M + tid];
+    for (int i = tid; i < nE * TILE_M; i += NT) sIdx[i / TILE_M][i % TILE_M] = tb.entries[(long long)e0 * TILE_M + i];
+    if (tid < 32 && (mask & (1u << tid))) sK[__popc(mask & ((1u << tid) - 1u))] = (int8_t)tid;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NS + 1; ++i) mbar_init(bar_full + i * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int kchunks = (Kd + KC - 1) / KC;
+  const int steps = nE * kchunks;
+  const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
+
+  auto issue = [&](int st) {
+    const int stage = st % NS;
+    const int e = st / kchunks, c = st - e * kchunks;
+    const int ncore = min(NCORE, (Kd - c * KC) >> 2);
+    const int j = tid & 7;
+    if (j < ncore) {
+      const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
+      const float *colp = X + c * KC + j * 4;
+#pragma unroll
+      for (int i = 0; i < TILE_M / 32; ++i) {
+        const int row = (tid >> 3) + 32 * i;
+        const int idx = sIdx[e][row];
+        cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
+      }
+    }
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)ncore * N * 16;
+      mbar_expect_tx(bar_full + stage * 8, bytes);
+      bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)sK[e] * Kd + (long long)c * KC) * N, bytes,
+                    bar_full + stage * 8);
+    }
+    cp_async_commit();
+  };
+
+  if (steps > 0) issue(0);
+  for (int st = 0; st < steps; ++st) {
+    if (st + 1 < steps) {
+      const int nst = st + 1;
+      if (nst >= NS) mbar_wait(bar_empty + (nst % NS) * 8, ((nst / NS) - 1) & 1);
+      issue(nst);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    fence_proxy_async();      // generic-proxy smem writes (cp.async) -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      const int stage = st % NS;
+      const int c = st % kchunks;
+      const int ncore = min(NCORE, (Kd - c * KC) >> 2);
+      mbar_wait(bar_full + stage * 8, (st / NS) & 1);
+      tc_fence_after();
+      const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
+      for (int kk = 0; kk < (ncore >> 1); ++kk) {
+        const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
+        const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
+        mma_tf32(tmem_d, ad, bd, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+      }
+      tc_commit(bar_empty + stage * 8);
+      if (st == steps - 1) tc_commit(bar_done);
+    }
+  }
+
+  // ---- epilogue: TMEM -> registers -> global; warp w reads lane quadrant w&3, column half w>>2 ----
+  if (steps > 0) {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+  }
+  {
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int orow = sPerm[row];
+    const int half = N >> 1;                // N % 16 == 0  ->  half % 8 == 0
+    float *yp = Y + (long long)(orow < 0 ? 0 : orow) * N;
+    for (int c0 = h * half; c0 < (h + 1) * half; c0 += 8) {
+      uint32_t v[8];
+      if (steps > 0) {
+        tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0u;
+      }
+      if (orow >= 0) {
+        float4 o0 = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+        float4 o1 = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        if (bias) {
+          const float4 b0 = *reinterpret_cast<const float4 *>(bias + c0), b1 = *reinterpret_cast<const float4 *>(bias + c0 + 4);
+          o0.x += b0.x; o0.y += b0.y; o0.z += b0.z; o0.w += b0.w;
+          o1.x += b1.x; o1.y += b1.y; o1.z += b1.z; o1.w += b1.w;
+        }
+        *reinterpret_cast<float4 *>(yp + c0) = o0;
+        *reinterpret_cast<float4 *>(yp + c0 + 4) = o1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+static bool tf32_shape_ok(const float *X, const float *W, const float *bias, float *Y, int Kd, int N) {
+  auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+  return Kd >= 8 && Kd % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
+}
+
+}  // namespace tc
+
+// Y[stationary] = bias + sum_k X[partner_k] @ Wg[k], where Wg[k] is W[k] (transpose_w = 0, W is
+// [K][Kd][N]) or W[k]^T (transpose_w = 1, W is [K][N][Kd]).
+int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N, long long n_rows,
+              const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s) {
+  using namespace tc;
+  if (precision != SCN_PRECISION_TF32) return 1;
+  if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
+  float *wp = nullptr;
+  if (dev_alloc_t(&wp, (size_t)K * Kd * N, s)) return -1;
+  const long long total = (long long)K * Kd * N;
+  int pb = cdiv(total, 256);
+  if (pb > num_sms() * 8) pb = num_sms() * 8;
+  const int cin = transpose_w ? N : Kd, cout = transpose_w ? Kd : N;
+  k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const Smem L(N, K);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_osgemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem(256, MAX_K).total) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      dev_free(wp, s);
+      return -1;
+    }
+    attr_set = true;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < N) cols <<= 1;
+  k_osgemm_tf32<<<tv.n_tiles, NT, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  dev_free(wp, s);
+  if (e != cudaSuccess) {
+    set_error("k_osgemm_tf32 launch failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
+int weight_grad_tc(const float *, const float *, float *, int, int, RuleBook *, int, int, int, cudaStream_t) {
+  return 1;
+}
+
 }  // namespace scn

@@ -20,12 +20,12 @@ if not os.path.exists(LIB_PATH):
 
 lib = ctypes.CDLL(LIB_PATH)
 
-PRECISIONS = {"fp32": 0, "bf16": 1, "tf32x3": 2}
+PRECISIONS = {"fp32": 0, "tf32": 1}
 _precision = PRECISIONS[os.environ.get("SCN_B200_PRECISION", "fp32")]
 
 
 def set_conv_precision(name):
-    """'fp32' (exact FFMA, parity mode), 'bf16' or 'tf32x3' (tcgen05 tensor cores)."""
+    """'fp32' (exact FFMA tiles, parity mode) or 'tf32' (tcgen05 tensor cores, fp32 accumulate)."""
     global _precision
     _precision = PRECISIONS[name]
 

@@ -35,9 +35,8 @@ typedef struct scn_metadata scn_metadata_t;
 
 /* Precision of the convolution contraction (accumulation is always fp32). */
 enum {
-  SCN_PRECISION_FP32 = 0,   /* exact fp32 FFMA tiles (parity mode)                        */
-  SCN_PRECISION_BF16 = 1,   /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accum     */
-  SCN_PRECISION_TF32X3 = 2  /* 3xTF32 split on tcgen05: fp32-equivalent accuracy          */
+  SCN_PRECISION_FP32 = 0,   /* exact fp32 FFMA tiles (parity mode)                               */
+  SCN_PRECISION_TF32 = 1    /* tf32 operands on tcgen05 tensor cores, fp32 accumulators in TMEM  */
 };
 
 /* ---- library ---------------------------------------------------------------------- */

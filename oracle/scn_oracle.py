@@ -373,3 +373,103 @@ def to_input(xyz_list, scale=50, full=(4096, 4096, 512), seed=0):
         f[:, 0:3] = torch.from_numpy(a / scale).float()
         feats.append(f)
     return torch.cat(locs), torch.cat(feats)
+
+
+# --------------------------------------------------------------------------------------------
+# the whole backbone on the restated ops, any dtype (float64 = ground truth for tolerance studies)
+# --------------------------------------------------------------------------------------------
+class OracleBackbone(object):
+    """FPN_Net graph (fpn_net.py:95-265) evaluated with the restated ops above through torch autograd
+    in `dtype`.  With dtype=float64 it serves as ground truth to separate rounding noise from real
+    discrepancies: tests compare |impl - f64| with |reference_fp32 - f64|."""
+
+    def __init__(self, state_dict, full_scale, n_planes, rpn_map_sizes, dtype=torch.float64, leakiness=0.0,
+                 eps=1e-4, fpn_scales_from_top=(4, 3, 2, 1), roi_scales_from_top=(4, 3),
+                 rpn_3d_2d_selector=(1, 2, 3, 4, 5, 6)):
+        self.dt = dtype
+        self.p = {k: v.detach().clone().to(dtype) for k, v in state_dict.items()}
+        for k, v in self.p.items():
+            if "running_" not in k:
+                v.requires_grad_(True)
+        self.full_scale = [int(v) for v in full_scale]
+        self.n_scales = len(n_planes)
+        self.rpn_map_sizes = [list(s) for s in rpn_map_sizes]
+        self.leak, self.eps = leakiness, eps
+        self.fpn, self.roi, self.sel = list(fpn_scales_from_top), list(roi_scales_from_top), list(rpn_3d_2d_selector)
+        self.rules = {}
+
+    def _conv(self, x, w, rules, n_out, swap=False):
+        y = torch.zeros(n_out, w.shape[3], dtype=self.dt)
+        for k, r in enumerate(rules):
+            if len(r):
+                r = torch.as_tensor(np.asarray(r), dtype=torch.int64)
+                i, o = (r[:, 1], r[:, 0]) if swap else (r[:, 0], r[:, 1])
+                y = y.index_add(0, o, x[i] @ w[k, 0])
+        return y
+
+    def _bn(self, key, x):
+        n = x.shape[0]
+        mean = x.sum(0) / n
+        s = (x * x).sum(0) - mean * mean * n
+        invstd = torch.pow(s / n + self.eps, -0.5)
+        w = invstd * self.p[key + ".weight"]
+        y = x * w + (self.p[key + ".bias"] - mean * w)
+        return torch.where(y > 0, y, y * self.leak)
+
+    def _subm(self, key, x, loc, ss, fs):
+        rk = ("s", tuple(ss), fs)
+        if rk not in self.rules:
+            self.rules[rk] = submanifold_rules(loc, ss, [fs] * 3)
+        return self._conv(x, self.p[key + ".weight"], self.rules[rk], len(loc))
+
+    def _down_rules(self, loc, ss, fs, st):
+        out_ss = [(a - f) // s + 1 for a, f, s in zip(ss, fs, st)]
+        rk = ("c", tuple(ss), tuple(fs), tuple(st))
+        if rk not in self.rules:
+            self.rules[rk] = conv_rules(loc, ss, fs, st, out_ss)
+        return self.rules[rk], out_ss
+
+    def _block(self, key, x, loc, ss):
+        h = self._subm(key + ".1.1", self._bn(key + ".1.0", x), loc, ss, 3)
+        h = self._subm(key + ".1.3", self._bn(key + ".1.2", h), loc, ss, 3)
+        return x + h
+
+    def forward(self, coords, feats):
+        loc, prow, header, table = input_layer_rules(np.asarray(coords), 4)
+        t = torch.as_tensor(np.asarray(table), dtype=torch.int64)
+        f = torch.as_tensor(feats).to(self.dt)
+        x = torch.zeros(header[3], f.shape[1], dtype=self.dt)
+        for j in range(header[1]):
+            sel = t[:, 0] > j
+            x[sel] += (1.0 / t[sel, 0].to(self.dt))[:, None] * f[t[sel, 1 + j]]
+        ss = self.full_scale
+        x = self._subm("layers_in.1", x, loc, ss, 3)
+        downs = []
+        for k in range(self.n_scales):
+            if k == 0:
+                x = self._block("m_downs.0.0", x, loc, ss)
+            else:
+                (nloc, rules), nss = self._down_rules(loc, ss, [2, 2, 2], [2, 2, 2])
+                x = self._conv(self._bn("m_downs.%d.0.0" % k, x), self.p["m_downs.%d.0.1.weight" % k], rules, len(nloc))
+                loc, ss = nloc, nss
+                x = self._block("m_downs.%d.1" % k, x, loc, ss)
+            downs.append((x, loc, ss))
+        x = self._subm("m_shortcuts.%d" % (self.n_scales - 1), x, loc, ss, 1)
+        ups = [(x, loc, ss)]
+        for k in range(self.n_scales - 1):
+            j = self.n_scales - 2 - k
+            dx, dloc, dss = downs[j]
+            (_, rules), _ = self._down_rules(dloc, dss, [2, 2, 2], [2, 2, 2])
+            x = self._conv(self._bn("m_ups.%d.0" % k, x), self.p["m_ups.%d.1.weight" % k], rules, len(dloc), swap=True)
+            x = x + self._subm("m_shortcuts.%d" % j, dx, dloc, dss, 1)
+            ups.append((self._subm("m_mergeds.%d" % k, x, dloc, dss, 3), dloc, dss))
+        maps3d = [ups[i] for i in self.fpn]
+        maps2d = []
+        for i, (mx, mloc, mss) in enumerate(maps3d):
+            (zloc, rules), zss = self._down_rules(mloc, mss, [1, 1, self.rpn_map_sizes[i][2]], [1, 1, 1])
+            maps2d.append((self._conv(mx, self.p["convs_pro2d.%d.weight" % i], rules, len(zloc)), zloc, zss))
+        both = maps3d + maps2d
+        return [both[i] for i in self.sel], [ups[i] for i in self.roi]
+
+    def grads(self):
+        return {k: v.grad for k, v in self.p.items() if v.requires_grad and v.grad is not None}

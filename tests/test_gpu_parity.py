@@ -24,11 +24,20 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.fixture(scope="module")
-def scn():
+# fp32: exact FFMA tiles (north-star bound 1e-4).  tf32: tcgen05 tensor cores - operands carry a
+# 10-bit mantissa (unit round-off 2^-11 ~ 4.9e-4, features truncated / weights rounded), fp32
+# accumulation; stated tolerance per layer 2e-3 of max|ref|, 1e-2 through the whole backbone.
+PREC_TOL = {"fp32": 1e-4, "tf32": 2e-3}
+
+
+@pytest.fixture(scope="module", params=["fp32", "tf32"])
+def scn(request):
     import sparseconvnet
+    sparseconvnet.set_conv_precision(request.param)
+    sparseconvnet.TOL = PREC_TOL[request.param]
+    sparseconvnet.PREC = request.param
+    yield sparseconvnet
     sparseconvnet.set_conv_precision("fp32")
-    return sparseconvnet
 
 
 def make_input(scn, coords, ss, feats=None, mode=4, C=4, seed=0):
@@ -244,14 +253,14 @@ def test_submanifold_convolution(scn, cin, cout, fs):
     w = conv.weight.detach().cpu()
     b = conv.bias.detach().cpu() if cin == 5 else None
     want = O.conv_forward(x, w, rules, len(loc), b)
-    assert rel(y.features, want) <= TOL
+    assert rel(y.features, want) <= scn.TOL
     dy = torch.randn_like(y.features)
     y.features.backward(dy)
     dx, dw, db = O.conv_backward(x, dy.cpu(), w, rules)
-    assert rel(conv.weight.grad, dw) <= TOL
-    assert rel(t.leaf.grad, _input_grad(t, c, dx)) <= TOL
+    assert rel(conv.weight.grad, dw) <= scn.TOL
+    assert rel(t.leaf.grad, _input_grad(t, c, dx)) <= scn.TOL
     if cin == 5:
-        assert rel(conv.bias.grad, db) <= TOL
+        assert rel(conv.bias.grad, db) <= scn.TOL
 
 
 def _input_grad(t, coords, dx_sites):
@@ -279,16 +288,16 @@ def test_strided_convolution_and_deconvolution(scn, cin, cout):
     assert np.array_equal(gloc1[pg], oloc1[po])
     x, w, w2 = t.features.detach().cpu(), conv.weight.detach().cpu(), dec.weight.detach().cpu()
     oy = O.conv_forward(x, w, rules, len(oloc1))
-    assert rel(y.features[pg], oy[po]) <= TOL
+    assert rel(y.features[pg], oy[po]) <= scn.TOL
     oz = O.conv_forward(oy, w2, rules, len(loc0), swap=True)
-    assert rel(z.features, oz) <= TOL
+    assert rel(z.features, oz) <= scn.TOL
     dz = torch.randn_like(z.features)
     z.features.backward(dz)
     ody, odw2, _ = O.conv_backward(oy, dz.cpu(), w2, rules, swap=True)
-    assert rel(dec.weight.grad, odw2) <= TOL
+    assert rel(dec.weight.grad, odw2) <= scn.TOL
     odx, odw, _ = O.conv_backward(x, ody, w, rules)
-    assert rel(conv.weight.grad, odw) <= TOL
-    assert rel(t.leaf.grad, _input_grad(t, c, odx)) <= TOL
+    assert rel(conv.weight.grad, odw) <= scn.TOL
+    assert rel(t.leaf.grad, _input_grad(t, c, odx)) <= scn.TOL
 
 
 @pytest.mark.parametrize("Z", [4, 8, 16, 32])
@@ -304,13 +313,13 @@ def test_z_collapse_convolution(scn, Z):
     pg, po = np.argsort(O.canonical_rank(gl, [32, 32, 1])), np.argsort(O.canonical_rank(ol, [32, 32, 1]))
     x, w = t.features.detach().cpu(), conv.weight.detach().cpu()
     oy = O.conv_forward(x, w, rules, len(ol))
-    assert rel(y.features[pg], oy[po]) <= TOL
+    assert rel(y.features[pg], oy[po]) <= scn.TOL
     dy = torch.randn_like(y.features)
     y.features.backward(dy)
     ody = torch.zeros_like(oy)
     ody[po] = dy.cpu()[pg]
     odx, odw, _ = O.conv_backward(x, ody, w, rules)
-    assert rel(conv.weight.grad, odw) <= TOL
+    assert rel(conv.weight.grad, odw) <= scn.TOL
 
 
 def test_network_in_network(scn):
@@ -320,11 +329,11 @@ def test_network_in_network(scn):
     y = nin(t)
     x = t.features.detach().cpu().requires_grad_(True)
     want = x @ nin.weight.detach().cpu() + nin.bias.detach().cpu()
-    assert rel(y.features, want) <= TOL
+    assert rel(y.features, want) <= scn.TOL
     dy = torch.randn_like(y.features)
     y.features.backward(dy)
-    assert rel(nin.weight.grad, x.detach().t() @ dy.cpu()) <= TOL
-    assert rel(nin.bias.grad, dy.cpu().sum(0)) <= TOL
+    assert rel(nin.weight.grad, x.detach().t() @ dy.cpu()) <= scn.TOL
+    assert rel(nin.bias.grad, dy.cpu().sum(0)) <= scn.TOL
 
 
 @pytest.mark.parametrize("C", [9, 32, 64, 128, 256, 20])
@@ -341,14 +350,16 @@ def test_batchnorm_train(scn, C, leak, n):
     rm, rv = torch.zeros(C), torch.ones(C)
     oy, sm, si = O.bn_forward(x.detach().cpu(), bn.weight.detach().cpu(), bn.bias.detach().cpu(), rm, rv, 1e-4,
                               0.95, True, leak)
-    assert rel(y, oy) <= TOL
-    assert rel(bn.running_mean, rm) <= TOL and rel(bn.running_var, rv) <= TOL
+    assert rel(y, oy) <= scn.TOL
+    assert rel(bn.running_mean, rm) <= scn.TOL and rel(bn.running_var, rv) <= scn.TOL
     dy = torch.randn_like(y)
     dy0 = dy.clone()
     y.backward(dy)
     assert torch.equal(dy, dy0)          # unlike the reference, grad_output is not clobbered
-    odx, odw, odb = O.bn_backward(x.detach().cpu(), oy, dy.cpu(), sm, si, bn.weight.detach().cpu(), leak)
-    assert rel(x.grad, odx) <= TOL and rel(bn.weight.grad, odw) <= 5 * TOL and rel(bn.bias.grad, odb) <= 5 * TOL
+    # the (Leaky)ReLU mask is taken from the implementation's own saved output, as the reference does
+    # (outputs within rounding of 0 would otherwise flip the mask of isolated elements)
+    odx, odw, odb = O.bn_backward(x.detach().cpu(), y.detach().cpu(), dy.cpu(), sm, si, bn.weight.detach().cpu(), leak)
+    assert rel(x.grad, odx) <= scn.TOL and rel(bn.weight.grad, odw) <= 5 * TOL and rel(bn.bias.grad, odb) <= 5 * TOL
 
 
 @pytest.mark.parametrize("track", [True, False])
@@ -363,7 +374,7 @@ def test_batchnorm_eval(scn, track):
     xc = x.cpu()
     rm, rv = (bn.running_mean.cpu(), bn.running_var.cpu()) if track else (xc.mean(0), xc.var(0))
     oy, _, _ = O.bn_forward(xc, bn.weight.detach().cpu(), bn.bias.detach().cpu(), rm, rv, 1e-4, 0.95, False, 0.0)
-    assert rel(y, oy) <= TOL
+    assert rel(y, oy) <= scn.TOL
 
 
 def test_sparse_to_dense(scn):
@@ -394,17 +405,18 @@ def test_dense_equivalence(scn):
     order = torch.argsort(c[:, 3], stable=True)
     c = c[order]
     t, _ = make_input(scn, c.numpy(), [S] * 3, C=cin)
-    dense = scn.SparseToDense(3, cin)(t)
+    dense = scn.SparseToDense(3, cin)(t).cpu()          # dense torch ops on the CPU: plain fp32
     sub = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
-    w = sub.weight.detach().view(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
-    assert rel(scn.SparseToDense(3, cout)(sub(t)), F.conv3d(dense, w, padding=1)) <= TOL
+    w = sub.weight.detach().cpu().view(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
+    assert rel(scn.SparseToDense(3, cout)(sub(t)), F.conv3d(dense, w, padding=1)) <= scn.TOL
     conv = scn.Convolution(3, cin, cout, 2, 2, False).cuda()
-    w = conv.weight.detach().view(2, 2, 2, cin, cout).permute(4, 3, 0, 1, 2)
+    w = conv.weight.detach().cpu().view(2, 2, 2, cin, cout).permute(4, 3, 0, 1, 2)
     y = conv(t)
-    assert rel(scn.SparseToDense(3, cout)(y), F.conv3d(dense, w, stride=2)) <= TOL
+    assert rel(scn.SparseToDense(3, cout)(y), F.conv3d(dense, w, stride=2)) <= scn.TOL
     dec = scn.Deconvolution(3, cout, cin, 2, 2, False).cuda()
-    w = dec.weight.detach().view(2, 2, 2, cout, cin).permute(3, 4, 0, 1, 2)
-    assert rel(scn.SparseToDense(3, cin)(dec(y)), F.conv_transpose3d(scn.SparseToDense(3, cout)(y), w, stride=2)) <= TOL
+    w = dec.weight.detach().cpu().view(2, 2, 2, cout, cin).permute(3, 4, 0, 1, 2)
+    assert rel(scn.SparseToDense(3, cin)(dec(y)),
+               F.conv_transpose3d(scn.SparseToDense(3, cout)(y).cpu(), w, stride=2)) <= scn.TOL
 
 
 # ---------------------------------------------------------------------------------------------
@@ -422,35 +434,52 @@ def _small_net(scn, g):
     return net.cuda()
 
 
-def test_backbone_matches_reference_golden(scn, gold):
+@pytest.fixture(scope="module")
+def truth64(gold):
+    """float64 evaluation of the same graph (oracle/scn_oracle.py OracleBackbone): ground truth that
+    separates rounding noise from real discrepancies.  The reference CPU path accumulates BN sums
+    sequentially in fp32 (CPU/BatchNormalization.cpp:19-33,86-95): its own parameter gradients are
+    1e-3..1.5e-2 away from this truth on this fixture, so gradients are checked against the truth
+    (bound 1e-4 in fp32 mode), forward features against the reference itself (bound 1e-4)."""
+    g = gold("small_net")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    net = O.OracleBackbone(sd, [512] * 3, [8] + [16] * 8, [[32] * 3, [16] * 3, [8] * 3, [4] * 3])
+    rpn, roi = net.forward(g["locs"], g["feats"])
+    sum((m[0] ** 2).sum() for m in rpn + roi).backward()
+    return net.grads()
+
+
+def test_backbone_matches_reference_golden(scn, gold, truth64):
     g = gold("small_net")
     net = _small_net(scn, g).train()
     rpn, roi = net([torch.from_numpy(g["locs"]), torch.from_numpy(g["feats"]).cuda()])
     loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
     loss.backward()
-    assert abs(loss.item() - float(g["loss"])) <= TOL * float(g["loss"])
+    assert abs(loss.item() - float(g["loss"])) <= scn.TOL * float(g["loss"])
+    feat_tol = scn.TOL * (5 if scn.PREC == "tf32" else 1)
     for i, m in enumerate(list(rpn) + list(roi)):
         loc = m.get_spatial_locations().numpy()
         assert (np.diff(loc[:, 3]) >= 0).all()
         order = np.argsort(O.canonical_rank(loc, m.spatial_size.tolist()))
         assert np.array_equal(loc[order], g["out%d_loc" % i])
-        assert rel(m.features.detach().cpu()[order], g["out%d_feat" % i]) <= TOL
+        assert rel(m.features.detach().cpu()[order], g["out%d_feat" % i]) <= feat_tol
     n = 0
     for k, p in net.named_parameters():
         if "grad/" + k in g.files:
             assert p.grad is not None, k
-            assert rel(p.grad, g["grad/" + k]) <= 3 * TOL, k
+            ref_err = rel(g["grad/" + k], truth64[k])              # the reference's own rounding error
+            assert rel(p.grad, truth64[k]) <= max(scn.TOL * (5 if scn.PREC == "tf32" else 1), 0.0), (k, ref_err)
             n += 1
         else:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
     assert n > 40
     for k, v in net.state_dict().items():
         if "running_" in k and "after/" + k in g.files:
-            assert rel(v, g["after/" + k]) <= TOL, k
+            assert rel(v, g["after/" + k]) <= scn.TOL, k
     ge = gold("small_net_eval")
     net.eval()
     with torch.no_grad():
         rpn, roi = net([torch.from_numpy(g["locs"]), torch.from_numpy(g["feats"]).cuda()])
     for i, m in enumerate(list(rpn) + list(roi)):
         order = np.argsort(O.canonical_rank(m.get_spatial_locations().numpy(), m.spatial_size.tolist()))
-        assert rel(m.features.cpu()[order], ge["out%d_feat" % i]) <= TOL
+        assert rel(m.features.cpu()[order], ge["out%d_feat" % i]) <= feat_tol
