@@ -3,7 +3,8 @@
 // Reference: SparseConvNet/sparseconvnet/SCN/CPU/BatchNormalization.cpp:13-107 (math) and
 // CUDA/BatchNormalization.cu:14-184 (which runs on <= 16 thread blocks).  Here: a full-grid
 // statistics pass with 128-bit coalesced loads and per-thread fp32 / cross-thread fp64
-// accumulation, a one-block-per-128-channels finalize, and a vectorised elementwise apply.
+// accumulation folded into 2C fp64 sums, and a vectorised elementwise apply whose blocks derive
+// the per-channel coefficients themselves (no separate finalize launch).
 #include "common.cuh"
 #include "../../include/scn_b200.h"
 
@@ -32,7 +33,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(BN_T)
 k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
-               long long n, int C, double *__restrict__ part) {
+               long long n, int C, double *__restrict__ acc) {
   __shared__ double red[2][BN_T * 4];
   const int qpr = C >> 2;               // quads per row
   const int rpb = BN_T / qpr;           // rows per block iteration (>= 1 since C <= 1024)
@@ -64,8 +65,8 @@ k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
   for (int c = threadIdx.x; c < C; c += BN_T) {
     double a = 0, b = 0;
     for (int j = 0; j < rpb; ++j) { a += red[0][j * C + c]; b += red[1][j * C + c]; }
-    part[((long long)blockIdx.x * 2 + 0) * C + c] = a;
-    part[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+    atomicAdd(&acc[c], a);        // fp64: the order of the <= 2*SMs block sums is immaterial
+    atomicAdd(&acc[C + c], b);
   }
 }
 
@@ -74,7 +75,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(BN_T)
 k_bn_stats_gen(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
-               long long n, int C, double *__restrict__ part) {
+               long long n, int C, double *__restrict__ acc) {
   __shared__ double red[2][8][33];
   const int c = blockIdx.y * 32 + threadIdx.x;
   double s0 = 0, s1 = 0;
@@ -94,66 +95,54 @@ k_bn_stats_gen(const float *__restrict__ X, const float *__restrict__ Yo,
   if (threadIdx.y == 0 && c < C) {
     double a = 0, b = 0;
     for (int j = 0; j < 8; ++j) { a += red[0][j][threadIdx.x]; b += red[1][j][threadIdx.x]; }
-    part[((long long)blockIdx.x * 2 + 0) * C + c] = a;
-    part[((long long)blockIdx.x * 2 + 1) * C + c] = b;
+    atomicAdd(&acc[c], a);        // fp64: the order of the <= 2*SMs block sums is immaterial
+    atomicAdd(&acc[C + c], b);
   }
 }
 
-// ---- finalize --------------------------------------------------------------------------
+// ---- coefficients -------------------------------------------------------------------------
+// Every apply block derives the per-channel coefficients from the fp64 sums itself (2C loads);
+// block 0 also publishes the saved / running statistics or the parameter gradients.
 // forward train (CPU/BatchNormalization.cpp:19-40): coef = [scale, shift]
-__global__ void k_bn_fwd_finalize(const double *__restrict__ part, int gx, long long n, int C,
-                                  float *save_mean, float *save_invstd, float *running_mean,
-                                  float *running_var, const float *weight, const float *bias,
-                                  float eps, float momentum, float *__restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double sum = 0, sq = 0;
-  for (int g = 0; g < gx; ++g) {
-    sum += part[((long long)g * 2 + 0) * C + c];
-    sq += part[((long long)g * 2 + 1) * C + c];
+__device__ __forceinline__ void bn_fwd_coef(const double *__restrict__ acc, long long n, int C, int c,
+                                            float *save_mean, float *save_invstd, float *running_mean,
+                                            float *running_var, const float *weight, const float *bias,
+                                            float eps, float momentum, int train, bool publish,
+                                            float *coef) {
+  float mean, invstd;
+  if (train) {
+    const double sum = acc[c], sq = acc[C + c];
+    const double dmean = sum / (double)n;
+    const double s = sq - dmean * dmean * (double)n;  // sum of squared deviations
+    mean = (float)dmean;
+    invstd = powf((float)(s / (double)n) + eps, -0.5f);
+    if (publish) {
+      running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mean;
+      running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(s / (double)(n - 1));
+    }
+  } else {  // :41-46 statistics are the buffers as passed
+    mean = running_mean[c];
+    invstd = powf(running_var[c] + eps, -0.5f);
   }
-  const double mean = sum / (double)n;
-  const double s = sq - mean * mean * (double)n;  // sum of squared deviations
-  running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
-  running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(s / (double)(n - 1));
-  const float invstd = powf((float)(s / (double)n) + eps, -0.5f);
-  save_mean[c] = (float)mean;
-  save_invstd[c] = invstd;
-  const float w = invstd * (weight ? weight[c] : 1.f);
-  coef[c] = w;
-  coef[C + c] = -(float)mean * w + (bias ? bias[c] : 0.f);
-}
-
-// forward eval (:41-46): statistics are the running buffers as passed
-__global__ void k_bn_eval_coef(int C, float *save_mean, float *save_invstd,
-                               const float *running_mean, const float *running_var,
-                               const float *weight, const float *bias, float eps,
-                               float *__restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float mean = running_mean[c];
-  const float invstd = powf(running_var[c] + eps, -0.5f);
-  save_mean[c] = mean;
-  save_invstd[c] = invstd;
+  if (publish) {
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+  }
   const float w = invstd * (weight ? weight[c] : 1.f);
   coef[c] = w;
   coef[C + c] = -mean * w + (bias ? bias[c] : 0.f);
 }
 
 // backward (:86-106): coef = [gradMean, k, invstd*gamma]
-__global__ void k_bn_bwd_finalize(const double *__restrict__ part, int gx, long long n, int C,
-                                  const float *save_invstd, const float *weight, float *d_weight,
-                                  float *d_bias, float *__restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double gsum = 0, dotp = 0;
-  for (int g = 0; g < gx; ++g) {
-    gsum += part[((long long)g * 2 + 0) * C + c];
-    dotp += part[((long long)g * 2 + 1) * C + c];
-  }
+__device__ __forceinline__ void bn_bwd_coef(const double *__restrict__ acc, long long n, int C, int c,
+                                            const float *save_invstd, const float *weight,
+                                            float *d_weight, float *d_bias, bool publish, float *coef) {
+  const double gsum = acc[c], dotp = acc[C + c];
   const float invstd = save_invstd[c];
-  if (d_bias) d_bias[c] = (float)gsum;
-  if (d_weight) d_weight[c] = (float)dotp * invstd;
+  if (publish) {
+    if (d_bias) d_bias[c] = (float)gsum;
+    if (d_weight) d_weight[c] = (float)dotp * invstd;
+  }
   coef[c] = (float)(gsum / (double)n);
   coef[C + c] = (float)dotp * invstd * invstd / (float)n;
   coef[2 * C + c] = invstd * (weight ? weight[c] : 1.f);
@@ -162,10 +151,24 @@ __global__ void k_bn_bwd_finalize(const double *__restrict__ part, int gx, long 
 // ---- apply -----------------------------------------------------------------------------
 __device__ __forceinline__ float lrelu(float v, float leak) { return v > 0.f ? v : v * leak; }
 
+struct BnFwdArgs {
+  const double *acc;
+  float *save_mean, *save_invstd, *running_mean, *running_var;
+  const float *weight, *bias;
+  float eps, momentum;
+  int train;
+};
+
 template <bool VEC>
 __global__ void __launch_bounds__(BN_T)
-k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, const float *__restrict__ coef,
-               float leak, long long total, int C) {
+k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, float leak,
+               long long n, int C) {
+  extern __shared__ float coef[];  // [2C]
+  for (int c = threadIdx.x; c < C; c += BN_T)
+    bn_fwd_coef(a.acc, n, C, c, a.save_mean, a.save_invstd, a.running_mean, a.running_var, a.weight,
+                a.bias, a.eps, a.momentum, a.train, blockIdx.x == 0, coef);
+  __syncthreads();
+  const long long total = n * C;
   const long long st = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (VEC) {
@@ -194,8 +197,17 @@ template <bool VEC>
 __global__ void __launch_bounds__(BN_T)
 k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, float *__restrict__ dX,
-               const float *__restrict__ mean, const float *__restrict__ coef, float leak,
-               long long total, int C) {
+               const float *__restrict__ mean, const double *__restrict__ acc,
+               const float *__restrict__ save_invstd, const float *__restrict__ weight,
+               float *d_weight, float *d_bias, float leak, long long n, int C) {
+  extern __shared__ float coef[];  // [3C] then mean [C]
+  float *smean = coef + 3 * C;
+  for (int c = threadIdx.x; c < C; c += BN_T) {
+    bn_bwd_coef(acc, n, C, c, save_invstd, weight, d_weight, d_bias, blockIdx.x == 0, coef);
+    smean[c] = mean[c];
+  }
+  __syncthreads();
+  const long long total = n * C;
   const long long st = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (VEC) {
@@ -205,7 +217,7 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
       const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + i);
       const float4 y = __ldg(reinterpret_cast<const float4 *>(Yo) + i);
       const float4 d = __ldg(reinterpret_cast<const float4 *>(dY) + i);
-      const float4 mu = *reinterpret_cast<const float4 *>(mean + c);
+      const float4 mu = *reinterpret_cast<const float4 *>(smean + c);
       const float4 gm = *reinterpret_cast<const float4 *>(coef + c);
       const float4 kk = *reinterpret_cast<const float4 *>(coef + C + c);
       const float4 sc = *reinterpret_cast<const float4 *>(coef + 2 * C + c);
@@ -220,7 +232,7 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
     for (; i < total; i += st) {
       const int c = (int)(i % C);
       const float d = dY[i] * (Yo[i] > 0.f ? 1.f : leak);
-      dX[i] = (d - coef[c] - (X[i] - mean[c]) * coef[C + c]) * coef[2 * C + c];
+      dX[i] = (d - coef[c] - (X[i] - smean[c]) * coef[C + c]) * coef[2 * C + c];
     }
   }
 }
@@ -232,7 +244,7 @@ static bool vec_ok(long long n, int C, const void *a, const void *b, const void 
 
 static int stats_grid(long long n, int rows_per_iter) {
   long long g = (n + (long long)rows_per_iter * 4 - 1) / ((long long)rows_per_iter * 4);
-  const long long cap = (long long)num_sms() * 4;
+  const long long cap = (long long)num_sms() * 2;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -258,42 +270,29 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
                           int64_t n, int64_t C64, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)C64;
-  SCN_CHECK(C > 0 && save_mean && save_invstd && running_mean && running_var, "bad BN arguments");
+  SCN_CHECK(C > 0 && C <= 4096 && save_mean && save_invstd && running_mean && running_var, "bad BN arguments");
   if (n == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, out, in, out);
   prof_begin(PROF_BN, s);
-  float *coef = nullptr;
-  SCN_TRY(dev_alloc_t(&coef, (size_t)3 * C, s));
+  double *acc = nullptr;
   if (train) {
-    int gx;
-    double *part = nullptr;
-    if (vec) {
-      gx = stats_grid(n, BN_T / (C / 4));
-      SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
-      k_bn_stats_vec<false><<<gx, BN_T, 0, s>>>(in, nullptr, nullptr, nullptr, 0.f, n, C, part);
-    } else {
-      gx = stats_grid(n, 8);
-      SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
-      k_bn_stats_gen<false><<<dim3(gx, cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, nullptr, nullptr,
-                                                                        nullptr, 0.f, n, C, part);
-    }
-    SCN_LAUNCHED();
-    k_bn_fwd_finalize<<<cdiv(C, 128), 128, 0, s>>>(part, gx, n, C, save_mean, save_invstd,
-                                                   running_mean, running_var, weight, bias, eps,
-                                                   momentum, coef);
-    SCN_LAUNCHED();
-    dev_free(part, s);
-  } else {
-    k_bn_eval_coef<<<cdiv(C, 128), 128, 0, s>>>(C, save_mean, save_invstd, running_mean,
-                                                running_var, weight, bias, eps, coef);
+    SCN_TRY(dev_alloc_t(&acc, (size_t)2 * C, s));
+    SCN_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), s));
+    if (vec)
+      k_bn_stats_vec<false><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, nullptr, nullptr, nullptr, 0.f, n, C, acc);
+    else
+      k_bn_stats_gen<false><<<dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, nullptr, nullptr, nullptr,
+                                                                                     0.f, n, C, acc);
     SCN_LAUNCHED();
   }
+  BnFwdArgs a{acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train ? 1 : 0};
   const long long total = (long long)n * C;
-  if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, 0, s>>>(in, out, coef, leakiness, total, C);
-  else k_bn_fwd_apply<false><<<apply_grid(total), BN_T, 0, s>>>(in, out, coef, leakiness, total, C);
+  const size_t sm = (size_t)2 * C * sizeof(float);
+  if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
+  else k_bn_fwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
   SCN_LAUNCHED();
-  dev_free(coef, s);
+  dev_free(acc, s);
   prof_end(PROF_BN, s, (train ? 3.0 : 2.0) * 4.0 * (double)n * C, 0);  // 3 n C s
   return 0;
 }
@@ -304,7 +303,7 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
                            void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)C64;
-  SCN_CHECK(C > 0 && save_mean && save_invstd, "bad BN arguments");
+  SCN_CHECK(C > 0 && C <= 4096 && save_mean && save_invstd, "bad BN arguments");
   if (n == 0) {
     if (d_weight) SCN_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)C * 4, s));
     if (d_bias) SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)C * 4, s));
@@ -313,34 +312,25 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   SCN_CHECK(in && d_in && out && d_out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0);
   prof_begin(PROF_BN, s);
-  float *coef = nullptr;
-  double *part = nullptr;
-  SCN_TRY(dev_alloc_t(&coef, (size_t)3 * C, s));
-  int gx;
-  if (vec) {
-    gx = stats_grid(n, BN_T / (C / 4));
-    SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
-    k_bn_stats_vec<true><<<gx, BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, part);
-  } else {
-    gx = stats_grid(n, 8);
-    SCN_TRY(dev_alloc_t(&part, (size_t)gx * 2 * C, s));
-    k_bn_stats_gen<true><<<dim3(gx, cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, out, d_out, save_mean,
-                                                                     leakiness, n, C, part);
-  }
-  SCN_LAUNCHED();
-  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, s>>>(part, gx, n, C, save_invstd, weight, d_weight,
-                                                 d_bias, coef);
+  double *acc = nullptr;
+  SCN_TRY(dev_alloc_t(&acc, (size_t)2 * C, s));
+  SCN_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), s));
+  if (vec)
+    k_bn_stats_vec<true><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, acc);
+  else
+    k_bn_stats_gen<true><<<dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, out, d_out, save_mean,
+                                                                                   leakiness, n, C, acc);
   SCN_LAUNCHED();
   const long long total = (long long)n * C;
+  const size_t sm = (size_t)4 * C * sizeof(float);
   if (vec)
-    k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, 0, s>>>(in, out, d_out, d_in, save_mean, coef,
-                                                             leakiness, total, C);
+    k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
+                                                              weight, d_weight, d_bias, leakiness, n, C);
   else
-    k_bn_bwd_apply<false><<<apply_grid(total), BN_T, 0, s>>>(in, out, d_out, d_in, save_mean, coef,
-                                                          leakiness, total, C);
+    k_bn_bwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
+                                                           weight, d_weight, d_bias, leakiness, n, C);
   SCN_LAUNCHED();
-  dev_free(part, s);
-  dev_free(coef, s);
+  dev_free(acc, s);
   prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;
 }

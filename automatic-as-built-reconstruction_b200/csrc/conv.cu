@@ -399,10 +399,10 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
   int ident_chunk = 0;
   if (rb->identity) {
     ident_n = rb->total_pairs;
-    long long chunk = (ident_n + 4LL * num_sms() - 1) / (4LL * num_sms());
-    chunk = (chunk + 31) / 32 * 32;
-    if (chunk < 256) chunk = 256;
-    if (chunk > 8192) chunk = 8192;
+    long long chunk = (ident_n + 2LL * num_sms() - 1) / (2LL * num_sms());
+    chunk = (chunk + 63) / 64 * 64;
+    if (chunk < 512) chunk = 512;
+    if (chunk > 16384) chunk = 16384;
     ident_chunk = (int)chunk;
     n_work = cdiv(ident_n, chunk);
     first.v[0] = 0;
@@ -421,23 +421,22 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
     first.v[K] = w;
   }
   prof_begin(PROF_DW, s);
-  const double dw_bytes = 4.0 * ((double)rb->n_in * (xcol ? Cout : Cin) + (double)rb->n_out * (xcol ? Cin : Cout)) +
+  const double dw_bytes = 4.0 * ((double)(xcol ? rb->n_out : rb->n_in) * Cin + (double)(ycol ? rb->n_out : rb->n_in) * Cout) +
                           4.0 * K * cc + (rb->identity ? 0.0 : 8.0 * rb->total_pairs);
   const double dw_flops = 2.0 * rb->total_pairs * cc;
-  if (precision != SCN_PRECISION_FP32 && n_work > 0) {
-    int r = weight_grad_tc(X, dY, dW, Cin, Cout, rb, xcol, ycol, precision, s);
-    if (r <= 0) { prof_end(PROF_DW, s, dw_bytes, dw_flops); return -r; }
-  }
   float *partial = nullptr;
   if (n_work > 0) {
     SCN_TRY(dev_alloc_t(&partial, (size_t)n_work * cc, s));
-    const int cmin = Cin < Cout ? Cin : Cout, cmax = Cin < Cout ? Cout : Cin;
-    (void)cmin;
-    int r;
-    if (cmax <= 32) r = launch_dw_partial<2, 2>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
+    const int cmax = Cin < Cout ? Cout : Cin;
+    int r = 1;
+    if (precision != SCN_PRECISION_FP32)
+      r = dw_partial_tc(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, precision, s);
+    if (r < 0) r = 1000;   // error already recorded
+    else if (r == 0) r = 0;
+    else if (cmax <= 32) r = launch_dw_partial<2, 2>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
     else if (cmax <= 64) r = launch_dw_partial<4, 4>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
     else r = launch_dw_partial<8, 8>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
-    if (r) { dev_free(partial, s); return r; }
+    if (r) { dev_free(partial, s); return 1; }
   }
   dim3 grid(cdiv(cc, 256), K);
   k_dw_reduce<<<grid, 256, 0, s>>>(partial, dW, first, cc);

@@ -25,8 +25,9 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Kd, 
 // kernels), <0 = -(error) with scn_last_error set.
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
               long long n_rows, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s);
-int weight_grad_tc(const float *X, const float *dY, float *dW, int Cin, int Cout, RuleBook *rb,
-                   int xcol, int ycol, int precision, cudaStream_t s);
+int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const DwWork *work, float *partial,
+                  int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,
+                  int precision, cudaStream_t s);
 
 int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, cudaStream_t s);
 

@@ -10,7 +10,7 @@
 //     layout, while the matching weight slice - pre-packed into the same layout by k_pack_weights -
 //     arrives as one cp.async.bulk (TMA, mbarrier complete_tx);
 //   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=Cout, K=8) on the staged slices and
-//     tcgen05.commit releases the stage; a 3-stage ring keeps gathers of step s+1/s+2 in flight
+//     tcgen05.commit releases the stage; a 4-stage ring keeps the gathers of steps s+1, s+2 in flight
 //     while the tensor core works on step s;
 //   * epilogue: tcgen05.ld TMEM -> registers -> (+bias) -> each stationary row written exactly once.
 // fp32 features are fed unconverted (kind::tf32 reads the upper 19 bits); weights are rounded to
@@ -25,7 +25,8 @@ constexpr int KC = 32;                      // reduction elements per pipeline s
 constexpr int NCORE = KC / 4;               // 16-byte k-cores (4 tf32) per step
 constexpr int A_LBO = TILE_M * 16 + 16;     // bytes between k-cores of A (+16: bank spread for the gather)
 constexpr int A_STAGE = NCORE * A_LBO;      // 16512
-constexpr int NS = 3;                       // pipeline stages
+constexpr int NS = 4;                       // pipeline stages
+constexpr int PD = 2;                       // prefetch distance (steps issued ahead of the MMA)
 constexpr int NT = 256;                     // threads
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -223,19 +224,22 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)sK[e] * Kd + (long long)c * KC) * N, bytes,
                     bar_full + stage * 8);
     }
-    cp_async_commit();
   };
 
-  if (steps > 0) issue(0);
+  // one cp.async group per step (empty past the end), so wait_group<PD> always means "step st landed"
+  for (int p = 0; p < PD; ++p) {
+    if (p < steps) issue(p);
+    cp_async_commit();
+  }
   for (int st = 0; st < steps; ++st) {
-    if (st + 1 < steps) {
-      const int nst = st + 1;
+    const int nst = st + PD;
+    if (nst < steps) {
+      // the stage was last read by the MMAs of step nst-NS (issued NS-PD iterations ago)
       if (nst >= NS) mbar_wait(bar_empty + (nst % NS) * 8, ((nst / NS) - 1) & 1);
       issue(nst);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
+    cp_async_commit();
+    cp_async_wait<PD>();
     fence_proxy_async();      // generic-proxy smem writes (cp.async) -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -338,8 +342,208 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   return 0;
 }
 
-int weight_grad_tc(const float *, const float *, float *, int, int, RuleBook *, int, int, int, cudaStream_t) {
-  return 1;
+// ---------------------------------------------------------------------------------------------
+// weight gradient on the tensor cores: partial[w] = X[in rows of work item w]^T @ dY[out rows]
+// M = Cin (zero-padded to 128; two accumulators when Cin = 256), N = Cout, reduction over the pairs.
+// Both operands are gathered rows, i.e. MN-major: pair p lands in k-block p/8, k-row p%8 of the
+// canonical no-swizzle MN-major layout [k-block][16-byte channel piece][8 pairs][16 B].
+// ---------------------------------------------------------------------------------------------
+namespace tc {
+
+constexpr int DW_NS = 3;   // stages
+constexpr int DW_PD = 1;   // prefetch distance
+
+struct DwSmem {
+  int a, b, bars, tmem_slot, total, a_stage, b_stage;
+  __host__ __device__ DwSmem(int MI, int Cout, int KP) {
+    a_stage = KP * MI * 16;
+    b_stage = KP * Cout * 4;
+    a = 0;
+    b = a + DW_NS * a_stage;
+    bars = b + DW_NS * b_stage;
+    tmem_slot = bars + (DW_NS + 1) * 8;
+    total = tmem_slot + 16;
+  }
+};
+
+__global__ void __launch_bounds__(NT)
+k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
+          const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
+          long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int MI = Cin > 128 ? Cin >> 2 : 32;       // 16-byte channel pieces per k-block of A (M padded to 128)
+  const int NI = Cout >> 2;
+  const int halves = Cin > 128 ? 2 : 1;
+  const DwSmem L(MI, Cout, KP);
+  const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
+  const uint32_t bar_empty = smem_u32(smem + L.bars), bar_done = bar_empty + DW_NS * 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kr = tid & 7, q = tid >> 3;
+  const int KB = KP >> 3;                          // k-blocks (8 pairs) per step
+  const uint32_t lbo_a = MI * 128, lbo_b = NI * 128;
+
+  long long start;
+  int len;
+  if (work) {
+    const DwWork w = work[blockIdx.x];
+    start = w.start;
+    len = w.len;
+  } else {
+    start = (long long)blockIdx.x * ident_chunk;
+    len = (int)min((long long)ident_chunk, ident_n - start);
+  }
+  // zero the channel pieces that pad M up to 128 (never written by the gathers)
+  if (Cin < 128) {
+    const int pad0 = Cin >> 2, npad = 32 - pad0;
+    const int total16 = DW_NS * KB * npad * 8;     // 16-byte units
+    for (int i = tid; i < total16; i += NT) {
+      const int r8 = i & 7, rest = i >> 3;
+      const int mi = pad0 + rest % npad, kbs = rest / npad;   // kbs = stage*KB + kb
+      *reinterpret_cast<float4 *>(smem + L.a + (kbs / KB) * L.a_stage + (kbs % KB) * lbo_a + mi * 128 + r8 * 16) =
+          make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < DW_NS + 1; ++i) mbar_init(bar_empty + i * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int steps = (len + KP - 1) / KP;
+  const uint32_t idesc = make_idesc(128, Cout, 1, 1);
+
+  int2 pr[8];
+  auto load_idx = [&](int st) {
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      if (kb < KB) {
+        const int p = st * KP + kb * 8 + kr;
+        int2 v = make_int2(-1, -1);
+        if (p < len) {
+          if (pairs) v = __ldg(reinterpret_cast<const int2 *>(pairs) + start + p);
+          else v = make_int2((int)(start + p), (int)(start + p));
+        }
+        pr[kb] = v;
+      }
+    }
+  };
+  auto issue = [&](int st) {
+    const int stage = st % DW_NS;
+    const uint32_t sa = a_base + stage * L.a_stage + kr * 16, sb = b_base + stage * L.b_stage + kr * 16;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      if (kb < KB) {
+        const int xi = xcol ? pr[kb].y : pr[kb].x, yi = ycol ? pr[kb].y : pr[kb].x;
+        const float *xp = X + (long long)(xi < 0 ? 0 : xi) * Cin;
+        const float *yp = dY + (long long)(yi < 0 ? 0 : yi) * Cout;
+        for (int mi = q; mi < (Cin >> 2); mi += 32) cp_async_16(sa + kb * lbo_a + mi * 128, xp + mi * 4, xi < 0 ? 0 : 16);
+        for (int ni = q; ni < NI; ni += 32) cp_async_16(sb + kb * lbo_b + ni * 128, yp + ni * 4, yi < 0 ? 0 : 16);
+      }
+    }
+  };
+
+  for (int p = 0; p < DW_PD; ++p) {
+    if (p < steps) { load_idx(p); issue(p); }
+    cp_async_commit();
+  }
+  if (DW_PD < steps) load_idx(DW_PD);
+  for (int st = 0; st < steps; ++st) {
+    const int nst = st + DW_PD;
+    if (nst < steps) {
+      if (nst >= DW_NS) mbar_wait(bar_empty + (nst % DW_NS) * 8, ((nst / DW_NS) - 1) & 1);
+      issue(nst);
+      if (nst + 1 < steps) load_idx(nst + 1);      // indices of the following step: in flight during the MMA
+    }
+    cp_async_commit();
+    cp_async_wait<DW_PD>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      const int stage = st % DW_NS;
+      tc_fence_after();
+      const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t bd = make_desc(sb + kb * lbo_b, lbo_b, 128);
+        for (int h = 0; h < halves; ++h) {
+          const uint64_t ad = make_desc(sa + kb * lbo_a + h * 32 * 128, lbo_a, 128);
+          mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
+        }
+      }
+      tc_commit(bar_empty + stage * 8);
+      if (st == steps - 1) tc_commit(bar_done);
+    }
+  }
+  if (steps > 0) {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+  }
+  // epilogue: accumulator row = input channel, columns = output channels
+  {
+    const int qd = warp & 3, hc = warp >> 2;
+    const int half = Cout >> 1;
+    float *out = partial + (long long)blockIdx.x * Cin * Cout;
+    for (int h = 0; h < halves; ++h) {
+      const int ci = h * 128 + qd * 32 + lane;
+      for (int c0 = hc * half; c0 < (hc + 1) * half; c0 += 8) {
+        uint32_t v[8];
+        if (steps > 0) {
+          tmem_ld8(tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * Cout + c0), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0u;
+        }
+        if (ci < Cin) {
+          float *o = out + (long long)ci * Cout + c0;
+          *reinterpret_cast<float4 *>(o) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          *reinterpret_cast<float4 *>(o + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+}  // namespace tc
+
+// partial[w] (w < n_work) = X[rows]^T @ dY[rows] over the pairs of work item w.  >0: shape not handled.
+int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const DwWork *work, float *partial,
+                  int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,
+                  int precision, cudaStream_t s) {
+  using namespace tc;
+  auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+  if (precision != SCN_PRECISION_TF32) return 1;
+  if (Cin < 8 || Cin % 8 || Cin > 256 || (Cin > 128 && Cin != 256) || Cout < 16 || Cout % 16 || Cout > 256) return 1;
+  if (!al(X) || !al(dY) || !al(partial)) return 1;
+  const int MI = Cin > 128 ? Cin >> 2 : 32;
+  const int KP = (MI * 4 + Cout) <= 256 ? 64 : 32;
+  const DwSmem L(MI, Cout, KP);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem(64, 256, 32).total) !=
+        cudaSuccess) {
+      set_error("cudaFuncSetAttribute(k_dw_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -1;
+    }
+    attr_set = true;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < Cout * (Cin > 128 ? 2 : 1)) cols <<= 1;
+  k_dw_tf32<<<n_work, NT, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("k_dw_tf32 launch failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
 }
 
 }  // namespace scn

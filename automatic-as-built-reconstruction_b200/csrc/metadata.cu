@@ -381,27 +381,31 @@ __global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t 
 // ---------------------------------------------------------------------------------------
 // tile books
 // ---------------------------------------------------------------------------------------
+// mask[r] = set of offsets at which row r has a partner; key[r] = 16-bit hash of the mask (rows are
+// grouped by equal key: two radix passes instead of four, a collision only merges two groups)
 __global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
-                            uint32_t *__restrict__ mask, int32_t *__restrict__ idx) {
+                            uint32_t *__restrict__ mask, uint32_t *__restrict__ key,
+                            int32_t *__restrict__ idx) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   uint32_t m = 0;
   for (int k = 0; k < K; ++k)
     if (T[(long long)k * n + r] >= 0) m |= (1u << k);
   mask[r] = m;
+  key[r] = K <= 16 ? m : (m * 0x9E3779B1u) >> 16;
   idx[r] = (int)r;
 }
 
 // one block per tile: pad the permutation, OR the row masks
 __global__ void __launch_bounds__(TILE_M)
-k_tile_masks(const uint32_t *__restrict__ sorted_mask, const int32_t *__restrict__ sorted_idx,
+k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ sorted_idx,
              long long n, int32_t *__restrict__ perm, uint32_t *__restrict__ tile_mask,
              int32_t *__restrict__ tile_pop) {
   __shared__ uint32_t wm[TILE_M / 32];
   const long long slot = (long long)blockIdx.x * TILE_M + threadIdx.x;
   uint32_t m = 0;
   int row = -1;
-  if (slot < n) { m = sorted_mask[slot]; row = sorted_idx[slot]; }
+  if (slot < n) { row = sorted_idx[slot]; m = row_mask[row]; }
   perm[slot] = row;
   m = __reduce_or_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
@@ -442,13 +446,14 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
     SCN_CUDA(cudaMemsetAsync(meta_slot, 0, 4, s));
     return 0;
   }
-  uint32_t *mask = nullptr;
+  uint32_t *mask = nullptr, *key = nullptr;
   int32_t *idx = nullptr, *pop = nullptr;
   SCN_TRY(dev_alloc_t(&mask, (size_t)n_rows, s));
+  SCN_TRY(dev_alloc_t(&key, (size_t)n_rows, s));
   SCN_TRY(dev_alloc_t(&idx, (size_t)n_rows, s));
-  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, idx);
+  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx);
   SCN_LAUNCHED();
-  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(mask, idx, n_rows, K, s));
+  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(key, idx, n_rows, K < 16 ? K : 16, s));
   SCN_TRY(dev_alloc_t(&tb.perm, (size_t)tb.n_tiles * TILE_M, s));
   SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
   SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
@@ -458,6 +463,7 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   SCN_TRY(exclusive_scan_i32(pop, tb.tile_off, tb.n_tiles, s));
   SCN_CUDA(cudaMemcpyAsync(meta_slot, tb.tile_off + tb.n_tiles, 4, cudaMemcpyDeviceToDevice, s));
   dev_free(mask, s);
+  dev_free(key, s);
   dev_free(idx, s);
   dev_free(pop, s);
   return 0;
@@ -560,9 +566,10 @@ int ensure_tilebook(RuleBook *rb, bool stationary_out, cudaStream_t s) {
 
 int ensure_dw_work(RuleBook *rb, cudaStream_t s) {
   if (rb->dw_work || rb->total_pairs == 0) return 0;
-  long long chunk = (rb->total_pairs + 4LL * num_sms() - 1) / (4LL * num_sms());
-  chunk = (chunk + 31) / 32 * 32;
-  chunk = std::min<long long>(std::max<long long>(chunk, 256), 8192);
+  // ~2 waves of work items: every item costs one Cin x Cout partial (written + re-read by the reduce)
+  long long chunk = (rb->total_pairs + 2LL * num_sms() - 1) / (2LL * num_sms());
+  chunk = (chunk + 63) / 64 * 64;
+  chunk = std::min<long long>(std::max<long long>(chunk, 512), 16384);
   std::vector<DwWork> w;
   for (int k = 0; k < rb->K; ++k) {
     int slot = 0;
