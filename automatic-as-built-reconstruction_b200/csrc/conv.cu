@@ -97,7 +97,7 @@ k_osgemm_ffma(const float *__restrict__ X, const float *__restrict__ W,
         ras[j] = (idx >= 0 && kc + kk < Cin) ? __ldg(X + (long long)idx * Cin + kc + kk) : 0.f;
       }
     }
-    const float *Wk = W + (long long)k * Cin * Cout;
+    const float *Wk = W + (long long)(tb.k_flip >= 0 ? tb.k_flip - k : k) * Cin * Cout;
     if (VB) {
       if (tid < BK * BN / 4) {
         const int kk = tid / (BN / 4), n4 = tid % (BN / 4);
@@ -205,10 +205,11 @@ static int launch_osgemm_ffma(const float *X, const float *W, const float *bias,
   return 0;
 }
 
-TileView make_view(const TileBook &tb) {
+TileView make_view(const TileBook &tb, int k_flip) {
   TileView v;
   v.identity = tb.identity ? 1 : 0;
   v.n_tiles = tb.n_tiles;
+  v.k_flip = k_flip;
   v.perm = tb.perm;
   v.tile_mask = tb.tile_mask;
   v.tile_off = tb.tile_off;
@@ -218,9 +219,9 @@ TileView make_view(const TileBook &tb) {
 
 // Y[stationary rows] = bias + sum_k X[partner_k] @ W[k]   (W: [K,Cin,Cout] row-major)
 int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
-           const TileBook &tb, int precision, int transpose_w, cudaStream_t s) {
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip) {
   if (tb.n_tiles == 0) return 0;
-  const TileView tv = make_view(tb);
+  const TileView tv = make_view(tb, k_flip);
   prof_begin(PROF_GEMM, s);
   int r = 1;
   if (precision != SCN_PRECISION_FP32)
@@ -478,9 +479,14 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
                                 const float *d_out, const float *weight, float *d_weight,
                                 float *d_bias, int Cin, int Cout, int xcol, int ycol,
                                 long long n_dout_rows, int precision, cudaStream_t s) {
-  SCN_TRY(ensure_tilebook(rb, dx_stationary_out, s));
-  TileBook &tb = dx_stationary_out ? rb->tb_out : rb->tb_in;
-  if (d_in) SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s));
+  // submanifold rulebooks with odd filters are their own mirror image: the out-row that in-row i
+  // feeds at offset k is the site at i - delta_k = t_out[K-1-k][i], so dX runs on the forward lists
+  // with the weight index flipped and no second tile book is ever built
+  const bool mirror = rb->kind == 0 && !rb->identity && (rb->filter[0] & rb->filter[1] & rb->filter[2] & 1);
+  if (!mirror) SCN_TRY(ensure_tilebook(rb, dx_stationary_out, s));
+  TileBook &tb = (dx_stationary_out || mirror) ? rb->tb_out : rb->tb_in;
+  if (d_in)
+    SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s, mirror ? rb->K - 1 : -1));
   if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, s));
   SCN_TRY(bias_grad(d_out, d_bias, n_dout_rows, Cout, s));
   return 0;

@@ -7,19 +7,22 @@ namespace scn {
 struct TileView {            // device view of a TileBook, passed by value to kernels
   int identity;
   int n_tiles;
+  int k_flip;                // >= 0: table offset k uses weight slice k_flip - k (submanifold dX), else k
   const int32_t *perm;
   const uint32_t *tile_mask;
   const int32_t *tile_off;
   const int32_t *entries;
 };
 
-TileView make_view(const TileBook &tb);
+TileView make_view(const TileBook &tb, int k_flip = -1);
 
 // Y[stationary] = bias + sum_k X[partner_k] @ Wg[k]; Kd = reduction width (row width of X), N = row
 // width of Y.  transpose_w = 0: Wg[k] = W[k] with W [K,Kd,N]; transpose_w = 1: Wg[k] = W[k]^T with
 // W [K,N,Kd] (the dX pass reads the forward weights in place).
+// k_flip >= 0: the gather lists were built for the mirrored problem (submanifold dX through the
+// forward lists): table offset k pairs with weight slice k_flip - k.
 int osgemm(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
-           const TileBook &tb, int precision, int transpose_w, cudaStream_t s);
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip = -1);
 
 // tensor-core variants. Return 0 = done, >0 = shape/precision not handled (caller uses the FFMA
 // kernels), <0 = -(error) with scn_last_error set.

@@ -221,7 +221,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     if (tid == 0) {
       const uint32_t bytes = (uint32_t)ncore * N * 16;
       mbar_expect_tx(bar_full + stage * 8, bytes);
-      bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)sK[e] * Kd + (long long)c * KC) * N, bytes,
+      const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
+      bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
                     bar_full + stage * 8);
     }
   };
@@ -345,22 +346,30 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
 // ---------------------------------------------------------------------------------------------
 // weight gradient on the tensor cores: partial[w] = X[in rows of work item w]^T @ dY[out rows]
 // M = Cin (zero-padded to 128; two accumulators when Cin = 256), N = Cout, reduction over the pairs.
-// Both operands are gathered rows, i.e. MN-major: pair p lands in k-block p/8, k-row p%8 of the
-// canonical no-swizzle MN-major layout [k-block][16-byte channel piece][8 pairs][16 B].
+// Both operands are gathered rows, i.e. MN-major.  For 32-bit operands tcgen05 accepts MN-major only
+// in the SWIZZLE_128B_BASE32B layout (measured with tools/umma_probe.py: every other layout type
+// yields zeros): atoms of 4 pairs x 128 B (32 channels), the 32-byte chunks of a row XOR-ed with the
+// pair index inside the atom (cute Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>).  Atoms along the
+// channels are 512 B apart (LBO), atoms along the pairs SBO = 512 * channel-atoms apart.
 // ---------------------------------------------------------------------------------------------
 namespace tc {
 
 constexpr int DW_NS = 3;   // stages
 constexpr int DW_PD = 1;   // prefetch distance
 
+__device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return make_desc(saddr, lbo, sbo) | (1ull << 61);   // layout_type 1 = SWIZZLE_128B_BASE32B
+}
+
 struct DwSmem {
-  int a, b, bars, tmem_slot, total, a_stage, b_stage;
-  __host__ __device__ DwSmem(int MI, int Cout, int KP) {
-    a_stage = KP * MI * 16;
-    b_stage = KP * Cout * 4;
+  int a, b, pairs, bars, tmem_slot, total, a_stage, b_stage;
+  __host__ __device__ DwSmem(int MA, int NA, int KP) {
+    a_stage = KP * MA * 128;
+    b_stage = KP * NA * 128;
     a = 0;
     b = a + DW_NS * a_stage;
-    bars = b + DW_NS * b_stage;
+    pairs = b + DW_NS * b_stage;
+    bars = pairs + 2 * KP * 8;
     tmem_slot = bars + (DW_NS + 1) * 8;
     total = tmem_slot + 16;
   }
@@ -370,18 +379,21 @@ __global__ void __launch_bounds__(NT)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
           long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int MI = Cin > 128 ? Cin >> 2 : 32;       // 16-byte channel pieces per k-block of A (M padded to 128)
-  const int NI = Cout >> 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
+  const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)
   const int halves = Cin > 128 ? 2 : 1;
-  const DwSmem L(MI, Cout, KP);
+  const DwSmem L(MA, CB, KP);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_empty = smem_u32(smem + L.bars), bar_done = bar_empty + DW_NS * 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
+  int2 *sPairs = reinterpret_cast<int2 *>(smem + L.pairs);      // [2][KP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kr = tid & 7, q = tid >> 3;
-  const int KB = KP >> 3;                          // k-blocks (8 pairs) per step
-  const uint32_t lbo_a = MI * 128, lbo_b = NI * 128;
+  const int j8 = tid & 7, p4 = (tid >> 3) & 3;
+  const int KA = KP >> 2;                          // k-atoms (4 pairs) per step
+  const uint32_t sbo_a = MA * 512, sbo_b = CB * 512;
+  // byte offset of this thread's 16-byte piece inside an atom: row p4, 32B chunk (j8/2)^p4, half j8&1
+  const uint32_t piece = p4 * 128 + ((((uint32_t)j8 >> 1) ^ (uint32_t)p4) << 5) + (j8 & 1) * 16;
 
   long long start;
   int len;
@@ -393,16 +405,29 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     start = (long long)blockIdx.x * ident_chunk;
     len = (int)min((long long)ident_chunk, ident_n - start);
   }
-  // zero the channel pieces that pad M up to 128 (never written by the gathers)
-  if (Cin < 128) {
-    const int pad0 = Cin >> 2, npad = 32 - pad0;
-    const int total16 = DW_NS * KB * npad * 8;     // 16-byte units
+  // zero the atoms that pad M up to 128 (never written by the gathers)
+  if (CA < MA) {
+    const int per_ka = (MA - CA) * 32;             // 16-byte units per k-atom
+    const int total16 = DW_NS * KA * per_ka;
     for (int i = tid; i < total16; i += NT) {
-      const int r8 = i & 7, rest = i >> 3;
-      const int mi = pad0 + rest % npad, kbs = rest / npad;   // kbs = stage*KB + kb
-      *reinterpret_cast<float4 *>(smem + L.a + (kbs / KB) * L.a_stage + (kbs % KB) * lbo_a + mi * 128 + r8 * 16) =
+      const int ka = i / per_ka, r = i - ka * per_ka;   // ka counts over all stages
+      *reinterpret_cast<float4 *>(smem + L.a + (ka / KA) * L.a_stage + (ka % KA) * sbo_a + CA * 512 + r * 16) =
           make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  auto load_pair = [&](int st) -> int2 {          // pair tid of step st
+    const int p = st * KP + tid;
+    int2 v = make_int2(-1, -1);
+    if (p < len) {
+      if (pairs) v = __ldg(reinterpret_cast<const int2 *>(pairs) + start + p);
+      else v = make_int2((int)(start + p), (int)(start + p));
+    }
+    return v;
+  };
+  const int steps = (len + KP - 1) / KP;
+  if (tid < KP) {
+    sPairs[tid] = load_pair(0);
+    sPairs[KP + tid] = load_pair(1);
   }
   if (tid == 0) {
     for (int i = 0; i < DW_NS + 1; ++i) mbar_init(bar_empty + i * 8, 1);
@@ -414,63 +439,52 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  const int steps = (len + KP - 1) / KP;
   const uint32_t idesc = make_idesc(128, Cout, 1, 1);
 
-  int2 pr[8];
-  auto load_idx = [&](int st) {
-#pragma unroll
-    for (int kb = 0; kb < 8; ++kb) {
-      if (kb < KB) {
-        const int p = st * KP + kb * 8 + kr;
-        int2 v = make_int2(-1, -1);
-        if (p < len) {
-          if (pairs) v = __ldg(reinterpret_cast<const int2 *>(pairs) + start + p);
-          else v = make_int2((int)(start + p), (int)(start + p));
-        }
-        pr[kb] = v;
-      }
-    }
-  };
   auto issue = [&](int st) {
     const int stage = st % DW_NS;
-    const uint32_t sa = a_base + stage * L.a_stage + kr * 16, sb = b_base + stage * L.b_stage + kr * 16;
-#pragma unroll
-    for (int kb = 0; kb < 8; ++kb) {
-      if (kb < KB) {
-        const int xi = xcol ? pr[kb].y : pr[kb].x, yi = ycol ? pr[kb].y : pr[kb].x;
-        const float *xp = X + (long long)(xi < 0 ? 0 : xi) * Cin;
-        const float *yp = dY + (long long)(yi < 0 ? 0 : yi) * Cout;
-        for (int mi = q; mi < (Cin >> 2); mi += 32) cp_async_16(sa + kb * lbo_a + mi * 128, xp + mi * 4, xi < 0 ? 0 : 16);
-        for (int ni = q; ni < NI; ni += 32) cp_async_16(sb + kb * lbo_b + ni * 128, yp + ni * 4, yi < 0 ? 0 : 16);
-      }
+    const int2 *sp = sPairs + (st & 1) * KP;
+    const uint32_t sa = a_base + stage * L.a_stage + piece, sb = b_base + stage * L.b_stage + piece;
+    for (int c = warp; c < KA * CA; c += NT / 32) {
+      const int ka = c / CA, mi = c - ka * CA;
+      const int2 pr = sp[ka * 4 + p4];
+      const int xi = xcol ? pr.y : pr.x;
+      cp_async_16(sa + ka * sbo_a + mi * 512, X + (long long)(xi < 0 ? 0 : xi) * Cin + mi * 32 + j8 * 4, xi < 0 ? 0 : 16);
+    }
+    for (int c = warp; c < KA * CB; c += NT / 32) {
+      const int ka = c / CB, ni = c - ka * CB;
+      const int2 pr = sp[ka * 4 + p4];
+      const int yi = ycol ? pr.y : pr.x;
+      cp_async_16(sb + ka * sbo_b + ni * 512, dY + (long long)(yi < 0 ? 0 : yi) * Cout + ni * 32 + j8 * 4, yi < 0 ? 0 : 16);
     }
   };
 
-  for (int p = 0; p < DW_PD; ++p) {
-    if (p < steps) { load_idx(p); issue(p); }
-    cp_async_commit();
-  }
-  if (DW_PD < steps) load_idx(DW_PD);
+  // DW_PD == 1: step st+1 is issued while the tensor core works on step st
+  if (steps > 0) issue(0);
+  cp_async_commit();
+  __syncthreads();           // pair slot 0 is rewritten in iteration 0
   for (int st = 0; st < steps; ++st) {
     const int nst = st + DW_PD;
+    int2 nxt = make_int2(-1, -1);
+    if (tid < KP && nst + 1 < steps) nxt = load_pair(nst + 1);   // in flight across this iteration
     if (nst < steps) {
       if (nst >= DW_NS) mbar_wait(bar_empty + (nst % DW_NS) * 8, ((nst / DW_NS) - 1) & 1);
       issue(nst);
-      if (nst + 1 < steps) load_idx(nst + 1);      // indices of the following step: in flight during the MMA
     }
     cp_async_commit();
     cp_async_wait<DW_PD>();
     fence_proxy_async();
+    // pair slot (nst+1)&1 == st&1 was last read by issue(st) in the previous iteration
+    if (tid < KP) sPairs[((nst + 1) & 1) * KP + tid] = nxt;
     __syncthreads();
     if (tid == 0) {
       const int stage = st % DW_NS;
       tc_fence_after();
       const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
-      for (int kb = 0; kb < KB; ++kb) {
-        const uint64_t bd = make_desc(sb + kb * lbo_b, lbo_b, 128);
+      for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
+        const uint64_t bd = make_desc_b32(sb + kb * 2 * sbo_b, 512, sbo_b);
         for (int h = 0; h < halves; ++h) {
-          const uint64_t ad = make_desc(sa + kb * lbo_a + h * 32 * 128, lbo_a, 128);
+          const uint64_t ad = make_desc_b32(sa + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
           mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
         }
       }
@@ -520,14 +534,14 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   using namespace tc;
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
   if (precision != SCN_PRECISION_TF32) return 1;
-  if (Cin < 8 || Cin % 8 || Cin > 256 || (Cin > 128 && Cin != 256) || Cout < 16 || Cout % 16 || Cout > 256) return 1;
+  if (Cin < 32 || Cin % 32 || (Cin > 128 && Cin != 256) || Cout < 32 || Cout % 32 || Cout > 256) return 1;
   if (!al(X) || !al(dY) || !al(partial)) return 1;
-  const int MI = Cin > 128 ? Cin >> 2 : 32;
-  const int KP = (MI * 4 + Cout) <= 256 ? 64 : 32;
-  const DwSmem L(MI, Cout, KP);
+  const int MA = Cin > 128 ? Cin >> 5 : 4, NA = Cout >> 5;
+  const int KP = (MA + NA) <= 8 ? 64 : 32;
+  const DwSmem L(MA, NA, KP);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem(64, 256, 32).total) !=
+    if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem(8, 8, 32).total) !=
         cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_dw_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return -1;

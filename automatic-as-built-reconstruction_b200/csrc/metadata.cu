@@ -489,7 +489,7 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   SCN_CHECK(total < (1LL << 31), "rulebook table too large (%lld entries)", total);
   int32_t *pos = nullptr, *meta = nullptr;
   SCN_TRY(dev_alloc_t(&pos, (size_t)total + 1, s));
-  SCN_TRY(dev_alloc_t(&meta, (size_t)K + 4, s));
+  SCN_TRY(dev_alloc_t(&meta, (size_t)K + 8, s));
   if (total > 0) {
     k_flag_table<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, total);
     SCN_LAUNCHED();
@@ -498,10 +498,14 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   k_pair_offsets<<<1, 64, 0, s>>>(pos, n, K, meta);
   SCN_LAUNCHED();
   SCN_TRY(tilebook_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s));
+  // strided rulebooks also carry the in-stationary lists (conv dX, deconv forward); building them
+  // here shares this read-back, so the backward pass never synchronises
+  const bool both = rb->kind == 1 && rb->t_in != nullptr;
+  if (both) SCN_TRY(tilebook_phase1(rb->tb_in, rb->t_in, K, rb->n_in, rb->n_out, meta + K + 2, s));
   int64_t *hs = host_scratch(64);
   int32_t *h32 = (int32_t *)hs;
-  SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)(K + 2) * 4, cudaMemcpyDeviceToHost, s));
-  SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back: pair counts + entry total
+  SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)(K + 3) * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back: pair counts + entry totals
   for (int k = 0; k <= K; ++k) rb->pair_off[k] = h32[k];
   for (int k = 0; k < K; ++k) rb->counts[k] = h32[k + 1] - h32[k];
   rb->total_pairs = h32[K];
@@ -512,6 +516,11 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   }
   SCN_TRY(tilebook_phase2(rb->tb_out, rb->t_out, h32[K + 1], s));
   rb->tb_out.n_pairs = rb->total_pairs;
+  if (both) {
+    SCN_TRY(tilebook_phase2(rb->tb_in, rb->t_in, h32[K + 2], s));
+    rb->tb_in.n_pairs = rb->total_pairs;
+  }
+  SCN_TRY(ensure_dw_work(rb, s));
   dev_free(pos, s);
   dev_free(meta, s);
   return 0;
@@ -570,7 +579,8 @@ int ensure_dw_work(RuleBook *rb, cudaStream_t s) {
   long long chunk = (rb->total_pairs + 2LL * num_sms() - 1) / (2LL * num_sms());
   chunk = (chunk + 63) / 64 * 64;
   chunk = std::min<long long>(std::max<long long>(chunk, 512), 16384);
-  std::vector<DwWork> w;
+  std::vector<DwWork> &w = rb->dw_host;
+  w.clear();
   for (int k = 0; k < rb->K; ++k) {
     int slot = 0;
     for (long long st = 0; st < rb->counts[k]; st += chunk) {
@@ -585,9 +595,9 @@ int ensure_dw_work(RuleBook *rb, cudaStream_t s) {
   rb->n_dw_work = (int)w.size();
   rb->dw_chunk = (int)chunk;
   SCN_TRY(dev_alloc_t(&rb->dw_work, w.size(), s));
+  // pageable source: staged by the driver before the call returns; rb->dw_host outlives it anyway
   SCN_CUDA(cudaMemcpyAsync(rb->dw_work, w.data(), w.size() * sizeof(DwWork),
                            cudaMemcpyHostToDevice, s));
-  SCN_CUDA(cudaStreamSynchronize(s));  // host vector dies at return
   return 0;
 }
 

@@ -55,6 +55,7 @@ struct RuleBook {                 // Metadata.h:35 RuleBook + its derived gather
   TileBook tb_out;                // stationary = out rows, gathers in rows
   TileBook tb_in;                 // stationary = in rows, gathers out rows
   DwWork *dw_work = nullptr;      // device work list for the weight gradient
+  std::vector<DwWork> dw_host;    // its host image (kept alive for the asynchronous upload)
   int n_dw_work = 0;
   int dw_chunk = 0;
 };

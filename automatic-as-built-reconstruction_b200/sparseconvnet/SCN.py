@@ -69,6 +69,20 @@ class Metadata_3(object):
         check(lib.scn_get_spatial_locations_device(self._h, i64x3(spatial_size), ptr(out), stream()))
         return out
 
+    # ---- eager rulebook construction (B200 extension) ---------------------------------------
+    # The reference builds rulebooks lazily inside the first layer that needs them
+    # (Metadata.cpp:430-512); every build reads counts back to the host.  Building the whole
+    # network's rulebooks up front keeps those read-backs out of the feature-kernel stream.
+    def prepareSubmanifoldRuleBook(self, spatial_size, filter_size):
+        check(lib.scn_submanifold_rulebook_prepare(self._h, i64x3(spatial_size), i64x3(filter_size),
+                                                   stream(), None))
+
+    def prepareRuleBook(self, in_size, out_size, filter_size, filter_stride):
+        n_out = c_int64()
+        check(lib.scn_conv_rulebook_prepare(self._h, i64x3(in_size), i64x3(out_size), i64x3(filter_size),
+                                            i64x3(filter_stride), stream(), byref(n_out), None))
+        return n_out.value
+
     # ---- rulebook export (parity tests; reference: Metadata.h:35 RuleBook) ----------------
     def inputLayerRuleBook(self):
         hd = (c_int64 * 4)()

@@ -98,7 +98,27 @@ class FPN_Net(torch.nn.Module):
     def forward(self, net0):
         if CHECK_NAN and not torch.isnan(self.layers_in[1].weight).sum() == 0:
             raise FloatingPointError("FPN_Net: NaN in stem weights")
-        return self.forward_fpn(self.layers_in(net0))
+        net = self.layers_in[0](net0)                  # InputLayer: voxel hashing
+        self._prebuild_rulebooks(net)
+        return self.forward_fpn(self.layers_in[1](net))
+
+    def _prebuild_rulebooks(self, net):
+        """Build every hash grid / rulebook the graph below will ask for, back to back, before any
+        feature kernel is queued.  Each build needs a count read-back; done lazily (as the reference
+        does, layer by layer) those read-backs would drain the GPU between layers."""
+        m, ss = net.metadata, net.spatial_size
+        three = torch.tensor([3] * self.dimension)
+        for k in range(len(self.m_downs)):
+            m.prepareSubmanifoldRuleBook(ss, three)
+            if k + 1 < len(self.m_downs):
+                fs, st = torch.tensor(self.down_kernels[k]), torch.tensor(self.down_strides[k])
+                out = (ss - fs) // st + 1
+                m.prepareRuleBook(ss, out, fs, st)
+                ss = out
+        for conv, size in zip(self.convs_pro2d, self.rpn_map_sizes):
+            size = torch.tensor([int(v) for v in size])
+            m.prepareRuleBook(size, (size - conv.filter_size) // conv.filter_stride + 1, conv.filter_size,
+                              conv.filter_stride)
 
     def forward_fpn(self, net):
         n_scales = len(self.m_downs)
