@@ -169,39 +169,39 @@ int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_
 }
 
 // ---------------------------------------------------------------------------------------
-// stable LSD radix sort, 8-bit digits; every warp owns one contiguous chunk
+// stable LSD radix sort, 9-bit digits (27-bit neighbour masks = 3 passes); every warp owns one contiguous chunk
 // ---------------------------------------------------------------------------------------
-constexpr int RS_WARPS = 8, RS_CHUNK = 2048;
+constexpr int RS_WARPS = 8, RS_CHUNK = 2048, RS_BITS = 9, RS_BINS = 1 << RS_BITS;
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rs_hist(const uint32_t *__restrict__ keys, int32_t *__restrict__ H, long long n, int shift,
           int n_chunks) {
-  __shared__ int32_t hist[RS_WARPS][256];
+  __shared__ int32_t hist[RS_WARPS][RS_BINS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * RS_WARPS + w;
-  for (int d = lane; d < 256; d += 32) hist[w][d] = 0;
+  for (int d = lane; d < RS_BINS; d += 32) hist[w][d] = 0;
   __syncwarp();
   if (chunk < n_chunks) {
     const long long b = (long long)chunk * RS_CHUNK;
     for (int it = 0; it < RS_CHUNK; it += 32) {
       long long g = b + it + lane;
-      if (g < n) atomicAdd(&hist[w][(keys[g] >> shift) & 255], 1);
+      if (g < n) atomicAdd(&hist[w][(keys[g] >> shift) & (RS_BINS - 1)], 1);
     }
   }
   __syncwarp();
   if (chunk < n_chunks)
-    for (int d = lane; d < 256; d += 32) H[(long long)d * n_chunks + chunk] = hist[w][d];
+    for (int d = lane; d < RS_BINS; d += 32) H[(long long)d * n_chunks + chunk] = hist[w][d];
 }
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals,
              uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out,
              const int32_t *__restrict__ Hs, long long n, int shift, int n_chunks) {
-  __shared__ int32_t cnt[RS_WARPS][256];
+  __shared__ int32_t cnt[RS_WARPS][RS_BINS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * RS_WARPS + w;
   if (chunk >= n_chunks) return;
-  for (int d = lane; d < 256; d += 32) cnt[w][d] = Hs[(long long)d * n_chunks + chunk];
+  for (int d = lane; d < RS_BINS; d += 32) cnt[w][d] = Hs[(long long)d * n_chunks + chunk];
   __syncwarp();
   const long long b = (long long)chunk * RS_CHUNK;
   const unsigned lt = (1u << lane) - 1u;
@@ -210,7 +210,7 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals
     const bool valid = g < n;
     uint32_t key = valid ? keys[g] : 0u;
     int32_t val = valid ? vals[g] : 0;
-    const int d = valid ? (int)((key >> shift) & 255) : 256 + lane;
+    const int d = valid ? (int)((key >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & lt);
     if (valid) {
@@ -226,21 +226,21 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals
 
 int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s) {
   if (n <= 1 || bits <= 0) return 0;
-  const int passes = (bits + 7) / 8;
+  const int passes = (bits + RS_BITS - 1) / RS_BITS;
   const int n_chunks = cdiv(n, RS_CHUNK);
   const int nb = cdiv(n_chunks, RS_WARPS);
   uint32_t *k2 = nullptr;
   int32_t *v2 = nullptr, *H = nullptr;
   SCN_TRY(dev_alloc_t(&k2, (size_t)n, s));
   SCN_TRY(dev_alloc_t(&v2, (size_t)n, s));
-  SCN_TRY(dev_alloc_t(&H, (size_t)256 * n_chunks + 1, s));
+  SCN_TRY(dev_alloc_t(&H, (size_t)RS_BINS * n_chunks + 1, s));
   uint32_t *ka = keys, *kb = k2;
   int32_t *va = vals, *vb = v2;
   for (int p = 0; p < passes; ++p) {
-    k_rs_hist<<<nb, RS_WARPS * 32, 0, s>>>(ka, H, n, p * 8, n_chunks);
+    k_rs_hist<<<nb, RS_WARPS * 32, 0, s>>>(ka, H, n, p * RS_BITS, n_chunks);
     SCN_LAUNCHED();
-    SCN_TRY(exclusive_scan_i32(H, H, (long long)256 * n_chunks, s));
-    k_rs_scatter<<<nb, RS_WARPS * 32, 0, s>>>(ka, va, kb, vb, H, n, p * 8, n_chunks);
+    SCN_TRY(exclusive_scan_i32(H, H, (long long)RS_BINS * n_chunks, s));
+    k_rs_scatter<<<nb, RS_WARPS * 32, 0, s>>>(ka, va, kb, vb, H, n, p * RS_BITS, n_chunks);
     SCN_LAUNCHED();
     uint32_t *tk = ka; ka = kb; kb = tk;
     int32_t *tv = va; va = vb; vb = tv;

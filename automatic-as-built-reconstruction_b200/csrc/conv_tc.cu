@@ -154,8 +154,9 @@ struct Smem {
 
 __global__ void __launch_bounds__(NT)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
-              float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t tmem_cols) {
-  extern __shared__ __align__(128) uint8_t smem[];
+              float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t tmem_cols,
+              float *__restrict__ Ypart) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L(N, K);
   int32_t(*sIdx)[TILE_M] = reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.idx);
   int32_t *sPerm = reinterpret_cast<int32_t *>(smem + L.perm);
@@ -199,12 +200,17 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
+  // split-K for small grids: CTA (tile, split) owns the steps split, split+S, ... and writes a partial
+  // tile that k_splitk_reduce sums in fixed order
   const int kchunks = (Kd + KC - 1) / KC;
-  const int steps = nE * kchunks;
+  const int splits = gridDim.y, split = blockIdx.y;
+  const int all_steps = nE * kchunks;
+  const int steps = all_steps > split ? (all_steps - split + splits - 1) / splits : 0;
   const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
 
-  auto issue = [&](int st) {
-    const int stage = st % NS;
+  auto issue = [&](int lst) {
+    const int stage = lst % NS;
+    const int st = split + lst * splits;
     const int e = st / kchunks, c = st - e * kchunks;
     const int ncore = min(NCORE, (Kd - c * KC) >> 2);
     const int j = tid & 7;
@@ -245,7 +251,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     __syncthreads();
     if (tid == 0) {
       const int stage = st % NS;
-      const int c = st % kchunks;
+      const int c = (split + st * splits) % kchunks;
       const int ncore = min(NCORE, (Kd - c * KC) >> 2);
       mbar_wait(bar_full + stage * 8, (st / NS) & 1);
       tc_fence_after();
@@ -268,9 +274,14 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   {
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
-    const int orow = sPerm[row];
+    int orow = sPerm[row];
     const int half = N >> 1;                // N % 16 == 0  ->  half % 8 == 0
     float *yp = Y + (long long)(orow < 0 ? 0 : orow) * N;
+    if (splits > 1) {                       // partial tile, slot order, no bias
+      orow = 0;
+      bias = nullptr;
+      yp = Ypart + (((long long)split * gridDim.x + tile) * TILE_M + row) * N;
+    }
     for (int c0 = h * half; c0 < (h + 1) * half; c0 += 8) {
       uint32_t v[8];
       if (steps > 0) {
@@ -298,6 +309,24 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// Y[perm[slot]] = bias + sum_s Ypart[s][slot]   (fixed summation order)
+__global__ void k_splitk_reduce(const float *__restrict__ Ypart, const float *__restrict__ bias, float *__restrict__ Y,
+                                int N, int splits, long long n_slots, long long n_rows, TileView tb) {
+  const int q = N >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots * q) return;
+  const long long slot = i / q;
+  const int c = (int)(i - slot * q) * 4;
+  const long long orow = tb.identity ? (slot < n_rows ? slot : -1) : tb.perm[slot];
+  if (orow < 0) return;
+  float4 a = bias ? *reinterpret_cast<const float4 *>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4 *>(Ypart + ((long long)s * n_slots + slot) * N + c);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4 *>(Y + orow * N + c) = a;
+}
+
 static bool tf32_shape_ok(const float *X, const float *W, const float *bias, float *Y, int Kd, int N) {
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
   return Kd >= 8 && Kd % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
@@ -323,7 +352,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const Smem L(N, K);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_osgemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem(256, MAX_K).total) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_osgemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       dev_free(wp, s);
       return -1;
@@ -332,9 +361,30 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   }
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
-  k_osgemm_tf32<<<tv.n_tiles, NT, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols);
+  // small grids leave most SMs idle while one CTA walks K * Kd/32 latency-bound steps: split the
+  // steps over up to 32 CTAs per tile (each keeps >= 4 steps even for one active offset)
+  int splits = 1;
+  const int kchunks = (Kd + KC - 1) / KC;
+  if (tv.n_tiles * 2 <= num_sms() && !tv.identity) {
+    splits = num_sms() / tv.n_tiles;
+    const int max_split = (K * kchunks + 3) / 4;
+    if (splits > max_split) splits = max_split;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+  }
+  float *ypart = nullptr;
+  const long long n_slots = (long long)tv.n_tiles * TILE_M;
+  if (splits > 1 && dev_alloc_t(&ypart, (size_t)splits * n_slots * N, s)) { dev_free(wp, s); return -1; }
+  k_osgemm_tf32<<<dim3(tv.n_tiles, splits), NT, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
+  if (splits > 1 && e == cudaSuccess) {
+    const long long work = n_slots * (N >> 2);
+    k_splitk_reduce<<<cdiv(work, 256), 256, 0, s>>>(ypart, bias, Y, N, splits, n_slots, n_rows, tv);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+  }
+  dev_free(ypart, s);
   dev_free(wp, s);
   if (e != cudaSuccess) {
     set_error("k_osgemm_tf32 launch failed: %s", cudaGetErrorString(e));
@@ -541,7 +591,7 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   const DwSmem L(MA, NA, KP);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem(8, 8, 32).total) !=
+    if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_dw_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return -1;

@@ -381,8 +381,8 @@ __global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t 
 // ---------------------------------------------------------------------------------------
 // tile books
 // ---------------------------------------------------------------------------------------
-// mask[r] = set of offsets at which row r has a partner; key[r] = 16-bit hash of the mask (rows are
-// grouped by equal key: two radix passes instead of four, a collision only merges two groups)
+// mask[r] = set of offsets at which row r has a partner = the sort key: rows are ordered by mask value,
+// so a tile holds rows whose masks share their high offsets and its union mask stays small
 __global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
                             uint32_t *__restrict__ mask, uint32_t *__restrict__ key,
                             int32_t *__restrict__ idx) {
@@ -392,7 +392,7 @@ __global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
   for (int k = 0; k < K; ++k)
     if (T[(long long)k * n + r] >= 0) m |= (1u << k);
   mask[r] = m;
-  key[r] = K <= 16 ? m : (m * 0x9E3779B1u) >> 16;
+  key[r] = m;
   idx[r] = (int)r;
 }
 
@@ -453,7 +453,7 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   SCN_TRY(dev_alloc_t(&idx, (size_t)n_rows, s));
   k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx);
   SCN_LAUNCHED();
-  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(key, idx, n_rows, K < 16 ? K : 16, s));
+  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(key, idx, n_rows, K, s));
   SCN_TRY(dev_alloc_t(&tb.perm, (size_t)tb.n_tiles * TILE_M, s));
   SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
   SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
