@@ -25,9 +25,8 @@ constexpr int KC = 32;                      // reduction elements per pipeline s
 constexpr int NCORE = KC / 4;               // 16-byte k-cores (4 tf32) per step
 constexpr int A_LBO = TILE_M * 16 + 16;     // bytes between k-cores of A (+16: bank spread for the gather)
 constexpr int A_STAGE = NCORE * A_LBO;      // 16512
-constexpr int NS = 4;                       // pipeline stages
-constexpr int PD = 2;                       // prefetch distance (steps issued ahead of the MMA)
-constexpr int NT = 256;                     // threads
+constexpr int NT = 256;                     // threads of the weight-gradient kernel
+constexpr int NT_GEMM = 192;                // gather-GEMM: 4 producer/epilogue warps + MMA warp + weight-loader warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -140,32 +139,46 @@ __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
   int a, b, idx, perm, kofs, bars, tmem_slot, total;
-  __host__ __device__ Smem(int N, int K) {
+  __host__ __device__ Smem(int N, int K, int ns) {
     a = 0;
-    b = a + NS * A_STAGE;
-    idx = b + NS * NCORE * N * 16;
+    b = a + ns * A_STAGE;
+    idx = b + ns * NCORE * N * 16;
     perm = idx + K * TILE_M * 4;
     kofs = perm + TILE_M * 4;
     bars = kofs + 64;
-    tmem_slot = bars + (2 * NS + 1) * 8;
+    tmem_slot = bars + (3 * ns + 1) * 8;
     total = tmem_slot + 16;
   }
 };
 
-__global__ void __launch_bounds__(NT)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+// Warp-specialised: warps 0-3 gather the A rows (and run the epilogue), warp 4 issues the MMAs,
+// warp 5 streams the packed weight slices.  Nobody meets at a CTA-wide barrier inside the main loop:
+//   fullA[stage]  128 producer arrivals - each thread arrives for step s once ITS cp.async group of
+//                 step s has landed (it is by then NSTAGE-1 steps further down the road) and it has
+//                 fenced the generic->async proxy
+//   fullB[stage]  expect_tx / complete_tx of the weight slice's cp.async.bulk
+//   empty[stage]  tcgen05.commit: the MMAs that read the stage have retired
+template <int NSTAGE>
+__global__ void __launch_bounds__(NT_GEMM)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t tmem_cols,
               float *__restrict__ Ypart) {
+  constexpr int DEPTH = NSTAGE - 1;               // steps a producer runs ahead of its own arrivals
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Smem L(N, K);
+  const Smem L(N, K, NSTAGE);
   int32_t(*sIdx)[TILE_M] = reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.idx);
   int32_t *sPerm = reinterpret_cast<int32_t *>(smem + L.perm);
   int8_t *sK = reinterpret_cast<int8_t *>(smem + L.kofs);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
-  const uint32_t bar_full = smem_u32(smem + L.bars);            // [NS] weight slice landed
-  const uint32_t bar_empty = bar_full + NS * 8;                 // [NS] MMAs that read the stage retired
-  const uint32_t bar_done = bar_empty + NS * 8;                 // accumulator complete
+  const uint32_t bar_fullA = smem_u32(smem + L.bars);
+  const uint32_t bar_fullB = bar_fullA + NSTAGE * 8;
+  const uint32_t bar_empty = bar_fullB + NSTAGE * 8;
+  const uint32_t bar_done = bar_empty + NSTAGE * 8;
   const int B_STAGE = NCORE * N * 16;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -187,11 +200,16 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     const int e0 = tb.tile_off[tile];
     nE = __popc(mask);
     if (tid < TILE_M) sPerm[tid] = tb.perm[(long long)tile * TILE_M + tid];
-    for (int i = tid; i < nE * TILE_M; i += NT) sIdx[i / TILE_M][i % TILE_M] = tb.entries[(long long)e0 * TILE_M + i];
+    for (int i = tid; i < nE * TILE_M; i += NT_GEMM) sIdx[i / TILE_M][i % TILE_M] = tb.entries[(long long)e0 * TILE_M + i];
     if (tid < 32 && (mask & (1u << tid))) sK[__popc(mask & ((1u << tid) - 1u))] = (int8_t)tid;
   }
   if (tid == 0) {
-    for (int i = 0; i < 2 * NS + 1; ++i) mbar_init(bar_full + i * 8, 1);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(bar_fullA + i * 8, 128);
+      mbar_init(bar_fullB + i * 8, 1);
+      mbar_init(bar_empty + i * 8, 1);
+    }
+    mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
@@ -206,86 +224,93 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   const int splits = gridDim.y, split = blockIdx.y;
   const int all_steps = nE * kchunks;
   const int steps = all_steps > split ? (all_steps - split + splits - 1) / splits : 0;
-  const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
 
-  auto issue = [&](int lst) {
-    const int stage = lst % NS;
-    const int st = split + lst * splits;
-    const int e = st / kchunks, c = st - e * kchunks;
-    const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-    const int j = tid & 7;
-    if (j < ncore) {
-      const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
-      const float *colp = X + c * KC + j * 4;
-#pragma unroll
-      for (int i = 0; i < TILE_M / 32; ++i) {
-        const int row = (tid >> 3) + 32 * i;
-        const int idx = sIdx[e][row];
-        cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
-      }
-    }
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)ncore * N * 16;
-      mbar_expect_tx(bar_full + stage * 8, bytes);
-      const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
-      bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
-                    bar_full + stage * 8);
-    }
-  };
-
-  // one cp.async group per step (empty past the end), so wait_group<PD> always means "step st landed"
-  for (int p = 0; p < PD; ++p) {
-    if (p < steps) issue(p);
-    cp_async_commit();
-  }
-  for (int st = 0; st < steps; ++st) {
-    const int nst = st + PD;
-    if (nst < steps) {
-      // the stage was last read by the MMAs of step nst-NS (issued NS-PD iterations ago)
-      if (nst >= NS) mbar_wait(bar_empty + (nst % NS) * 8, ((nst / NS) - 1) & 1);
-      issue(nst);
-    }
-    cp_async_commit();
-    cp_async_wait<PD>();
-    fence_proxy_async();      // generic-proxy smem writes (cp.async) -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
-      const int stage = st % NS;
-      const int c = (split + st * splits) % kchunks;
+  if (warp < 4) {
+    // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
+    const int j = tid & 7, r0 = tid >> 3;
+    for (int lst = 0; lst < steps; ++lst) {
+      const int stage = lst % NSTAGE, use = lst / NSTAGE;
+      if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+      const int st = split + lst * splits;
+      const int e = st / kchunks, c = st - e * kchunks;
       const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-      mbar_wait(bar_full + stage * 8, (st / NS) & 1);
-      tc_fence_after();
-      const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
-      for (int kk = 0; kk < (ncore >> 1); ++kk) {
-        const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
-        const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
-        mma_tf32(tmem_d, ad, bd, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+      if (j < ncore) {
+        const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
+        const float *colp = X + c * KC + j * 4;
+#pragma unroll
+        for (int i = 0; i < TILE_M / 16; ++i) {
+          const int row = r0 + 16 * i;
+          const int idx = sIdx[e][row];
+          cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
+        }
       }
-      tc_commit(bar_empty + stage * 8);
-      if (st == steps - 1) tc_commit(bar_done);
+      cp_async_commit();
+      if (lst >= DEPTH) {
+        cp_async_wait<DEPTH>();                 // this thread's gathers of step lst-DEPTH have landed
+        fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(bar_fullA + ((lst - DEPTH) % NSTAGE) * 8);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int lst = (steps > DEPTH ? steps - DEPTH : 0); lst < steps; ++lst) mbar_arrive(bar_fullA + (lst % NSTAGE) * 8);
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
+      for (int lst = 0; lst < steps; ++lst) {
+        const int stage = lst % NSTAGE, use = lst / NSTAGE;
+        const int c = (split + lst * splits) % kchunks;
+        const int ncore = min(NCORE, (Kd - c * KC) >> 2);
+        mbar_wait(bar_fullB + stage * 8, use & 1);
+        mbar_wait(bar_fullA + stage * 8, use & 1);
+        tc_fence_after();
+        const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
+        for (int kk = 0; kk < (ncore >> 1); ++kk) {
+          const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
+          const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
+          mma_tf32(tmem_d, ad, bd, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(bar_empty + stage * 8);
+      }
+      if (steps > 0) tc_commit(bar_done);
+    }
+  } else if (warp == 5) {
+    // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
+    if (lane == 0) {
+      for (int lst = 0; lst < steps; ++lst) {
+        const int stage = lst % NSTAGE, use = lst / NSTAGE;
+        if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+        const int st = split + lst * splits;
+        const int e = st / kchunks, c = st - e * kchunks;
+        const int ncore = min(NCORE, (Kd - c * KC) >> 2);
+        const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
+        const uint32_t bytes = (uint32_t)ncore * N * 16;
+        mbar_expect_tx(bar_fullB + stage * 8, bytes);
+        bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
+                      bar_fullB + stage * 8);
+      }
     }
   }
 
-  // ---- epilogue: TMEM -> registers -> global; warp w reads lane quadrant w&3, column half w>>2 ----
-  if (steps > 0) {
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-  }
-  {
-    const int q = warp & 3, h = warp >> 2;
-    const int row = q * 32 + lane;
+  // ---- epilogue (warps 0-3): TMEM -> registers -> global; warp w owns accumulator lanes 32w.. ----
+  if (warp < 4) {
+    if (steps > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
+    const int row = warp * 32 + lane;
     int orow = sPerm[row];
-    const int half = N >> 1;                // N % 16 == 0  ->  half % 8 == 0
     float *yp = Y + (long long)(orow < 0 ? 0 : orow) * N;
     if (splits > 1) {                       // partial tile, slot order, no bias
       orow = 0;
       bias = nullptr;
       yp = Ypart + (((long long)split * gridDim.x + tile) * TILE_M + row) * N;
     }
-    for (int c0 = h * half; c0 < (h + 1) * half; c0 += 8) {
+    for (int c0 = 0; c0 < N; c0 += 8) {
       uint32_t v[8];
       if (steps > 0) {
-        tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -349,10 +374,14 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int cin = transpose_w ? N : Kd, cout = transpose_w ? Kd : N;
   k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  const Smem L(N, K);
+  // stages by accumulator width: the ring takes what is left of ~210 KB after the index lists
+  const int ns = N > 128 ? 3 : (N > 64 ? 5 : 7);
+  const Smem L(N, K, ns);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_osgemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_osgemm_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_osgemm_tf32<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_osgemm_tf32<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       dev_free(wp, s);
       return -1;
@@ -375,7 +404,10 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   float *ypart = nullptr;
   const long long n_slots = (long long)tv.n_tiles * TILE_M;
   if (splits > 1 && dev_alloc_t(&ypart, (size_t)splits * n_slots * N, s)) { dev_free(wp, s); return -1; }
-  k_osgemm_tf32<<<dim3(tv.n_tiles, splits), NT, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
+  const dim3 grid(tv.n_tiles, splits);
+  if (ns == 3) k_osgemm_tf32<3><<<grid, NT_GEMM, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
+  else if (ns == 5) k_osgemm_tf32<5><<<grid, NT_GEMM, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
+  else k_osgemm_tf32<7><<<grid, NT_GEMM, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (splits > 1 && e == cudaSuccess) {
