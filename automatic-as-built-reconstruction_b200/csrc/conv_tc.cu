@@ -374,8 +374,10 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int cin = transpose_w ? N : Kd, cout = transpose_w ? Kd : N;
   k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  // stages by accumulator width: the ring takes what is left of ~210 KB after the index lists
-  const int ns = N > 128 ? 3 : (N > 64 ? 5 : 7);
+  // 3 stages (two steps of gathers in flight per CTA) keep a CTA at <= ~112 KB of shared memory for
+  // N <= 128, so two CTAs share an SM: tiles are short (4-30 steps) and one CTA's prologue / epilogue
+  // hides behind the other's main loop
+  const int ns = 3;
   const Smem L(N, K, ns);
   static bool attr_set = false;
   if (!attr_set) {
