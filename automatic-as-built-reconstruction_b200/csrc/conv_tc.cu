@@ -136,17 +136,19 @@ __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // the gather-GEMM kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int MS = 4;                        // tile-metadata slots (producers may run ~3 tiles ahead of the epilogue)
+constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight loader, 4 epilogue, metadata loader
+
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
-  int a, b, idx, perm, kofs, bars, tmem_slot, total;
+  int a, b, meta, meta_bytes, bars, tmem_slot, total;
   __host__ __device__ Smem(int N, int K, int ns) {
     a = 0;
     b = a + ns * A_STAGE;
-    idx = b + ns * NCORE * N * 16;
-    perm = idx + K * TILE_M * 4;
-    kofs = perm + TILE_M * 4;
-    bars = kofs + 64;
-    tmem_slot = bars + (3 * ns + 1) * 8;
+    meta = b + ns * NCORE * N * 16;
+    meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
+    bars = meta + MS * meta_bytes;
+    tmem_slot = bars + (3 * ns + 2 * MS + 4) * 8;
     total = tmem_slot + 16;
   }
 };
@@ -154,184 +156,282 @@ struct Smem {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 
-// Warp-specialised: warps 0-3 gather the A rows (and run the epilogue), warp 4 issues the MMAs,
-// warp 5 streams the packed weight slices.  Nobody meets at a CTA-wide barrier inside the main loop:
-//   fullA[stage]  128 producer arrivals - each thread arrives for step s once ITS cp.async group of
-//                 step s has landed (it is by then NSTAGE-1 steps further down the road) and it has
-//                 fenced the generic->async proxy
-//   fullB[stage]  expect_tx / complete_tx of the weight slice's cp.async.bulk
-//   empty[stage]  tcgen05.commit: the MMAs that read the stage have retired
+// Persistent, warp-specialised gather-GEMM.  A CTA walks work items (tile, split) round-robin; five
+// roles run decoupled through mbarrier rings, so the gathers of the next tiles, the MMAs of the
+// current one and the write-back of the previous one overlap:
+//   warp 10      metadata loader: tile's gather lists / row permutation / offset list -> smem slot
+//   warps 0-3    A producers: 16-byte cp.async gathers of the partner rows (zero-fill), one commit group
+//                per step; the arrival for a step is posted NSTAGE-1 steps later, after
+//                cp.async.wait_group + fence.proxy.async - a producer never waits for fresh data
+//   warp 5       weight loader: one cp.async.bulk (TMA) per step of the packed B slice
+//   warp 4       MMA issuer: tcgen05.mma.kind::tf32 into one of two TMEM accumulators
+//   warps 6-9    epilogue: tcgen05.ld -> (+bias) -> each stationary row written once
+// Rings: fullA/fullB/empty per smem stage, meta_full/meta_empty per metadata slot,
+// tmem_full/tmem_empty per accumulator.
 template <int NSTAGE>
-__global__ void __launch_bounds__(NT_GEMM)
+__global__ void __launch_bounds__(NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
-              float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t tmem_cols,
-              float *__restrict__ Ypart) {
-  constexpr int DEPTH = NSTAGE - 1;               // steps a producer runs ahead of its own arrivals
+              float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t acc_cols,
+              float *__restrict__ Ypart, int n_items, int splits) {
+  constexpr int DEPTH = NSTAGE - 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L(N, K, NSTAGE);
-  int32_t(*sIdx)[TILE_M] = reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.idx);
-  int32_t *sPerm = reinterpret_cast<int32_t *>(smem + L.perm);
-  int8_t *sK = reinterpret_cast<int8_t *>(smem + L.kofs);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_fullA = smem_u32(smem + L.bars);
   const uint32_t bar_fullB = bar_fullA + NSTAGE * 8;
   const uint32_t bar_empty = bar_fullB + NSTAGE * 8;
-  const uint32_t bar_done = bar_empty + NSTAGE * 8;
+  const uint32_t bar_mfull = bar_empty + NSTAGE * 8;
+  const uint32_t bar_mempty = bar_mfull + MS * 8;
+  const uint32_t bar_tfull = bar_mempty + MS * 8;
+  const uint32_t bar_tempty = bar_tfull + 2 * 8;
   const int B_STAGE = NCORE * N * 16;
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
+  const int n_tiles = tb.n_tiles;
+  const int kchunks = (Kd + KC - 1) / KC;
 
-  // ---- tile book-keeping ------------------------------------------------------------------
-  int nE;
-  if (tb.identity) {
-    nE = 1;
-    if (tid < TILE_M) {
-      const long long r = (long long)tile * TILE_M + tid;
-      const int v = r < n_rows ? (int)r : -1;
-      sPerm[tid] = v;
-      sIdx[0][tid] = v;
-    }
-    if (tid == 0) sK[0] = 0;
-  } else {
-    const uint32_t mask = tb.tile_mask[tile];
-    const int e0 = tb.tile_off[tile];
-    nE = __popc(mask);
-    if (tid < TILE_M) sPerm[tid] = tb.perm[(long long)tile * TILE_M + tid];
-    for (int i = tid; i < nE * TILE_M; i += NT_GEMM) sIdx[i / TILE_M][i % TILE_M] = tb.entries[(long long)e0 * TILE_M + i];
-    if (tid < 32 && (mask & (1u << tid))) sK[__popc(mask & ((1u << tid) - 1u))] = (int8_t)tid;
-  }
+  auto meta_idx = [&](int slot) { return reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.meta + slot * L.meta_bytes); };
+  auto meta_perm = [&](int slot) { return reinterpret_cast<int32_t *>(smem + L.meta + slot * L.meta_bytes + K * TILE_M * 4); };
+  auto meta_hdr = [&](int slot) { return reinterpret_cast<int32_t *>(smem + L.meta + slot * L.meta_bytes + (K + 1) * TILE_M * 4); };
+  // steps of work item `item` given the tile's entry count
+  auto item_steps = [&](int item, int nE) {
+    const int split = item / n_tiles, all_steps = nE * kchunks;
+    return all_steps > split ? (all_steps - split + splits - 1) / splits : 0;
+  };
+
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(bar_fullA + i * 8, 128);
       mbar_init(bar_fullB + i * 8, 1);
       mbar_init(bar_empty + i * 8, 1);
     }
-    mbar_init(bar_done, 1);
+    for (int i = 0; i < MS; ++i) {
+      mbar_init(bar_mfull + i * 8, 1);
+      mbar_init(bar_mempty + i * 8, 10);     // 4 producer warps + 4 epilogue warps + MMA + weight loader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + i * 8, 1);
+      mbar_init(bar_tempty + i * 8, 4);      // 4 epilogue warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  // split-K for small grids: CTA (tile, split) owns the steps split, split+S, ... and writes a partial
-  // tile that k_splitk_reduce sums in fixed order
-  const int kchunks = (Kd + KC - 1) / KC;
-  const int splits = gridDim.y, split = blockIdx.y;
-  const int all_steps = nE * kchunks;
-  const int steps = all_steps > split ? (all_steps - split + splits - 1) / splits : 0;
-
-  if (warp < 4) {
+  if (warp == 10) {
+    // ===== metadata loader =====
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int slot = it % MS, use = it / MS;
+      if (use > 0) mbar_wait(bar_mempty + slot * 8, (use - 1) & 1);
+      const int tile = item % n_tiles;
+      int32_t(*sIdx)[TILE_M] = meta_idx(slot);
+      int32_t *sPerm = meta_perm(slot), *hdr = meta_hdr(slot);
+      if (tb.identity) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long r = (long long)tile * TILE_M + lane * 4 + i;
+          const int v = r < n_rows ? (int)r : -1;
+          sPerm[lane * 4 + i] = v;
+          sIdx[0][lane * 4 + i] = v;
+        }
+        if (lane == 0) { hdr[0] = 1; reinterpret_cast<int8_t *>(hdr + 2)[0] = 0; }
+      } else {
+        const uint32_t mask = tb.tile_mask[tile];
+        const int e0 = tb.tile_off[tile];
+        const int nE = __popc(mask);
+        reinterpret_cast<int4 *>(sPerm)[lane] = __ldg(reinterpret_cast<const int4 *>(tb.perm + (long long)tile * TILE_M) + lane);
+        for (int e = 0; e < nE; ++e)
+          reinterpret_cast<int4 *>(sIdx[e])[lane] = __ldg(reinterpret_cast<const int4 *>(tb.entries + (long long)(e0 + e) * TILE_M) + lane);
+        if (mask & (1u << lane)) reinterpret_cast<int8_t *>(hdr + 2)[__popc(mask & ((1u << lane) - 1u))] = (int8_t)lane;
+        if (lane == 0) hdr[0] = nE;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_mfull + slot * 8);
+    }
+  } else if (warp < 4) {
     // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
     const int j = tid & 7, r0 = tid >> 3;
-    for (int lst = 0; lst < steps; ++lst) {
-      const int stage = lst % NSTAGE, use = lst / NSTAGE;
-      if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
-      const int st = split + lst * splits;
-      const int e = st / kchunks, c = st - e * kchunks;
-      const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-      if (j < ncore) {
-        const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
-        const float *colp = X + c * KC + j * 4;
-#pragma unroll
-        for (int i = 0; i < TILE_M / 16; ++i) {
-          const int row = r0 + 16 * i;
-          const int idx = sIdx[e][row];
-          cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
-        }
-      }
-      cp_async_commit();
-      if (lst >= DEPTH) {
-        cp_async_wait<DEPTH>();                 // this thread's gathers of step lst-DEPTH have landed
-        fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(bar_fullA + ((lst - DEPTH) % NSTAGE) * 8);
-      }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int lst = (steps > DEPTH ? steps - DEPTH : 0); lst < steps; ++lst) mbar_arrive(bar_fullA + (lst % NSTAGE) * 8);
-  } else if (warp == 4) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
-      for (int lst = 0; lst < steps; ++lst) {
-        const int stage = lst % NSTAGE, use = lst / NSTAGE;
-        const int c = (split + lst * splits) % kchunks;
-        const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-        mbar_wait(bar_fullB + stage * 8, use & 1);
-        mbar_wait(bar_fullA + stage * 8, use & 1);
-        tc_fence_after();
-        const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
-        for (int kk = 0; kk < (ncore >> 1); ++kk) {
-          const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
-          const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
-          mma_tf32(tmem_d, ad, bd, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
-        }
-        tc_commit(bar_empty + stage * 8);
-      }
-      if (steps > 0) tc_commit(bar_done);
-    }
-  } else if (warp == 5) {
-    // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
-    if (lane == 0) {
-      for (int lst = 0; lst < steps; ++lst) {
-        const int stage = lst % NSTAGE, use = lst / NSTAGE;
+    int g = 0, it = 0;                       // global step / item counters of this CTA
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int slot = it % MS;
+      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      int32_t(*sIdx)[TILE_M] = meta_idx(slot);
+      const int split = item / n_tiles;
+      const int steps = item_steps(item, meta_hdr(slot)[0]);
+      for (int lst = 0; lst < steps; ++lst, ++g) {
+        const int stage = g % NSTAGE, use = g / NSTAGE;
         if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
         const int st = split + lst * splits;
         const int e = st / kchunks, c = st - e * kchunks;
         const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-        const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
-        const uint32_t bytes = (uint32_t)ncore * N * 16;
-        mbar_expect_tx(bar_fullB + stage * 8, bytes);
-        bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
-                      bar_fullB + stage * 8);
-      }
-    }
-  }
-
-  // ---- epilogue (warps 0-3): TMEM -> registers -> global; warp w owns accumulator lanes 32w.. ----
-  if (warp < 4) {
-    if (steps > 0) {
-      mbar_wait(bar_done, 0);
-      tc_fence_after();
-    }
-    const int row = warp * 32 + lane;
-    int orow = sPerm[row];
-    float *yp = Y + (long long)(orow < 0 ? 0 : orow) * N;
-    if (splits > 1) {                       // partial tile, slot order, no bias
-      orow = 0;
-      bias = nullptr;
-      yp = Ypart + (((long long)split * gridDim.x + tile) * TILE_M + row) * N;
-    }
-    for (int c0 = 0; c0 < N; c0 += 8) {
-      uint32_t v[8];
-      if (steps > 0) {
-        tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-      } else {
+        if (j < ncore) {
+          const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
+          const float *colp = X + c * KC + j * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0u;
-      }
-      if (orow >= 0) {
-        float4 o0 = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-        float4 o1 = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-        if (bias) {
-          const float4 b0 = *reinterpret_cast<const float4 *>(bias + c0), b1 = *reinterpret_cast<const float4 *>(bias + c0 + 4);
-          o0.x += b0.x; o0.y += b0.y; o0.z += b0.z; o0.w += b0.w;
-          o1.x += b1.x; o1.y += b1.y; o1.z += b1.z; o1.w += b1.w;
+          for (int i = 0; i < TILE_M / 16; ++i) {
+            const int row = r0 + 16 * i;
+            const int idx = sIdx[e][row];
+            cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
+          }
         }
-        *reinterpret_cast<float4 *>(yp + c0) = o0;
-        *reinterpret_cast<float4 *>(yp + c0 + 4) = o1;
+        cp_async_commit();
+        if (g >= DEPTH) {
+          cp_async_wait<DEPTH>();             // this thread's gathers of step g-DEPTH have landed
+          fence_proxy_async();                // generic-proxy writes -> visible to the tensor core
+          mbar_arrive(bar_fullA + ((g - DEPTH) % NSTAGE) * 8);
+        }
       }
+      __syncwarp();                           // the tile's lists are no longer needed by this warp
+      if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int q = (g > DEPTH ? g - DEPTH : 0); q < g; ++q) mbar_arrive(bar_fullA + (q % NSTAGE) * 8);
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
+      int g = 0, it = 0, accn = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int slot = it % MS;
+        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int split = item / n_tiles;
+        const int steps = item_steps(item, meta_hdr(slot)[0]);
+        mbar_arrive(bar_mempty + slot * 8);
+        if (steps == 0) continue;
+        const int acc = accn & 1;
+        if (accn >= 2) mbar_wait(bar_tempty + acc * 8, ((accn >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
+        for (int lst = 0; lst < steps; ++lst, ++g) {
+          const int stage = g % NSTAGE, use = g / NSTAGE;
+          const int c = (split + lst * splits) % kchunks;
+          const int ncore = min(NCORE, (Kd - c * KC) >> 2);
+          mbar_wait(bar_fullB + stage * 8, use & 1);
+          mbar_wait(bar_fullA + stage * 8, use & 1);
+          tc_fence_after();
+          const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
+          for (int kk = 0; kk < (ncore >> 1); ++kk) {
+            const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
+            const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
+            mma_tf32(tmem_d, ad, bd, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(bar_empty + stage * 8);
+        }
+        tc_commit(bar_tfull + acc * 8);
+        ++accn;
+      }
+    }
+  } else if (warp == 5) {
+    // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
+    if (lane == 0) {
+      int g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int slot = it % MS;
+        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int split = item / n_tiles;
+        const int steps = item_steps(item, meta_hdr(slot)[0]);
+        const int8_t *sK = reinterpret_cast<const int8_t *>(meta_hdr(slot) + 2);
+        for (int lst = 0; lst < steps; ++lst, ++g) {
+          const int stage = g % NSTAGE, use = g / NSTAGE;
+          if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+          const int st = split + lst * splits;
+          const int e = st / kchunks, c = st - e * kchunks;
+          const int ncore = min(NCORE, (Kd - c * KC) >> 2);
+          const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
+          const uint32_t bytes = (uint32_t)ncore * N * 16;
+          mbar_expect_tx(bar_fullB + stage * 8, bytes);
+          bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
+                        bar_fullB + stage * 8);
+        }
+        mbar_arrive(bar_mempty + slot * 8);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 6-9): TMEM lanes 32*(warp%4).. -> registers -> global =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0, accn = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int slot = it % MS;
+      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      const int tile = item % n_tiles, split = item / n_tiles;
+      const int steps = item_steps(item, meta_hdr(slot)[0]);
+      int orow = meta_perm(slot)[row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
+      const float *bs = bias;
+      float *yp = Y + (long long)(orow < 0 ? 0 : orow) * N;
+      if (splits > 1) {                     // partial tile, slot order, no bias
+        orow = 0;
+        bs = nullptr;
+        yp = Ypart + (((long long)split * n_tiles + tile) * TILE_M + row) * N;
+      }
+      const int acc = accn & 1;
+      if (steps > 0) {
+        mbar_wait(bar_tfull + acc * 8, (accn >> 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        if (steps > 0) {
+          if (N - c0 >= 32) {
+            tmem_ld32(taddr + (uint32_t)c0, v);
+          } else {                          // N = 16 (mod 32): two 8-column loads
+            uint32_t w0[8], w1[8];
+            tmem_ld8(taddr + (uint32_t)c0, w0);
+            tmem_ld8(taddr + (uint32_t)c0 + 8, w1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i] = w0[i]; v[8 + i] = w1[i]; }
+          }
+          tmem_ld_wait();
+          if (c0 + 32 >= N) {               // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (orow >= 0) {
+          const int nc = min(32, N - c0);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (i < nc) {
+              float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                     __uint_as_float(v[i + 3]));
+              if (bs) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(bs + c0 + i);
+                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              }
+              *reinterpret_cast<float4 *>(yp + c0 + i) = o;
+            }
+          }
+        }
+      }
+      if (steps > 0) ++accn;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * acc_cols);
 }
 
 // Y[perm[slot]] = bias + sum_s Ypart[s][slot]   (fixed summation order)
@@ -374,16 +474,17 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int cin = transpose_w ? N : Kd, cout = transpose_w ? Kd : N;
   k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  // 3 stages (two steps of gathers in flight per CTA) keep a CTA at <= ~112 KB of shared memory for
-  // N <= 128, so two CTAs share an SM: tiles are short (4-30 steps) and one CTA's prologue / epilogue
-  // hides behind the other's main loop
-  const int ns = 3;
+  // pipeline stages: what fits beside the metadata slots in ~215 KB
+  const int stage_bytes = A_STAGE + NCORE * N * 16;
+  const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
+  int ns = (215 * 1024 - meta_total) / stage_bytes;
+  ns = ns >= 6 ? 6 : (ns >= 4 ? 4 : 3);
   const Smem L(N, K, ns);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_osgemm_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(k_osgemm_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_osgemm_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       dev_free(wp, s);
       return -1;
@@ -393,7 +494,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
   // small grids leave most SMs idle while one CTA walks K * Kd/32 latency-bound steps: split the
-  // steps over up to 32 CTAs per tile (each keeps >= 4 steps even for one active offset)
+  // steps over up to 32 work items per tile (each keeps >= 4 steps even for one active offset)
   int splits = 1;
   const int kchunks = (Kd + KC - 1) / KC;
   if (tv.n_tiles * 2 <= num_sms() && !tv.identity) {
@@ -406,10 +507,11 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   float *ypart = nullptr;
   const long long n_slots = (long long)tv.n_tiles * TILE_M;
   if (splits > 1 && dev_alloc_t(&ypart, (size_t)splits * n_slots * N, s)) { dev_free(wp, s); return -1; }
-  const dim3 grid(tv.n_tiles, splits);
-  if (ns == 3) k_osgemm_tf32<3><<<grid, NT_GEMM, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
-  else if (ns == 5) k_osgemm_tf32<5><<<grid, NT_GEMM, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
-  else k_osgemm_tf32<7><<<grid, NT_GEMM, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart);
+  const int n_items = tv.n_tiles * splits;
+  const int grid = n_items < num_sms() ? n_items : num_sms();      // persistent: one CTA per SM
+  if (ns == 3) k_osgemm_tf32<3><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
+  else if (ns == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
+  else k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (splits > 1 && e == cudaSuccess) {
