@@ -156,6 +156,14 @@ struct Smem {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -267,9 +275,20 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
     const int j = tid & 7, r0 = tid >> 3;
     int g = 0, it = 0;                       // global step / item counters of this CTA
+    int arrived = 0;                         // steps this thread has posted on fullA
+    auto flush = [&]() {                     // post everything issued so far
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (; arrived < g; ++arrived) mbar_arrive(bar_fullA + (arrived % NSTAGE) * 8);
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int slot = it % MS;
-      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      // never block with arrivals pending: the metadata slot may only be recycled once the items
+      // whose last steps are still unposted here have drained (deadlock with 1-step items otherwise)
+      if (!mbar_test(bar_mfull + slot * 8, (it / MS) & 1)) {
+        flush();
+        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      }
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
       const int split = item / n_tiles;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
@@ -290,18 +309,16 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           }
         }
         cp_async_commit();
-        if (g >= DEPTH) {
-          cp_async_wait<DEPTH>();             // this thread's gathers of step g-DEPTH have landed
+        if (g - arrived >= DEPTH) {
+          cp_async_wait<DEPTH>();             // this thread's gathers of steps <= g-DEPTH have landed
           fence_proxy_async();                // generic-proxy writes -> visible to the tensor core
-          mbar_arrive(bar_fullA + ((g - DEPTH) % NSTAGE) * 8);
+          for (; arrived <= g - DEPTH; ++arrived) mbar_arrive(bar_fullA + (arrived % NSTAGE) * 8);
         }
       }
       __syncwarp();                           // the tile's lists are no longer needed by this warp
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int q = (g > DEPTH ? g - DEPTH : 0); q < g; ++q) mbar_arrive(bar_fullA + (q % NSTAGE) * 8);
+    flush();
   } else if (warp == 4) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -452,6 +469,8 @@ __global__ void k_splitk_reduce(const float *__restrict__ Ypart, const float *__
   *reinterpret_cast<float4 *>(Y + orow * N + c) = a;
 }
 
+int g_gemm_grid_limit = 0;   // test knob (scn_set_gemm_grid_limit): force many work items per CTA
+
 static bool tf32_shape_ok(const float *X, const float *W, const float *bias, float *Y, int Kd, int N) {
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
   return Kd >= 8 && Kd % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
@@ -508,7 +527,8 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const long long n_slots = (long long)tv.n_tiles * TILE_M;
   if (splits > 1 && dev_alloc_t(&ypart, (size_t)splits * n_slots * N, s)) { dev_free(wp, s); return -1; }
   const int n_items = tv.n_tiles * splits;
-  const int grid = n_items < num_sms() ? n_items : num_sms();      // persistent: one CTA per SM
+  int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
+  if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
   if (ns == 3) k_osgemm_tf32<3><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
   else if (ns == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
   else k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
@@ -714,6 +734,13 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
 }  // namespace tc
 
 // partial[w] (w < n_work) = X[rows]^T @ dY[rows] over the pairs of work item w.  >0: shape not handled.
+}  // namespace scn
+extern "C" int scn_set_gemm_grid_limit(int max_ctas) {
+  scn::tc::g_gemm_grid_limit = max_ctas;
+  return 0;
+}
+namespace scn {
+
 int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const DwWork *work, float *partial,
                   int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,
                   int precision, cudaStream_t s) {

@@ -89,6 +89,7 @@ _sig = {
     "scn_launch_count": (c_int64, []),
     "scn_rulebook_stats": (c_int, [c_void_p, c_int, I64P, I64P, I64P, I64P]),
     "scn_set_tile_grouping": (c_int, [c_int]),
+    "scn_set_gemm_grid_limit": (c_int, [c_int]),
     "scn_prof_enable": (c_int, [c_int]),
     "scn_prof_read": (c_int, [c_int, POINTER(c_double)]),
 }

@@ -219,6 +219,9 @@ int scn_prof_read(int cls, double out[4]);
 int scn_rulebook_stats(scn_metadata_t *m, int kind, const int64_t *in_spatial_size,
                        const int64_t *filter_size, const int64_t *filter_stride,
                        int64_t stats[3]);
+/* test / tuning knob: cap the grid of the persistent gather-GEMM (0 = one CTA per SM), so that small
+ * inputs exercise the many-work-items-per-CTA paths */
+int scn_set_gemm_grid_limit(int max_ctas);
 /* 0: tiles in natural row order, 1 (default): rows grouped by neighbour mask */
 int scn_set_tile_grouping(int enabled);
 
