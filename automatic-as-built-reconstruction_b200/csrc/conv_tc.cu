@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t acc_cols,
               float *__restrict__ Ypart, int n_items, int splits) {
-  constexpr int DEPTH = NSTAGE - 1;
+  // a producer posts step g-DEPTH while issuing step g.  DEPTH steps of gathers cover the memory
+  // latency; the other NSTAGE-DEPTH stages are slack between the MMA warp and the producers - with
+  // DEPTH = NSTAGE-1 every MMA would wait for a full producer round trip after the previous one
+  constexpr int DEPTH = NSTAGE / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L(N, K, NSTAGE);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
