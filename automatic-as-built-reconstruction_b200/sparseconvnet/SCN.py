@@ -155,18 +155,30 @@ def _dims(*sizes):
 
 
 # ---- InputLayer / OutputLayer (pybind.cpp:154-170) ---------------------------------------
-def InputLayer_updateOutput(m, spatial_size, coords, input_features, output_features, batch_size,
-                            mode):
-    input_features = require_cuda_f32(input_features, "InputLayer features")
+def InputLayer_prepare(m, spatial_size, coords, batch_size, mode):
+    """the integer half of InputLayer_updateOutput (Metadata::inputLayer, Metadata.cpp:406-417): hash
+    grid, first-occurrence numbering, point lists.  Returns nActive.  B200 extension: it can run ahead
+    of time, on another stream / host thread (modules.InputPrefetcher)."""
     assert coords.dim() == 2 and coords.size(1) in (3, 4), coords.shape
     coords = coords.long().contiguous()
     n_active = c_int64()
     check(lib.scn_input_layer_prepare(m._h, i64x3(spatial_size), ptr(coords), coords.size(0),
                                       coords.size(1), 1 if coords.is_cuda else 0, int(batch_size),
                                       int(mode), stream(), byref(n_active)))
+    m._n_points = coords.size(0)
+    return n_active.value
+
+
+def InputLayer_updateOutput(m, spatial_size, coords, input_features, output_features, batch_size,
+                            mode, prepared_n_active=None):
+    input_features = require_cuda_f32(input_features, "InputLayer features")
+    if prepared_n_active is None:
+        n_active = InputLayer_prepare(m, spatial_size, coords, batch_size, mode)
+    else:
+        n_active = prepared_n_active
     planes = input_features.size(1)
-    assert input_features.size(0) == coords.size(0), (input_features.shape, coords.shape)
-    output_features.resize_(n_active.value, planes)
+    assert input_features.size(0) == m._n_points, (input_features.shape, m._n_points)
+    output_features.resize_(n_active, planes)
     check(lib.scn_input_layer_forward(m._h, ptr(input_features), ptr(output_features), planes,
                                       stream()))
 

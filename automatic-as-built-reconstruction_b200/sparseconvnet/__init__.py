@@ -9,7 +9,8 @@ from . import SCN  # noqa: E402
 from .tensor import SparseConvNetTensor  # noqa: E402
 from .modules import (  # noqa: E402
     AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, CheckpointedSequential,
-    ConcatTable, Convolution, Deconvolution, Identity, InputLayer, InputLayerInput, JoinTable,
+    ConcatTable, Convolution, Deconvolution, Identity, InputLayer, InputLayerInput, InputPrefetcher,
+    JoinTable, PreparedInput,
     Metadata, NetworkInNetwork, OutputLayer, Sequential, SparseToDense, SubmanifoldConvolution,
     ValidConvolution, add_feature_planes, concatenate_feature_planes, optionalTensor,
     optionalTensorReturn, toLongTensor)

@@ -98,9 +98,21 @@ class FPN_Net(torch.nn.Module):
     def forward(self, net0):
         if CHECK_NAN and not torch.isnan(self.layers_in[1].weight).sum() == 0:
             raise FloatingPointError("FPN_Net: NaN in stem weights")
-        net = self.layers_in[0](net0)                  # InputLayer: voxel hashing
-        self._prebuild_rulebooks(net)
+        net = self.layers_in[0](net0)                  # InputLayer: voxel hashing (or a PreparedInput)
+        if not getattr(net, "rulebooks_built", False):
+            self._prebuild_rulebooks(net)
         return self.forward_fpn(self.layers_in[1](net))
+
+    def prepare(self, coords, batch_size=0):
+        """All integer work of a batch - input grid, the 12 coarser grids and every rulebook - on the
+        current stream; returns a PreparedInput to pass as `net([prepared, features])`.  Meant to run
+        one batch ahead on a side stream (scn.InputPrefetcher(net.prepare))."""
+        p = self.layers_in[0].prepare(coords, batch_size)
+        self._prebuild_rulebooks(p)
+        p.rulebooks_built = True
+        p.event = torch.cuda.Event()
+        p.event.record()
+        return p
 
     def _prebuild_rulebooks(self, net):
         """Build every hash grid / rulebook the graph below will ask for, back to back, before any

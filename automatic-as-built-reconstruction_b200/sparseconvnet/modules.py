@@ -64,8 +64,9 @@ class InputLayerFunction(Function):
     def forward(ctx, dimension, metadata, spatial_size, coords, input_features, batch_size, mode):
         ctx.metadata_ = metadata
         out = input_features.new_empty(0)
-        SCN.InputLayer_updateOutput(metadata, spatial_size, coords, input_features.contiguous(), out,
-                                    batch_size, mode)
+        prepared = coords.n_active if isinstance(coords, PreparedInput) else None
+        SCN.InputLayer_updateOutput(metadata, spatial_size, None if prepared is not None else coords,
+                                    input_features.contiguous(), out, batch_size, mode, prepared)
         return out
 
     @staticmethod
@@ -90,6 +91,18 @@ class OutputLayerFunction(Function):
         return None, None, grad_input
 
 
+class PreparedInput(object):
+    """The integer work of one batch, done ahead of time: a Metadata whose input grid (and, through
+    FPN_Net.prepare, every downstream grid / rulebook) is already built, plus the CUDA event that
+    marks its completion on the stream it was built on.  Pass it where coords would go:
+    `net([prepared, features])`."""
+
+    def __init__(self, metadata, spatial_size, n_active, n_points, event, coords):
+        self.metadata, self.spatial_size, self.n_active, self.n_points = metadata, spatial_size, n_active, n_points
+        self.event, self.coords = event, coords      # coords kept alive until the build has consumed them
+        self.rulebooks_built = False
+
+
 class InputLayer(Module):
     """(coords, features[, batch_size]) -> SparseConvNetTensor.
 
@@ -109,15 +122,80 @@ class InputLayer(Module):
         self.device = device
         return self
 
+    def prepare(self, coords, batch_size=0):
+        """Build the input hash grid for `coords` on the CURRENT stream and return a PreparedInput
+        (B200 extension: the integer work depends on the coordinates only, so it can be overlapped
+        with the previous step's feature kernels - see InputPrefetcher)."""
+        m = Metadata(self.dimension)
+        n_active = SCN.InputLayer_prepare(m, self.spatial_size, coords, batch_size, self.mode)
+        ev = torch.cuda.Event()
+        ev.record()
+        return PreparedInput(m, self.spatial_size, n_active, coords.size(0), ev, coords)
+
     def forward(self, input):
         coords, feats = input[0], input[1]
         if self.device is not None:
             feats = feats.to(self.device)
+        if isinstance(coords, PreparedInput):
+            torch.cuda.current_stream().wait_event(coords.event)
+            out = SparseConvNetTensor(metadata=coords.metadata, spatial_size=self.spatial_size)
+            out.features = InputLayerFunction.apply(self.dimension, out.metadata, self.spatial_size, coords,
+                                                    feats, 0, self.mode)
+            out.rulebooks_built = coords.rulebooks_built
+            return out
         out = SparseConvNetTensor(metadata=Metadata(self.dimension), spatial_size=self.spatial_size)
         out.features = InputLayerFunction.apply(self.dimension, out.metadata, self.spatial_size,
                                                 coords.long(), feats,
                                                 0 if len(input) == 2 else input[2], self.mode)
         return out
+
+
+class InputPrefetcher(object):
+    """Runs `prepare_fn(coords)` (e.g. FPN_Net.prepare) for the NEXT batch on a side stream and a
+    worker thread while the current batch's feature kernels run on the main stream - the role the
+    DataLoader workers play for voxelisation in the reference (data3d/data.py:39-40).  The C calls
+    release the GIL, and their count read-backs only block the worker.
+
+        pf = scn.InputPrefetcher(net.prepare)
+        pf.submit(coords0)
+        for ...:
+            prepared = pf.get(); pf.submit(next_coords)
+            out = net([prepared, features])
+    """
+
+    def __init__(self, prepare_fn, device=None):
+        import queue
+        import threading
+        self.prepare_fn = prepare_fn
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.todo, self.done = queue.Queue(), queue.Queue()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            coords = self.todo.get()
+            if coords is None:
+                return
+            try:
+                with torch.cuda.stream(self.stream):
+                    self.done.put(self.prepare_fn(coords))
+            except Exception as e:  # noqa: BLE001  (re-raised in get())
+                self.done.put(e)
+
+    def submit(self, coords):
+        self.todo.put(coords)
+
+    def get(self):
+        r = self.done.get()
+        if isinstance(r, Exception):
+            raise r
+        return r
+
+    def close(self):
+        self.todo.put(None)
 
 
 class OutputLayer(Module):

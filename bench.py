@@ -207,6 +207,7 @@ def workload_config(args, points=None):
             "per_gpu_batch": args.batch, "points_per_building": points or args.points, "floors": args.floors,
             "full_scale": FULL_SCALE, "planes": PLANES, "precision": args.precision,
             "parallelism": "dp%d" % args.gpus,
+            "prefetch": "Metadata (hash grids + rulebooks) of batch i+1 built on a side stream during batch i",
             "l2": "256 MiB flush buffer written between steps; per-step activations (GBs) exceed the 126 MB L2"}
 
 
@@ -241,20 +242,31 @@ def run_b200(args, rank, local_rank, world):
         bucket.allreduce_mean()
         return loss
 
+    # The integer work of a batch (voxel hashing, 13 grids, 25 rulebooks) depends on its coordinates
+    # only: like the reference's DataLoader workers it runs one batch ahead - here on a side stream
+    # and a worker thread (scn.InputPrefetcher).  Every timed step still builds a fresh Metadata; the
+    # first build of a timed region is inside the region and not overlapped.
+    pf = scn.InputPrefetcher(net.prepare)
+
     def timed(n_steps, host_inputs):
+        coords = locs_pin if host_inputs else locs_dev
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = scn.SCN.launch_count()
         a.record()
-        for _ in range(n_steps):
+        pf.submit(coords)
+        for i in range(n_steps):
             flush.fill_(1)
+            prepared = pf.get()
+            if i + 1 < n_steps:
+                pf.submit(coords)                             # next batch: overlaps this step
             if host_inputs:
-                loss = step(locs_pin, feats_pin.to(dev, non_blocking=True))
+                loss = step(prepared, feats_pin.to(dev, non_blocking=True))
                 loss.item()                                   # D2H read of the step's result
             else:
-                step(locs_dev, feats_dev)
+                step(prepared, feats_dev)
         b.record()
         torch.cuda.synchronize()
         if world > 1:

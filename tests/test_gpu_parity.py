@@ -357,6 +357,28 @@ def test_persistent_gemm_many_items_per_cta(scn, limit):
         _lib.check(_lib.lib.scn_set_gemm_grid_limit(0))
 
 
+def test_prepared_input_and_prefetcher(scn, gold):
+    """FPN_Net.prepare on a side stream / worker thread gives the same result as the inline path"""
+    g = gold("small_net")
+    net = _small_net(scn, g).train()
+    locs, feats = torch.from_numpy(g["locs"]), torch.from_numpy(g["feats"]).cuda()
+    rpn0, roi0 = net([locs, feats])
+    pf = scn.InputPrefetcher(net.prepare)
+    try:
+        pf.submit(locs)
+        pf.submit(locs.cuda())
+        for _ in range(2):
+            prepared = pf.get()
+            assert prepared.rulebooks_built and prepared.n_active == rpn0[0].metadata.getNActive([512] * 3)
+            rpn1, roi1 = net([prepared, feats])
+            for a, b in zip(list(rpn0) + list(roi0), list(rpn1) + list(roi1)):
+                assert torch.equal(a.get_spatial_locations(), b.get_spatial_locations())
+                assert torch.equal(a.features, b.features)
+            sum((m.features ** 2).sum() for m in list(rpn1) + list(roi1)).backward()
+    finally:
+        pf.close()
+
+
 def test_network_in_network(scn):
     t, _ = make_input(scn, _cloud(), [64, 64, 16], C=32)
     nin = scn.NetworkInNetwork(32, 48, True).cuda()
@@ -457,7 +479,7 @@ def test_dense_equivalence(scn):
 # ---------------------------------------------------------------------------------------------
 # whole backbone vs the reference's own fpn_net.py (golden)
 # ---------------------------------------------------------------------------------------------
-def _small_net(scn, g):
+def _small_net(scn, g):  # noqa: E302
     net = scn.FPN_Net([512] * 3, 3, ["xyz", "color", "normal"], 1, [8] + [16] * 8, nPlaneM=16,
                       residual_blocks=True, fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
                       downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8],
