@@ -55,6 +55,11 @@ static void init_pool() {
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long thr = ~0ULL;  // never trim: the per-step Metadata rebuild reuses it
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // Two streams allocate from this pool (feature kernels / the prefetcher's metadata builds).  Never
+    // let an allocation on one stream wait for the other stream's queue to reach a free: take a
+    // block whose free has already completed, or fresh memory.
+    int off = 0;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
   }
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }

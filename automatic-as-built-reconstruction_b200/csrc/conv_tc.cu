@@ -563,8 +563,8 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
 // ---------------------------------------------------------------------------------------------
 namespace tc {
 
-constexpr int DW_NS = 3;   // stages
-constexpr int DW_PD = 1;   // prefetch distance
+constexpr int DW_NS_MAX = 4;   // stages (3 when the operands are wide)
+constexpr int DW_PD = 2;   // prefetch distance (steps of gathers in flight beyond the one being multiplied)
 
 __device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return make_desc(saddr, lbo, sbo) | (1ull << 61);   // layout_type 1 = SWIZZLE_128B_BASE32B
@@ -572,14 +572,14 @@ __device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo, 
 
 struct DwSmem {
   int a, b, pairs, bars, tmem_slot, total, a_stage, b_stage;
-  __host__ __device__ DwSmem(int MA, int NA, int KP) {
+  __host__ __device__ DwSmem(int MA, int NA, int KP, int ns) {
     a_stage = KP * MA * 128;
     b_stage = KP * NA * 128;
     a = 0;
-    b = a + DW_NS * a_stage;
-    pairs = b + DW_NS * b_stage;
+    b = a + ns * a_stage;
+    pairs = b + ns * b_stage;
     bars = pairs + 2 * KP * 8;
-    tmem_slot = bars + (DW_NS + 1) * 8;
+    tmem_slot = bars + (DW_NS_MAX + 1) * 8;
     total = tmem_slot + 16;
   }
 };
@@ -587,14 +587,14 @@ struct DwSmem {
 __global__ void __launch_bounds__(NT)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
-          long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
+          long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols, int DW_NS) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
   const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)
   const int halves = Cin > 128 ? 2 : 1;
-  const DwSmem L(MA, CB, KP);
+  const DwSmem L(MA, CB, KP, DW_NS);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
-  const uint32_t bar_empty = smem_u32(smem + L.bars), bar_done = bar_empty + DW_NS * 8;
+  const uint32_t bar_empty = smem_u32(smem + L.bars), bar_done = bar_empty + DW_NS_MAX * 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   int2 *sPairs = reinterpret_cast<int2 *>(smem + L.pairs);      // [2][KP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -638,8 +638,9 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     sPairs[tid] = load_pair(0);
     sPairs[KP + tid] = load_pair(1);
   }
+  // (steps is used by load_pair's bound only through len; slots are rewritten below)
   if (tid == 0) {
-    for (int i = 0; i < DW_NS + 1; ++i) mbar_init(bar_empty + i * 8, 1);
+    for (int i = 0; i < DW_NS_MAX + 1; ++i) mbar_init(bar_empty + i * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
@@ -668,10 +669,15 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     }
   };
 
-  // DW_PD == 1: step st+1 is issued while the tensor core works on step st
+  // steps st+1 .. st+DW_PD are in flight while the tensor core works on step st
+  static_assert(DW_PD == 2, "prologue below issues exactly two steps");
   if (steps > 0) issue(0);
   cp_async_commit();
-  __syncthreads();           // pair slot 0 is rewritten in iteration 0
+  if (steps > 1) issue(1);
+  cp_async_commit();
+  __syncthreads();           // both pair slots consumed: slot 0 now takes the pairs of step 2
+  if (tid < KP) sPairs[tid] = load_pair(2);
+  __syncthreads();
   for (int st = 0; st < steps; ++st) {
     const int nst = st + DW_PD;
     int2 nxt = make_int2(-1, -1);
@@ -753,8 +759,10 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   if (Cin < 32 || Cin % 32 || (Cin > 128 && Cin != 256) || Cout < 32 || Cout % 32 || Cout > 256) return 1;
   if (!al(X) || !al(dY) || !al(partial)) return 1;
   const int MA = Cin > 128 ? Cin >> 5 : 4, NA = Cout >> 5;
-  const int KP = (MA + NA) <= 8 ? 64 : 32;
-  const DwSmem L(MA, NA, KP);
+  const int KP = (MA + NA) <= 5 ? 64 : 32;
+  int ns = (200 * 1024) / (KP * (MA + NA) * 128);
+  ns = ns >= DW_NS_MAX ? DW_NS_MAX : 3;
+  const DwSmem L(MA, NA, KP, ns);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -766,7 +774,7 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   }
   uint32_t cols = 32;
   while ((int)cols < Cout * (Cin > 128 ? 2 : 1)) cols <<= 1;
-  k_dw_tf32<<<n_work, NT, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
+  k_dw_tf32<<<n_work, NT, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols, ns);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -13,6 +13,7 @@
 #include "metadata.cuh"
 #include "../../include/scn_b200.h"
 #include <algorithm>
+#include <stdlib.h>
 #include <mutex>
 
 namespace scn {
@@ -385,14 +386,14 @@ __global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t 
 // so a tile holds rows whose masks share their high offsets and its union mask stays small
 __global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
                             uint32_t *__restrict__ mask, uint32_t *__restrict__ key,
-                            int32_t *__restrict__ idx) {
+                            int32_t *__restrict__ idx, int key_shift) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   uint32_t m = 0;
   for (int k = 0; k < K; ++k)
     if (T[(long long)k * n + r] >= 0) m |= (1u << k);
   mask[r] = m;
-  key[r] = m;
+  key[r] = m >> key_shift;
   idx[r] = (int)r;
 }
 
@@ -451,9 +452,13 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   SCN_TRY(dev_alloc_t(&mask, (size_t)n_rows, s));
   SCN_TRY(dev_alloc_t(&key, (size_t)n_rows, s));
   SCN_TRY(dev_alloc_t(&idx, (size_t)n_rows, s));
-  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx);
+  // sort key = the top `sort_bits` offsets of the mask (default 18 = two 9-bit radix passes): rows that
+  // agree on them end up adjacent; the low offsets are left unsorted inside such a group
+  static const int sort_bits = getenv("SCN_B200_SORT_BITS") ? atoi(getenv("SCN_B200_SORT_BITS")) : 18;
+  const int kbits = K < sort_bits ? K : sort_bits;
+  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx, K - kbits);
   SCN_LAUNCHED();
-  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(key, idx, n_rows, K, s));
+  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(key, idx, n_rows, kbits, s));
   SCN_TRY(dev_alloc_t(&tb.perm, (size_t)tb.n_tiles * TILE_M, s));
   SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
   SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
