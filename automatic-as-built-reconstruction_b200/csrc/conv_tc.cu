@@ -26,7 +26,6 @@ constexpr int NCORE = KC / 4;               // 16-byte k-cores (4 tf32) per step
 constexpr int A_LBO = TILE_M * 16 + 16;     // bytes between k-cores of A (+16: bank spread for the gather)
 constexpr int A_STAGE = NCORE * A_LBO;      // 16512
 constexpr int NT = 256;                     // threads of the weight-gradient kernel
-constexpr int NT_GEMM = 192;                // gather-GEMM: 4 producer/epilogue warps + MMA warp + weight-loader warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -169,6 +169,19 @@ def InputLayer_prepare(m, spatial_size, coords, batch_size, mode):
     return n_active.value
 
 
+def InputLayer_prepare_plan(m, spatial_size, coords, batch_size, mode, plan):
+    """InputLayer_prepare + every rulebook of `plan` (int64 tensor [n_ops, 13], see scn_build_plan) in one
+    foreign call"""
+    coords = coords.long().contiguous()
+    plan = plan.contiguous()
+    n_active = c_int64()
+    check(lib.scn_build_plan(m._h, i64x3(spatial_size), ptr(coords), coords.size(0), coords.size(1),
+                             1 if coords.is_cuda else 0, int(batch_size), int(mode), c_void_p(plan.data_ptr()),
+                             plan.size(0), stream(), byref(n_active)))
+    m._n_points = coords.size(0)
+    return n_active.value
+
+
 def InputLayer_updateOutput(m, spatial_size, coords, input_features, output_features, batch_size,
                             mode, prepared_n_active=None):
     input_features = require_cuda_f32(input_features, "InputLayer features")

@@ -54,6 +54,8 @@ _sig = {
                                     I64P, c_void_p]),
     "scn_input_layer_prepare": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_int, c_int, c_int64,
                                         c_int, c_void_p, I64P]),
+    "scn_build_plan": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+                               c_void_p, I64P]),
     "scn_input_layer_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "scn_input_layer_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "scn_output_layer_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

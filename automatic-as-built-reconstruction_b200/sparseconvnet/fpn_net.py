@@ -107,12 +107,35 @@ class FPN_Net(torch.nn.Module):
         """All integer work of a batch - input grid, the 12 coarser grids and every rulebook - on the
         current stream; returns a PreparedInput to pass as `net([prepared, features])`.  Meant to run
         one batch ahead on a side stream (scn.InputPrefetcher(net.prepare))."""
-        p = self.layers_in[0].prepare(coords, batch_size)
-        self._prebuild_rulebooks(p)
+        il = self.layers_in[0]
+        m = scn.Metadata(self.dimension)
+        n_active = scn.SCN.InputLayer_prepare_plan(m, il.spatial_size, coords, batch_size, il.mode,
+                                                   self._rulebook_plan(il.spatial_size))
+        ev = torch.cuda.Event()
+        ev.record()
+        p = scn.PreparedInput(m, il.spatial_size, n_active, coords.size(0), ev, coords)
         p.rulebooks_built = True
-        p.event = torch.cuda.Event()
-        p.event.record()
         return p
+
+    def _rulebook_plan(self, ss):
+        """[n_ops, 13] int64: (kind, in_size, out_size, filter, stride) of every rulebook of the graph"""
+        key = tuple(ss.tolist())
+        if getattr(self, "_plan_key", None) != key:
+            ops, three, ones = [], [3] * self.dimension, [1] * self.dimension
+            cur = list(key)
+            for k in range(len(self.m_downs)):
+                ops.append([0] + cur + cur + three + ones)
+                if k + 1 < len(self.m_downs):
+                    fs, st = list(self.down_kernels[k]), list(self.down_strides[k])
+                    out = [(c - f) // s + 1 for c, f, s in zip(cur, fs, st)]
+                    ops.append([1] + cur + out + fs + st)
+                    cur = out
+            for conv, size in zip(self.convs_pro2d, self.rpn_map_sizes):
+                size = [int(v) for v in size]
+                fs, st = conv.filter_size.tolist(), conv.filter_stride.tolist()
+                ops.append([1] + size + [(c - f) // s + 1 for c, f, s in zip(size, fs, st)] + fs + st)
+            self._plan, self._plan_key = torch.tensor(ops, dtype=torch.int64), key
+        return self._plan
 
     def _prebuild_rulebooks(self, net):
         """Build every hash grid / rulebook the graph below will ask for, back to back, before any

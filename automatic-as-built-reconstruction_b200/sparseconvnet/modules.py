@@ -168,7 +168,9 @@ class InputPrefetcher(object):
         import threading
         self.prepare_fn = prepare_fn
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        self.stream = torch.cuda.Stream(device=self.device)
+        # high priority: the build is ~500 tiny launches separated by count read-backs; each must slip in
+        # beside the main stream's SM-filling kernels instead of queueing behind them
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.todo, self.done = queue.Queue(), queue.Queue()
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()

@@ -85,6 +85,13 @@ int scn_input_layer_prepare(scn_metadata_t *m, const int64_t *spatial_size,
                             const int64_t *coords, int64_t n_points, int n_cols,
                             int coords_on_device, int64_t batch_size, int mode,
                             void *stream, int64_t *n_active);
+/* B200 extension: scn_input_layer_prepare followed by n_ops rulebook builds in ONE call (the whole
+ * integer work of a batch; meant for a prefetch thread - a single foreign call never re-enters the
+ * host language between builds).  plan: n_ops x 13 int64 =
+ * [kind (0 submanifold, 1 strided), in_spatial_size[3], out_spatial_size[3], filter[3], stride[3]]. */
+int scn_build_plan(scn_metadata_t *m, const int64_t *spatial_size, const int64_t *coords,
+                   int64_t n_points, int n_cols, int coords_on_device, int64_t batch_size, int mode,
+                   const int64_t *plan, int n_ops, void *stream, int64_t *n_active);
 /* out[site] = sum/mean/first/last of in[points of site]; in [n_points,planes], out [n_active,planes] */
 int scn_input_layer_forward(scn_metadata_t *m, const float *in_feats, float *out_feats,
                             int64_t n_planes, void *stream);

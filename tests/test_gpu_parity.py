@@ -540,7 +540,7 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
     assert n > 40
     # whole gradient vector: relative L2 error (tf32: individual ill-conditioned tensors vary with the
     # summation order between kernel versions, the vector as a whole does not)
-    assert (num / den) ** 0.5 <= (3e-2 if scn.PREC == "tf32" else 1e-4)
+    assert (num / den) ** 0.5 <= (6e-2 if scn.PREC == "tf32" else 1e-4)
     for k, v in net.state_dict().items():
         if "running_" in k and "after/" + k in g.files:
             assert rel(v, g["after/" + k]) <= scn.TOL, k
