@@ -176,7 +176,9 @@ int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_
 // ---------------------------------------------------------------------------------------
 // stable LSD radix sort, 9-bit digits (27-bit neighbour masks = 3 passes); every warp owns one contiguous chunk
 // ---------------------------------------------------------------------------------------
-constexpr int RS_WARPS = 8, RS_CHUNK = 2048, RS_BITS = 9, RS_BINS = 1 << RS_BITS;
+// 4 warps x 512 keys per block: a 278k-row scale gives 136 blocks (chunks of 2048 keys left 131 of
+// the 148 SMs idle)
+constexpr int RS_WARPS = 4, RS_CHUNK = 512, RS_BITS = 9, RS_BINS = 1 << RS_BITS;
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rs_hist(const uint32_t *__restrict__ keys, int32_t *__restrict__ H, long long n, int shift,

@@ -562,8 +562,8 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
 // ---------------------------------------------------------------------------------------------
 namespace tc {
 
-constexpr int DW_NS_MAX = 4;   // stages (3 when the operands are wide)
-constexpr int DW_PD = 2;   // prefetch distance (steps of gathers in flight beyond the one being multiplied)
+constexpr int DW_NPS = 8;          // pair-list slots
+constexpr int NT_DW = 192;         // 4 gather/epilogue warps, MMA warp, pair-list loader warp
 
 __device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return make_desc(saddr, lbo, sbo) | (1ull << 61);   // layout_type 1 = SWIZZLE_128B_BASE32B
@@ -577,31 +577,37 @@ struct DwSmem {
     a = 0;
     b = a + ns * a_stage;
     pairs = b + ns * b_stage;
-    bars = pairs + 2 * KP * 8;
-    tmem_slot = bars + (DW_NS_MAX + 1) * 8;
+    bars = pairs + DW_NPS * KP * 8;
+    tmem_slot = bars + (2 * ns + 2 * DW_NPS + 1) * 8;
     total = tmem_slot + 16;
   }
 };
 
-__global__ void __launch_bounds__(NT)
+// Warp-specialised like the gather-GEMM: warp 5 streams the work item's (in,out) pair list into a
+// ring of shared-memory slots, warps 0-3 gather both operands' rows with cp.async (arrivals lag
+// NSTAGE/2 steps behind the issue, so nobody waits for fresh data), warp 4 issues the MMAs.
+template <int NSTAGE>
+__global__ void __launch_bounds__(NT_DW)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
-          long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols, int DW_NS) {
+          long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
+  constexpr int DEPTH = NSTAGE / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
   const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)
   const int halves = Cin > 128 ? 2 : 1;
-  const DwSmem L(MA, CB, KP, DW_NS);
+  const DwSmem L(MA, CB, KP, NSTAGE);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
-  const uint32_t bar_empty = smem_u32(smem + L.bars), bar_done = bar_empty + DW_NS_MAX * 8;
+  const uint32_t bar_full = smem_u32(smem + L.bars);
+  const uint32_t bar_empty = bar_full + NSTAGE * 8;
+  const uint32_t bar_pfull = bar_empty + NSTAGE * 8;
+  const uint32_t bar_pempty = bar_pfull + DW_NPS * 8;
+  const uint32_t bar_done = bar_pempty + DW_NPS * 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
-  int2 *sPairs = reinterpret_cast<int2 *>(smem + L.pairs);      // [2][KP]
+  int2 *sPairs = reinterpret_cast<int2 *>(smem + L.pairs);      // [DW_NPS][KP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int j8 = tid & 7, p4 = (tid >> 3) & 3;
   const int KA = KP >> 2;                          // k-atoms (4 pairs) per step
   const uint32_t sbo_a = MA * 512, sbo_b = CB * 512;
-  // byte offset of this thread's 16-byte piece inside an atom: row p4, 32B chunk (j8/2)^p4, half j8&1
-  const uint32_t piece = p4 * 128 + ((((uint32_t)j8 >> 1) ^ (uint32_t)p4) << 5) + (j8 & 1) * 16;
 
   long long start;
   int len;
@@ -613,33 +619,27 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     start = (long long)blockIdx.x * ident_chunk;
     len = (int)min((long long)ident_chunk, ident_n - start);
   }
+  const int steps = (len + KP - 1) / KP;
   // zero the atoms that pad M up to 128 (never written by the gathers)
   if (CA < MA) {
     const int per_ka = (MA - CA) * 32;             // 16-byte units per k-atom
-    const int total16 = DW_NS * KA * per_ka;
-    for (int i = tid; i < total16; i += NT) {
+    const int total16 = NSTAGE * KA * per_ka;
+    for (int i = tid; i < total16; i += NT_DW) {
       const int ka = i / per_ka, r = i - ka * per_ka;   // ka counts over all stages
       *reinterpret_cast<float4 *>(smem + L.a + (ka / KA) * L.a_stage + (ka % KA) * sbo_a + CA * 512 + r * 16) =
           make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  auto load_pair = [&](int st) -> int2 {          // pair tid of step st
-    const int p = st * KP + tid;
-    int2 v = make_int2(-1, -1);
-    if (p < len) {
-      if (pairs) v = __ldg(reinterpret_cast<const int2 *>(pairs) + start + p);
-      else v = make_int2((int)(start + p), (int)(start + p));
-    }
-    return v;
-  };
-  const int steps = (len + KP - 1) / KP;
-  if (tid < KP) {
-    sPairs[tid] = load_pair(0);
-    sPairs[KP + tid] = load_pair(1);
-  }
-  // (steps is used by load_pair's bound only through len; slots are rewritten below)
   if (tid == 0) {
-    for (int i = 0; i < DW_NS_MAX + 1; ++i) mbar_init(bar_empty + i * 8, 1);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(bar_full + i * 8, 128);
+      mbar_init(bar_empty + i * 8, 1);
+    }
+    for (int i = 0; i < DW_NPS; ++i) {
+      mbar_init(bar_pfull + i * 8, 1);
+      mbar_init(bar_pempty + i * 8, 4);
+    }
+    mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
@@ -648,88 +648,119 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = make_idesc(128, Cout, 1, 1);
 
-  auto issue = [&](int st) {
-    const int stage = st % DW_NS;
-    const int2 *sp = sPairs + (st & 1) * KP;
-    const uint32_t sa = a_base + stage * L.a_stage + piece, sb = b_base + stage * L.b_stage + piece;
-    for (int c = warp; c < KA * CA; c += NT / 32) {
-      const int ka = c / CA, mi = c - ka * CA;
-      const int2 pr = sp[ka * 4 + p4];
-      const int xi = xcol ? pr.y : pr.x;
-      cp_async_16(sa + ka * sbo_a + mi * 512, X + (long long)(xi < 0 ? 0 : xi) * Cin + mi * 32 + j8 * 4, xi < 0 ? 0 : 16);
-    }
-    for (int c = warp; c < KA * CB; c += NT / 32) {
-      const int ka = c / CB, ni = c - ka * CB;
-      const int2 pr = sp[ka * 4 + p4];
-      const int yi = ycol ? pr.y : pr.x;
-      cp_async_16(sb + ka * sbo_b + ni * 512, dY + (long long)(yi < 0 ? 0 : yi) * Cout + ni * 32 + j8 * 4, yi < 0 ? 0 : 16);
-    }
-  };
-
-  // steps st+1 .. st+DW_PD are in flight while the tensor core works on step st
-  static_assert(DW_PD == 2, "prologue below issues exactly two steps");
-  if (steps > 0) issue(0);
-  cp_async_commit();
-  if (steps > 1) issue(1);
-  cp_async_commit();
-  __syncthreads();           // both pair slots consumed: slot 0 now takes the pairs of step 2
-  if (tid < KP) sPairs[tid] = load_pair(2);
-  __syncthreads();
-  for (int st = 0; st < steps; ++st) {
-    const int nst = st + DW_PD;
-    int2 nxt = make_int2(-1, -1);
-    if (tid < KP && nst + 1 < steps) nxt = load_pair(nst + 1);   // in flight across this iteration
-    if (nst < steps) {
-      if (nst >= DW_NS) mbar_wait(bar_empty + (nst % DW_NS) * 8, ((nst / DW_NS) - 1) & 1);
-      issue(nst);
-    }
-    cp_async_commit();
-    cp_async_wait<DW_PD>();
-    fence_proxy_async();
-    // pair slot (nst+1)&1 == st&1 was last read by issue(st) in the previous iteration
-    if (tid < KP) sPairs[((nst + 1) & 1) * KP + tid] = nxt;
-    __syncthreads();
-    if (tid == 0) {
-      const int stage = st % DW_NS;
-      tc_fence_after();
-      const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
-      for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
-        const uint64_t bd = make_desc_b32(sb + kb * 2 * sbo_b, 512, sbo_b);
-        for (int h = 0; h < halves; ++h) {
-          const uint64_t ad = make_desc_b32(sa + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
-          mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
+  if (warp == 5) {
+    // ===== pair-list loader: lane l carries pairs l and l+32 of a step, 4 steps ahead in registers =====
+    auto load_pair = [&](int st, int i) -> int2 {
+      const int p = st * KP + i;
+      int2 v = make_int2(-1, -1);
+      if (i < KP && st < steps && p < len) {
+        if (pairs) v = __ldg(reinterpret_cast<const int2 *>(pairs) + start + p);
+        else v = make_int2((int)(start + p), (int)(start + p));
+      }
+      return v;
+    };
+    int2 ra[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { ra[u] = load_pair(u, lane); rb[u] = load_pair(u, lane + 32); }
+    for (int st0 = 0; st0 < steps; st0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int st = st0 + u;
+        if (st < steps) {
+          const int slot = st % DW_NPS, use = st / DW_NPS;
+          if (use > 0) mbar_wait(bar_pempty + slot * 8, (use - 1) & 1);
+          sPairs[slot * KP + lane] = ra[u];
+          if (KP > 32) sPairs[slot * KP + lane + 32] = rb[u];
+          ra[u] = load_pair(st + 4, lane);
+          rb[u] = load_pair(st + 4, lane + 32);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_pfull + slot * 8);
         }
       }
-      tc_commit(bar_empty + stage * 8);
-      if (st == steps - 1) tc_commit(bar_done);
+    }
+  } else if (warp < 4) {
+    // ===== operand producers =====
+    const int j8 = tid & 7, p4 = (tid >> 3) & 3;
+    // byte offset of this thread's 16-byte piece inside an atom: row p4, 32B chunk (j8/2)^p4, half j8&1
+    const uint32_t piece = p4 * 128 + ((((uint32_t)j8 >> 1) ^ (uint32_t)p4) << 5) + (j8 & 1) * 16;
+    int arrived = 0;
+    for (int st = 0; st < steps; ++st) {
+      const int stage = st % NSTAGE, use = st / NSTAGE;
+      const int slot = st % DW_NPS;
+      mbar_wait(bar_pfull + slot * 8, (st / DW_NPS) & 1);
+      if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+      const int2 *sp = sPairs + slot * KP;
+      const uint32_t sa = a_base + stage * L.a_stage + piece, sb = b_base + stage * L.b_stage + piece;
+      for (int c = warp; c < KA * CA; c += 4) {
+        const int ka = c / CA, mi = c - ka * CA;
+        const int2 pr = sp[ka * 4 + p4];
+        const int xi = xcol ? pr.y : pr.x;
+        cp_async_16(sa + ka * sbo_a + mi * 512, X + (long long)(xi < 0 ? 0 : xi) * Cin + mi * 32 + j8 * 4, xi < 0 ? 0 : 16);
+      }
+      for (int c = warp; c < KA * CB; c += 4) {
+        const int ka = c / CB, ni = c - ka * CB;
+        const int2 pr = sp[ka * 4 + p4];
+        const int yi = ycol ? pr.y : pr.x;
+        cp_async_16(sb + ka * sbo_b + ni * 512, dY + (long long)(yi < 0 ? 0 : yi) * Cout + ni * 32 + j8 * 4, yi < 0 ? 0 : 16);
+      }
+      cp_async_commit();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pempty + slot * 8);
+      if (st - arrived >= DEPTH) {
+        cp_async_wait<DEPTH>();
+        fence_proxy_async();
+        for (; arrived <= st - DEPTH; ++arrived) mbar_arrive(bar_full + (arrived % NSTAGE) * 8);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; arrived < steps; ++arrived) mbar_arrive(bar_full + (arrived % NSTAGE) * 8);
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, Cout, 1, 1);
+      for (int st = 0; st < steps; ++st) {
+        const int stage = st % NSTAGE, use = st / NSTAGE;
+        mbar_wait(bar_full + stage * 8, use & 1);
+        tc_fence_after();
+        const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
+        for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
+          const uint64_t bd = make_desc_b32(sb + kb * 2 * sbo_b, 512, sbo_b);
+          for (int h = 0; h < halves; ++h) {
+            const uint64_t ad = make_desc_b32(sa + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
+            mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(bar_empty + stage * 8);
+      }
+      if (steps > 0) tc_commit(bar_done);
     }
   }
-  if (steps > 0) {
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-  }
-  // epilogue: accumulator row = input channel, columns = output channels
-  {
-    const int qd = warp & 3, hc = warp >> 2;
-    const int half = Cout >> 1;
+  // ===== epilogue (warps 0-3): accumulator row = input channel, columns = output channels =====
+  if (warp < 4) {
+    if (steps > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
     float *out = partial + (long long)blockIdx.x * Cin * Cout;
     for (int h = 0; h < halves; ++h) {
-      const int ci = h * 128 + qd * 32 + lane;
-      for (int c0 = hc * half; c0 < (hc + 1) * half; c0 += 8) {
-        uint32_t v[8];
+      const int ci = h * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < Cout; c0 += 32) {
+        uint32_t v[32];
         if (steps > 0) {
-          tmem_ld8(tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * Cout + c0), v);
+          tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * Cout + c0), v);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0u;
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
         if (ci < Cin) {
           float *o = out + (long long)ci * Cout + c0;
-          *reinterpret_cast<float4 *>(o) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-          *reinterpret_cast<float4 *>(o + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4 *>(o + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                             __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         }
       }
     }
@@ -759,13 +790,15 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   if (!al(X) || !al(dY) || !al(partial)) return 1;
   const int MA = Cin > 128 ? Cin >> 5 : 4, NA = Cout >> 5;
   const int KP = (MA + NA) <= 5 ? 64 : 32;
-  int ns = (200 * 1024) / (KP * (MA + NA) * 128);
-  ns = ns >= DW_NS_MAX ? DW_NS_MAX : 3;
+  const int stage_bytes = KP * (MA + NA) * 128;
+  int ns = (205 * 1024) / stage_bytes;
+  ns = ns >= 6 ? 6 : (ns >= 4 ? 4 : 3);
   const DwSmem L(MA, NA, KP, ns);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_dw_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(k_dw_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_dw_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_dw_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_dw_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return -1;
     }
@@ -773,7 +806,9 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   }
   uint32_t cols = 32;
   while ((int)cols < Cout * (Cin > 128 ? 2 : 1)) cols <<= 1;
-  k_dw_tf32<<<n_work, NT, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols, ns);
+  if (ns == 3) k_dw_tf32<3><<<n_work, NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
+  else if (ns == 4) k_dw_tf32<4><<<n_work, NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
+  else k_dw_tf32<6><<<n_work, NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
