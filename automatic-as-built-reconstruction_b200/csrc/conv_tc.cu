@@ -194,7 +194,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   // a producer posts step g-DEPTH while issuing step g.  DEPTH steps of gathers cover the memory
   // latency; the other NSTAGE-DEPTH stages are slack between the MMA warp and the producers - with
   // DEPTH = NSTAGE-1 every MMA would wait for a full producer round trip after the previous one
-  constexpr int DEPTH = NSTAGE / 2;
+  constexpr int DEPTH = NSTAGE >= 6 ? NSTAGE - 2 : NSTAGE / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L(N, K, NSTAGE);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(NT_DW)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
           long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
-  constexpr int DEPTH = NSTAGE / 2;
+  constexpr int DEPTH = NSTAGE >= 6 ? NSTAGE - 2 : NSTAGE / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
   const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)

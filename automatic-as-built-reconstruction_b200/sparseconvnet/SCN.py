@@ -240,9 +240,9 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     w = require_cuda_f32(weight, "weight")
     cin, cout = _planes(w)
     ss, fs = _dims(spatial_size, filter_size)
-    counts = (c_int64 * int(fs[0] * fs[1] * fs[2]))()
-    check(lib.scn_submanifold_rulebook_prepare(m._h, ss, fs, stream(), counts))
-    output_features.resize_(m.getNActive(spatial_size), cout)
+    # a submanifold convolution keeps the active set: one output row per input row (the rulebook is
+    # built, or found in the Metadata's cache, inside the forward call)
+    output_features.resize_(x.size(0), cout)
     macs = c_double()
     check(lib.scn_submanifold_conv_forward(m._h, ss, fs, ptr(x), ptr(output_features), ptr(w),
                                            ptr(bias), cin, cout, _lib.precision(), stream(),
@@ -272,7 +272,8 @@ def _strided(fwd, prepare_in, prepare_out, in_size, out_size, filter_size, filte
     n_new = c_int64()
     check(lib.scn_conv_rulebook_prepare(m._h, i64x3(prepare_in), i64x3(prepare_out), fs, st,
                                         stream(), byref(n_new), None))
-    output_features.resize_(m.getNActive(n_out_of), cout)
+    # convolution: rows of the grid the rulebook just created / found; deconvolution: the fine grid's
+    output_features.resize_(n_new.value if n_out_of is prepare_out else m.getNActive(n_out_of), cout)
     macs = c_double()
     check(fwd(m._h, i_s, o_s, fs, st, ptr(x), ptr(output_features), ptr(w), ptr(bias), cin, cout,
               _lib.precision(), stream(), byref(macs)))

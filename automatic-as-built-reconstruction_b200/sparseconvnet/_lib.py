@@ -115,9 +115,15 @@ def check(status):
 
 
 def i64x3(t):
-    """torch LongTensor / list of 3 ints -> ctypes int64[3]"""
+    """torch LongTensor / list of 3 ints -> ctypes int64[3].  Size tensors are shared by all layers of a
+    scale and never mutated in place, so the converted array is cached on the tensor object."""
     if isinstance(t, torch.Tensor):
-        t = t.tolist()
+        c = getattr(t, "_scn_i64x3", None)
+        if c is None:
+            v = t.tolist()
+            c = (c_int64 * 3)(int(v[0]), int(v[1]), int(v[2]))
+            t._scn_i64x3 = c
+        return c
     return (c_int64 * 3)(int(t[0]), int(t[1]), int(t[2]))
 
 
