@@ -17,14 +17,12 @@
 // tf32 when packed.  Accumulation is fp32.
 #include "conv.cuh"
 #include "../../include/scn_b200.h"
+#include <cuda.h>
 
 namespace scn {
 namespace tc {
 
 constexpr int KC = 32;                      // reduction elements per pipeline step
-constexpr int NCORE = KC / 4;               // 16-byte k-cores (4 tf32) per step
-constexpr int A_LBO = TILE_M * 16 + 16;     // bytes between k-cores of A (+16: bank spread for the gather)
-constexpr int A_STAGE = NCORE * A_LBO;      // 16512
 constexpr int NT = 256;                     // threads of the weight-gradient kernel
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -107,9 +105,10 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: W fp32 [K][Cin][Cout] -> Wp[k][chunk c][k-core j][n][4], the exact shared-memory
-// image of the K-major B operand.  transpose=0: reduction dim = Cin, n = Cout (forward);
-// transpose=1: reduction dim = Cout, n = Cin (dX = dY @ W[k]^T).
+// weight packing: W fp32 [K][Cin][Cout] -> Wp[k][chunk c][n][32], the exact shared-memory image of
+// the K-major SWIZZLE_128B B operand: row n of a 32-wide reduction slice is 128 bytes whose 16-byte
+// chunks are XOR-ed with n%8.  transpose=0: reduction dim = Cin, n = Cout (forward);
+// transpose=1: reduction dim = Cout, n = Cin (dX = dY @ W[k]^T).  Values are rounded to tf32.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ Wp, int K, int Cin, int Cout,
                                int transpose) {
@@ -120,13 +119,11 @@ __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ 
        i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i / per_k);
     long long r = i - (long long)k * per_k;
-    // destination order inside offset k: chunk c, core j, column n, element t
+    // destination order inside offset k: chunk c, row n, 32 floats (swizzled)
     const int c = (int)(r / ((long long)KC * N));
     r -= (long long)c * KC * N;
-    const int j = (int)(r / (4 * N));
-    r -= (long long)j * 4 * N;
-    const int n = (int)(r >> 2), t = (int)(r & 3);
-    const int kk = c * KC + j * 4 + t;
+    const int n = (int)(r >> 5), pos = (int)(r & 31);
+    const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
     const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
     Wp[i] = to_tf32(v);
   }
@@ -135,8 +132,10 @@ __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // the gather-GEMM kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int MS = 4;                        // tile-metadata slots (producers may run ~3 tiles ahead of the epilogue)
-constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight loader, 4 epilogue, metadata loader
+constexpr int MS = 4;                        // tile-metadata slots (the gather may run ~3 tiles ahead of the epilogue)
+constexpr int NS_MAX = 8;                    // pipeline stages (runtime: what fits in shared memory)
+constexpr int NT_P = 256;                    // 8 warps: TMA gather, MMA, weight loader, metadata loader, 4 epilogue
+constexpr int A_STAGE = TILE_M * 128;        // 128 rows x 32 floats
 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
@@ -144,24 +143,16 @@ struct Smem {
   __host__ __device__ Smem(int N, int K, int ns) {
     a = 0;
     b = a + ns * A_STAGE;
-    meta = b + ns * NCORE * N * 16;
+    meta = b + ns * N * 128;
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
     bars = meta + MS * meta_bytes;
-    tmem_slot = bars + (3 * ns + 2 * MS + 4) * 8;
+    tmem_slot = bars + (3 * NS_MAX + 2 * MS + 4) * 8;
     total = tmem_slot + 16;
   }
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-               : "=r"(ok)
-               : "r"(bar), "r"(parity)
-               : "memory");
-  return ok != 0;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -173,43 +164,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+// TMA row gather: 4 rows x 32 floats of the 2-D tensor behind `tm` -> 512 contiguous bytes of shared
+// memory (SWIZZLE_128B applied by the copy engine); a row index outside the tensor (-1 = "no
+// partner") is filled with zeros and still counts its 128 bytes on the mbarrier (tools/tma_gather_probe.cu)
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int col, int4 rows) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(col), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w)
+      : "memory");
+}
+// K-major SWIZZLE_128B operand: 8-row groups 1024 B apart, layout_type 2
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return make_desc(saddr, 16, 1024) | (2ull << 61);
+}
 
-// Persistent, warp-specialised gather-GEMM.  A CTA walks work items (tile, split) round-robin; five
+// Persistent, warp-specialised gather-GEMM.  A CTA walks work items (tile, split) round-robin; the
 // roles run decoupled through mbarrier rings, so the gathers of the next tiles, the MMAs of the
 // current one and the write-back of the previous one overlap:
-//   warp 10      metadata loader: tile's gather lists / row permutation / offset list -> smem slot
-//   warps 0-3    A producers: 16-byte cp.async gathers of the partner rows (zero-fill), one commit group
-//                per step; the arrival for a step is posted NSTAGE-1 steps later, after
-//                cp.async.wait_group + fence.proxy.async - a producer never waits for fresh data
-//   warp 5       weight loader: one cp.async.bulk (TMA) per step of the packed B slice
-//   warp 4       MMA issuer: tcgen05.mma.kind::tf32 into one of two TMEM accumulators
-//   warps 6-9    epilogue: tcgen05.ld -> (+bias) -> each stationary row written once
+//   warp 3       metadata loader: tile's gather lists / row permutation / offset list -> smem slot
+//   warp 0       A gather: per step 32 TMA gather4 copies (one per lane: 4 partner rows x 128 B, zero
+//                fill for missing partners) land the 128 x 32 slice in the K-major SWIZZLE_128B layout
+//                and complete_tx on the stage's fullA mbarrier - no thread ever waits for the data
+//   warp 2       weight loader: one cp.async.bulk (TMA) per step of the packed B slice
+//   warp 1       MMA issuer: 4 x tcgen05.mma.kind::tf32 (M=128, N, K=8) per step into one of two TMEM
+//                accumulators; tcgen05.commit frees the stage
+//   warps 4-7    epilogue: tcgen05.ld -> (+bias) -> each stationary row written once
 // Rings: fullA/fullB/empty per smem stage, meta_full/meta_empty per metadata slot,
 // tmem_full/tmem_empty per accumulator.
-template <int NSTAGE>
 __global__ void __launch_bounds__(NT_P, 1)
-k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
+k_osgemm_tf32(const __grid_constant__ CUtensorMap tmX, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t acc_cols,
-              float *__restrict__ Ypart, int n_items, int splits) {
-  // a producer posts step g-DEPTH while issuing step g.  DEPTH steps of gathers cover the memory
-  // latency; the other NSTAGE-DEPTH stages are slack between the MMA warp and the producers - with
-  // DEPTH = NSTAGE-1 every MMA would wait for a full producer round trip after the previous one
-  constexpr int DEPTH = NSTAGE >= 6 ? NSTAGE - 2 : NSTAGE / 2;
+              float *__restrict__ Ypart, int n_items, int splits, int NSTAGE) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L(N, K, NSTAGE);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_fullA = smem_u32(smem + L.bars);
-  const uint32_t bar_fullB = bar_fullA + NSTAGE * 8;
-  const uint32_t bar_empty = bar_fullB + NSTAGE * 8;
-  const uint32_t bar_mfull = bar_empty + NSTAGE * 8;
+  const uint32_t bar_fullB = bar_fullA + NS_MAX * 8;
+  const uint32_t bar_empty = bar_fullB + NS_MAX * 8;
+  const uint32_t bar_mfull = bar_empty + NS_MAX * 8;
   const uint32_t bar_mempty = bar_mfull + MS * 8;
   const uint32_t bar_tfull = bar_mempty + MS * 8;
   const uint32_t bar_tempty = bar_tfull + 2 * 8;
-  const int B_STAGE = NCORE * N * 16;
+  const int B_STAGE = N * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = tb.n_tiles;
-  const int kchunks = (Kd + KC - 1) / KC;
+  const int kchunks = Kd / KC;
 
   auto meta_idx = [&](int slot) { return reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.meta + slot * L.meta_bytes); };
   auto meta_perm = [&](int slot) { return reinterpret_cast<int32_t *>(smem + L.meta + slot * L.meta_bytes + K * TILE_M * 4); };
@@ -222,13 +222,13 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(bar_fullA + i * 8, 128);
+      mbar_init(bar_fullA + i * 8, 1);
       mbar_init(bar_fullB + i * 8, 1);
       mbar_init(bar_empty + i * 8, 1);
     }
     for (int i = 0; i < MS; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
-      mbar_init(bar_mempty + i * 8, 10);     // 4 producer warps + 4 epilogue warps + MMA + weight loader
+      mbar_init(bar_mempty + i * 8, 7);      // gather warp + MMA + weight loader + 4 epilogue warps
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
@@ -242,7 +242,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 10) {
+  if (warp == 3) {
     // ===== metadata loader =====
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -273,55 +273,31 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mfull + slot * 8);
     }
-  } else if (warp < 4) {
-    // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
-    const int j = tid & 7, r0 = tid >> 3;
+  } else if (warp == 0) {
+    // ===== A gather: lane l brings rows 4l..4l+3 of every step =====
     int g = 0, it = 0;                       // global step / item counters of this CTA
-    int arrived = 0;                         // steps this thread has posted on fullA
-    auto flush = [&]() {                     // post everything issued so far
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (; arrived < g; ++arrived) mbar_arrive(bar_fullA + (arrived % NSTAGE) * 8);
-    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int slot = it % MS;
-      // never block with arrivals pending: the metadata slot may only be recycled once the items
-      // whose last steps are still unposted here have drained (deadlock with 1-step items otherwise)
-      if (!mbar_test(bar_mfull + slot * 8, (it / MS) & 1)) {
-        flush();
-        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
-      }
+      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
       const int split = item / n_tiles;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
       for (int lst = 0; lst < steps; ++lst, ++g) {
         const int stage = g % NSTAGE, use = g / NSTAGE;
-        if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
         const int st = split + lst * splits;
         const int e = st / kchunks, c = st - e * kchunks;
-        const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-        if (j < ncore) {
-          const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
-          const float *colp = X + c * KC + j * 4;
-#pragma unroll
-          for (int i = 0; i < TILE_M / 16; ++i) {
-            const int row = r0 + 16 * i;
-            const int idx = sIdx[e][row];
-            cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
-          }
+        const int4 rows = reinterpret_cast<const int4 *>(sIdx[e])[lane];
+        if (lane == 0) {
+          if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+          mbar_expect_tx(bar_fullA + stage * 8, A_STAGE);
         }
-        cp_async_commit();
-        if (g - arrived >= DEPTH) {
-          cp_async_wait<DEPTH>();             // this thread's gathers of steps <= g-DEPTH have landed
-          fence_proxy_async();                // generic-proxy writes -> visible to the tensor core
-          for (; arrived <= g - DEPTH; ++arrived) mbar_arrive(bar_fullA + (arrived % NSTAGE) * 8);
-        }
+        __syncwarp();
+        tma_gather4(a_base + stage * A_STAGE + lane * 512, &tmX, bar_fullA + stage * 8, c * KC, rows);
       }
-      __syncwarp();                           // the tile's lists are no longer needed by this warp
+      __syncwarp();                           // the tile's lists are no longer needed
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
     }
-    flush();
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
@@ -329,7 +305,6 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int slot = it % MS;
         mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
-        const int split = item / n_tiles;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         mbar_arrive(bar_mempty + slot * 8);
         if (steps == 0) continue;
@@ -339,24 +314,20 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
         for (int lst = 0; lst < steps; ++lst, ++g) {
           const int stage = g % NSTAGE, use = g / NSTAGE;
-          const int c = (split + lst * splits) % kchunks;
-          const int ncore = min(NCORE, (Kd - c * KC) >> 2);
           mbar_wait(bar_fullB + stage * 8, use & 1);
           mbar_wait(bar_fullA + stage * 8, use & 1);
           tc_fence_after();
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
-          for (int kk = 0; kk < (ncore >> 1); ++kk) {
-            const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
-            const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
-            mma_tf32(tmem_d, ad, bd, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
-          }
+#pragma unroll
+          for (int kk = 0; kk < KC / 8; ++kk)   // K = 8 per instruction: 32 bytes further along the 128-byte rows
+            mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc, (lst > 0 || kk > 0) ? 1u : 0u);
           tc_commit(bar_empty + stage * 8);
         }
         tc_commit(bar_tfull + acc * 8);
         ++accn;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 2) {
     // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
     if (lane == 0) {
       int g = 0, it = 0;
@@ -371,18 +342,16 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
           const int st = split + lst * splits;
           const int e = st / kchunks, c = st - e * kchunks;
-          const int ncore = min(NCORE, (Kd - c * KC) >> 2);
           const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
-          const uint32_t bytes = (uint32_t)ncore * N * 16;
-          mbar_expect_tx(bar_fullB + stage * 8, bytes);
-          bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
+          mbar_expect_tx(bar_fullB + stage * 8, (uint32_t)B_STAGE);
+          bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, (uint32_t)B_STAGE,
                         bar_fullB + stage * 8);
         }
         mbar_arrive(bar_mempty + slot * 8);
       }
     }
   } else {
-    // ===== epilogue (warps 6-9): TMEM lanes 32*(warp%4).. -> registers -> global =====
+    // ===== epilogue (warps 4-7): TMEM lanes 32*(warp%4).. -> registers -> global =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int it = 0, accn = 0;
@@ -475,15 +444,19 @@ int g_gemm_grid_limit = 0;   // test knob (scn_set_gemm_grid_limit): force many 
 
 static bool tf32_shape_ok(const float *X, const float *W, const float *bias, float *Y, int Kd, int N) {
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
-  return Kd >= 8 && Kd % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
+  return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
 }
 
 }  // namespace tc
 
 // Y[stationary] = bias + sum_k X[partner_k] @ Wg[k], where Wg[k] is W[k] (transpose_w = 0, W is
 // [K][Kd][N]) or W[k]^T (transpose_w = 1, W is [K][N][Kd]).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N, long long n_rows,
-              const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s) {
+              long long n_partner, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s) {
   using namespace tc;
   if (precision != SCN_PRECISION_TF32) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
@@ -496,21 +469,42 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   // pipeline stages: what fits beside the metadata slots in ~215 KB
-  const int stage_bytes = A_STAGE + NCORE * N * 16;
+  const int stage_bytes = A_STAGE + N * 128;
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
   int ns = (215 * 1024 - meta_total) / stage_bytes;
-  ns = ns >= 6 ? 6 : (ns >= 4 ? 4 : 3);
+  if (ns > NS_MAX) ns = NS_MAX;
   const Smem L(N, K, ns);
+  // tensor map of the gathered feature matrix: rows x Kd floats, box = 32 floats x 1 row, 128B swizzle,
+  // zero fill outside (row index -1 = missing partner)
+  static PFN_encodeTiled encode = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_osgemm_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      dev_free(wp, s);
+      return -1;
+    }
+    if (cudaFuncSetAttribute(k_osgemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
       dev_free(wp, s);
       return -1;
     }
     attr_set = true;
+  }
+  CUtensorMap tmX;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)Kd, (cuuint64_t)(n_partner > 0 ? n_partner : 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)Kd * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, 1}, estr[2] = {1, 1};
+    const CUresult rc = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed (%d) for %lld x %d features", (int)rc, (long long)n_partner, Kd);
+      dev_free(wp, s);
+      return -1;
+    }
   }
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
@@ -531,9 +525,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int n_items = tv.n_tiles * splits;
   int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
-  if (ns == 3) k_osgemm_tf32<3><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
-  else if (ns == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
-  else k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
+  k_osgemm_tf32<<<grid, NT_P, L.total, s>>>(tmX, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, ns);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (splits > 1 && e == cudaSuccess) {

@@ -86,7 +86,26 @@ def run(name, a_fn, b_fn, a_mn, b_mn):
                                                                float(out.abs().max())))
 
 
+def run_k32_sw128():
+    """K-major SWIZZLE_128B for both operands, 4 MMAs of K=8 walking one 128-byte row (start += 32 B)"""
+    K32 = 32
+    rng = np.random.RandomState(1)
+    A = rng.randint(-4, 5, (M, K32)).astype(np.float32)
+    B = rng.randint(-4, 5, (N, K32)).astype(np.float32)
+    fa = lambda r, k: swz((r // 8) * 1024 + (r % 8) * 128 + k * 4, 3, 4, 3)
+    ia = torch.from_numpy(image(A, fa, M * 128)).cuda()
+    ib = torch.from_numpy(image(B, fa, N * 128)).cuda()
+    for lbo in (16, 1024):
+        out = torch.zeros(M, N, device="cuda")
+        rc = lib.umma_probe(ia.data_ptr(), ib.data_ptr(), M * 128, N * 128, desc_hi(lbo, 1024, 2), desc_hi(lbo, 1024, 2),
+                            idesc(0, 0), 4, 32, 32, N, out.data_ptr())
+        want = A @ B.T
+        print("K-major SW128 both, 4 MMAs step 32B, lbo=%d: rc=%d max|err|=%g (|D|max %g)" %
+              (lbo, rc, np.abs(out.cpu().numpy() - want).max(), np.abs(want).max()))
+
+
 if __name__ == "__main__":
+    run_k32_sw128()
     run("A MN base32 [katom][mi], B K-major", mn_base32, kmajor_noswz, 1, 0)
     run("A MN base32 [mi][katom], B K-major", mn_base32_b, kmajor_noswz, 1, 0)
     run("A K-major, B MN base32 [katom][ni]", kmajor_noswz, mn_base32, 0, 1)
