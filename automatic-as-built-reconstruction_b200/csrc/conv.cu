@@ -225,7 +225,7 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
   prof_begin(PROF_GEMM, s);
   int r = 1;
   if (precision != SCN_PRECISION_FP32)
-    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tb.n_partner, tv, tb.K, precision, transpose_w, s);
+    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s);
   if (r > 0) {  // 0 = done, negative = -(error); positive = shape outside the tensor path (e.g. Cin = 9)
     float *wt = nullptr;
     r = 0;
