@@ -22,9 +22,8 @@ namespace scn {
 namespace tc {
 
 constexpr int KC = 32;                      // reduction elements per pipeline step
-constexpr int NCORE = KC / 4;               // 16-byte k-cores (4 tf32) per step
-constexpr int A_LBO = TILE_M * 16 + 16;     // bytes between k-cores of A (+16: bank spread for the gather)
-constexpr int A_STAGE = NCORE * A_LBO;      // 16512
+constexpr int NCORE = KC / 4;               // 16-byte pieces (4 tf32) per row and step
+constexpr int A_STAGE = TILE_M * 128;       // 128 rows x 128 bytes, K-major SWIZZLE_128B
 constexpr int NT = 256;                     // threads of the weight-gradient kernel
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -107,9 +106,10 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: W fp32 [K][Cin][Cout] -> Wp[k][chunk c][k-core j][n][4], the exact shared-memory
-// image of the K-major B operand.  transpose=0: reduction dim = Cin, n = Cout (forward);
-// transpose=1: reduction dim = Cout, n = Cin (dX = dY @ W[k]^T).
+// weight packing: W fp32 [K][Cin][Cout] -> Wp[k][chunk c][n][32], the exact shared-memory image of
+// the K-major SWIZZLE_128B B operand: row n of a 32-wide reduction slice is 128 bytes whose 16-byte
+// chunks are XOR-ed with n%8.  transpose=0: reduction dim = Cin, n = Cout (forward);
+// transpose=1: reduction dim = Cout, n = Cin (dX = dY @ W[k]^T).  Values are rounded to tf32.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ Wp, int K, int Cin, int Cout,
                                int transpose) {
@@ -120,13 +120,11 @@ __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ 
        i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i / per_k);
     long long r = i - (long long)k * per_k;
-    // destination order inside offset k: chunk c, core j, column n, element t
+    // destination order inside offset k: chunk c, row n, 32 floats (swizzled)
     const int c = (int)(r / ((long long)KC * N));
     r -= (long long)c * KC * N;
-    const int j = (int)(r / (4 * N));
-    r -= (long long)j * 4 * N;
-    const int n = (int)(r >> 2), t = (int)(r & 3);
-    const int kk = c * KC + j * 4 + t;
+    const int n = (int)(r >> 5), pos = (int)(r & 31);
+    const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
     const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
     Wp[i] = to_tf32(v);
   }
@@ -154,6 +152,11 @@ struct Smem {
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B operand (rows of 128 bytes, 16-byte chunks XOR-ed with row%8): 8-row groups
+// 1024 B apart, layout_type 2; K advances by adding bytes to the start address (tools/umma_probe.py)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return make_desc(saddr, 16, 1024) | (2ull << 61);
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -209,7 +212,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   const int B_STAGE = NCORE * N * 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = tb.n_tiles;
-  const int kchunks = (Kd + KC - 1) / KC;
+  const int kchunks = Kd / KC;
 
   auto meta_idx = [&](int slot) { return reinterpret_cast<int32_t(*)[TILE_M]>(smem + L.meta + slot * L.meta_bytes); };
   auto meta_perm = [&](int slot) { return reinterpret_cast<int32_t *>(smem + L.meta + slot * L.meta_bytes + K * TILE_M * 4); };
@@ -299,15 +302,15 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
         const int st = split + lst * splits;
         const int e = st / kchunks, c = st - e * kchunks;
-        const int ncore = min(NCORE, (Kd - c * KC) >> 2);
-        if (j < ncore) {
-          const uint32_t dst = a_base + stage * A_STAGE + j * A_LBO;
+        {
+          // row r lives at (r/8)*1024 + (r%8)*128, its piece j at chunk j ^ (r%8): the 8 lanes of a row
+          // fill one 128-byte line of shared memory - no bank conflicts, no padding
+          const uint32_t dst = a_base + stage * A_STAGE + (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4);
           const float *colp = X + c * KC + j * 4;
 #pragma unroll
           for (int i = 0; i < TILE_M / 16; ++i) {
-            const int row = r0 + 16 * i;
-            const int idx = sIdx[e][row];
-            cp_async_16(dst + row * 16, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
+            const int idx = sIdx[e][r0 + 16 * i];     // rows r0 + 16 i share r0 % 8
+            cp_async_16(dst + i * 2048, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
           }
         }
         cp_async_commit();
@@ -339,17 +342,14 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
         for (int lst = 0; lst < steps; ++lst, ++g) {
           const int stage = g % NSTAGE, use = g / NSTAGE;
-          const int c = (split + lst * splits) % kchunks;
-          const int ncore = min(NCORE, (Kd - c * KC) >> 2);
           mbar_wait(bar_fullB + stage * 8, use & 1);
           mbar_wait(bar_fullA + stage * 8, use & 1);
           tc_fence_after();
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
-          for (int kk = 0; kk < (ncore >> 1); ++kk) {
-            const uint64_t ad = make_desc(sa + kk * 2 * A_LBO, A_LBO, 128);
-            const uint64_t bd = make_desc(sb + kk * 2 * N * 16, N * 16, 128);
-            mma_tf32(tmem_d, ad, bd, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
-          }
+#pragma unroll
+          for (int kk = 0; kk < KC / 8; ++kk)   // K = 8 per instruction: 32 bytes further along the 128-byte rows
+            mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
+                     (lst > 0 || kk > 0) ? 1u : 0u);
           tc_commit(bar_empty + stage * 8);
         }
         tc_commit(bar_tfull + acc * 8);
@@ -371,9 +371,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
           const int st = split + lst * splits;
           const int e = st / kchunks, c = st - e * kchunks;
-          const int ncore = min(NCORE, (Kd - c * KC) >> 2);
           const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
-          const uint32_t bytes = (uint32_t)ncore * N * 16;
+          const uint32_t bytes = (uint32_t)B_STAGE;
           mbar_expect_tx(bar_fullB + stage * 8, bytes);
           bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
                         bar_fullB + stage * 8);
@@ -475,7 +474,7 @@ int g_gemm_grid_limit = 0;   // test knob (scn_set_gemm_grid_limit): force many 
 
 static bool tf32_shape_ok(const float *X, const float *W, const float *bias, float *Y, int Kd, int N) {
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
-  return Kd >= 8 && Kd % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
+  return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256 && al(X) && al(W) && al(Y) && (!bias || al(bias));
 }
 
 }  // namespace tc

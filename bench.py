@@ -164,15 +164,36 @@ def reference_state_dict():
     return sd
 
 
-def cpu_reference_step(sd, locs, feats):
-    """one fwd+bwd of the compiled reference CPU path (fresh Metadata); returns seconds"""
+def cpu_reference_step(sd, locs, feats, keep_outputs=False):
+    """one fwd+bwd of the compiled reference CPU path (fresh Metadata); returns seconds (and, for the
+    parity report, the 8 output maps as (locations, features))"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_backbone as RB
     net = RB.RefBackbone(sd, full_scale=FULL_SCALE, n_planes=PLANES, rpn_map_sizes=RPN_SIZES)
     t0 = time.perf_counter()
     rpn, roi = net.forward(locs, feats)
     RB.backbone_loss(rpn, roi).backward()
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    if keep_outputs:
+        return dt, [(m.locations(), m.features.detach(), m.ss.tolist()) for m in list(rpn) + list(roi)]
+    return dt
+
+
+def parity_report(gpu_maps, ref_maps):
+    """max relative feature error of the backbone's 8 output maps against the reference CPU run of the
+    same batch and weights, rows matched by coordinate (canonical order)"""
+    import scn_oracle as O
+    worst, sites_equal = 0.0, True
+    for g, (rloc, rfeat, ss) in zip(gpu_maps, ref_maps):
+        gloc = g.get_spatial_locations().numpy()
+        og, orf = np.argsort(O.canonical_rank(gloc, ss)), np.argsort(O.canonical_rank(rloc.numpy(), ss))
+        if gloc.shape != tuple(rloc.shape) or not np.array_equal(gloc[og], rloc.numpy()[orf]):
+            sites_equal = False
+            continue
+        a, b = g.features.detach().cpu().numpy()[og], rfeat.numpy()[orf]
+        worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)))
+    return {"active_site_sets_equal": sites_equal, "max_rel_feature_err_vs_reference_cpu": worst,
+            "maps_compared": len(ref_maps)}
 
 
 def run_reference(args, rank, world):
@@ -345,7 +366,10 @@ def run_b200(args, rank, local_rank, world):
             cores = os.cpu_count()
             torch.set_num_threads(cores)
             sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-            t = cpu_reference_step(sd, locs, feats)
+            with torch.no_grad():
+                rpn_g, roi_g = net([locs_dev, feats_dev])
+            t, ref_maps = cpu_reference_step(sd, locs, feats, keep_outputs=True)
+            out["parity"] = parity_report(list(rpn_g) + list(roi_g), ref_maps)
             out["cpu_baseline"] = {"value": na_local / t, "unit": "active voxels/s", "cores": cores,
                                    "kind": "reference", "seconds_per_step": t,
                                    "sample": "1 step (same %d-point batch, nActive %d) fwd+bwd on the compiled "
