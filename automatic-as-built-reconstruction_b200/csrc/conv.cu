@@ -222,10 +222,14 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
            const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip) {
   if (tb.n_tiles == 0) return 0;
   const TileView tv = make_view(tb, k_flip);
-  prof_begin(PROF_GEMM, s);
+  // algorithmic bytes: every feature row once, the weights once, 8 B per pair.  The timed
+  // region is the gather-GEMM kernel itself (weight packing / split-K reduce are outside it).
+  const double bytes = 4.0 * ((double)tb.n_partner * Cin + (double)tb.n_rows * Cout) +
+                       4.0 * tb.K * Cin * Cout + (tb.identity ? 0.0 : 8.0 * tb.n_pairs);
+  const double flops = 2.0 * tb.n_pairs * Cin * Cout;
   int r = 1;
   if (precision != SCN_PRECISION_FP32)
-    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s);
+    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s, bytes, flops);
   if (r > 0) {  // 0 = done, negative = -(error); positive = shape outside the tensor path (e.g. Cin = 9)
     float *wt = nullptr;
     r = 0;
@@ -234,17 +238,15 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
       if (!r) r = transpose_weights(W, wt, tb.K, Cout, Cin, s);   // W is [K][Cout=N][Cin=Kd] -> [K][Kd][N]
     }
     const float *w = transpose_w ? wt : W;
+    prof_begin(PROF_GEMM, s);
     if (!r)
       r = Cout <= 32 ? launch_osgemm_ffma<32>(X, w, bias, Y, Cin, Cout, tb.n_rows, tv, s)
                      : launch_osgemm_ffma<64>(X, w, bias, Y, Cin, Cout, tb.n_rows, tv, s);
+    prof_end(PROF_GEMM, s, bytes, flops);
     dev_free(wt, s);
   } else {
     r = -r;
   }
-  // algorithmic bytes: every feature row once, the weights once, 8 B per pair
-  const double bytes = 4.0 * ((double)tb.n_partner * Cin + (double)tb.n_rows * Cout) +
-                       4.0 * tb.K * Cin * Cout + (tb.identity ? 0.0 : 8.0 * tb.n_pairs);
-  prof_end(PROF_GEMM, s, bytes, 2.0 * tb.n_pairs * Cin * Cout);
   return r;
 }
 

@@ -27,7 +27,8 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Kd, 
 // tensor-core variants. Return 0 = done, >0 = shape/precision not handled (caller uses the FFMA
 // kernels), <0 = -(error) with scn_last_error set.
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
-              long long n_rows, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s);
+              long long n_rows, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s,
+              double prof_bytes, double prof_flops);
 int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const DwWork *work, float *partial,
                   int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,
                   int precision, cudaStream_t s);

@@ -482,7 +482,8 @@ static bool tf32_shape_ok(const float *X, const float *W, const float *bias, flo
 // Y[stationary] = bias + sum_k X[partner_k] @ Wg[k], where Wg[k] is W[k] (transpose_w = 0, W is
 // [K][Kd][N]) or W[k]^T (transpose_w = 1, W is [K][N][Kd]).
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N, long long n_rows,
-              const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s) {
+              const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
+              double prof_flops) {
   using namespace tc;
   if (precision != SCN_PRECISION_TF32) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
@@ -530,9 +531,11 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int n_items = tv.n_tiles * splits;
   int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
+  prof_begin(PROF_GEMM, s);
   if (ns == 3) k_osgemm_tf32<3><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
   else if (ns == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
   else k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
+  prof_end(PROF_GEMM, s, prof_bytes, prof_flops);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (splits > 1 && e == cudaSuccess) {
