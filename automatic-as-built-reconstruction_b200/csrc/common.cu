@@ -1,6 +1,7 @@
 // common.cu - error state, stream-ordered allocation, device-wide scan and radix sort.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 #include "../../include/scn_b200.h"
@@ -60,6 +61,20 @@ static void init_pool() {
     // block whose free has already completed, or fresh memory.
     int off = 0;
     cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
+    // Pre-size the pool (it never trims): without this the first ~25 steps each extend it through the
+    // driver (hundreds of microseconds per extension) until it covers the window of steps in flight.
+    // SCN_B200_POOL_MB overrides the 6 GB default (0 = grow on demand).
+    const char *env = getenv("SCN_B200_POOL_MB");
+    const size_t mb = env ? (size_t)atoll(env) : 6144;
+    if (mb > 0) {
+      void *p = nullptr;
+      if (cudaMallocAsync(&p, mb << 20, 0) == cudaSuccess) {
+        cudaFreeAsync(p, 0);
+        cudaStreamSynchronize(0);
+      } else {
+        cudaGetLastError();   // not enough free memory: fall back to growing on demand
+      }
+    }
   }
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }

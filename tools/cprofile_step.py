@@ -21,14 +21,20 @@ locs, feats = bench.make_batch(300000, 1, 1, 0)
 c, f = locs.to(dev), feats.to(dev)
 
 
+pf = scn.InputPrefetcher(net.prepare)
+pf.submit(c)
+
+
 def step():
     net.zero_grad(set_to_none=True)
-    rpn, roi = net([c, f])
+    p = pf.get()
+    pf.submit(c)
+    rpn, roi = net([p, f])
     loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
     loss.backward()
 
 
-for _ in range(3):
+for _ in range(25):
     step()
 torch.cuda.synchronize()
 pr = cProfile.Profile()
@@ -38,4 +44,4 @@ for _ in range(5):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("tottime").print_stats(28)
+st.sort_stats("tottime").print_stats(45)
