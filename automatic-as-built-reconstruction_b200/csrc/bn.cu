@@ -277,7 +277,7 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   prof_begin(PROF_BN, s);
   double *acc = nullptr;
   if (train) {
-    SCN_TRY(dev_alloc_t(&acc, (size_t)2 * C, s));
+    SCN_TRY(workspace_t(&acc, WS_BN, (size_t)2 * C, s));
     SCN_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), s));
     if (vec)
       k_bn_stats_vec<false><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, nullptr, nullptr, nullptr, 0.f, n, C, acc);
@@ -292,7 +292,6 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
   else k_bn_fwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
   SCN_LAUNCHED();
-  dev_free(acc, s);
   prof_end(PROF_BN, s, (train ? 3.0 : 2.0) * 4.0 * (double)n * C, 0);  // 3 n C s
   return 0;
 }
@@ -313,7 +312,7 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0);
   prof_begin(PROF_BN, s);
   double *acc = nullptr;
-  SCN_TRY(dev_alloc_t(&acc, (size_t)2 * C, s));
+  SCN_TRY(workspace_t(&acc, WS_BN, (size_t)2 * C, s));
   SCN_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), s));
   if (vec)
     k_bn_stats_vec<true><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, acc);
@@ -330,7 +329,6 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
     k_bn_bwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
                                                            weight, d_weight, d_bias, leakiness, n, C);
   SCN_LAUNCHED();
-  dev_free(acc, s);
   prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;
 }

@@ -95,6 +95,33 @@ void dev_free(void *p, cudaStream_t s) {
   if (p) cudaFreeAsync(p, s);
 }
 
+struct WsBuf { void *p = nullptr; size_t cap = 0; };
+static std::mutex g_ws_mu;
+static std::vector<std::pair<cudaStream_t, WsBuf *>> g_ws;   // a handful of streams: linear search
+
+int workspace(void **p, int slot, size_t bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  WsBuf *bufs = nullptr;
+  for (auto &e : g_ws)
+    if (e.first == s) { bufs = e.second; break; }
+  if (!bufs) {
+    bufs = new WsBuf[WS_SLOTS];
+    g_ws.emplace_back(s, bufs);
+  }
+  WsBuf &b = bufs[slot];
+  if (b.cap < bytes) {
+    if (b.p) cudaFreeAsync(b.p, s);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t cap = bytes + bytes / 4;
+    cap = (cap + 255) & ~(size_t)255;
+    SCN_TRY(dev_alloc(&b.p, cap, s));
+    b.cap = cap;
+  }
+  *p = b.p;
+  return 0;
+}
+
 int64_t *host_scratch(size_t n) {
   static thread_local int64_t *buf = nullptr;
   static thread_local size_t cap = 0;

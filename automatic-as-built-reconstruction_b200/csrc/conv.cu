@@ -234,7 +234,7 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
     float *wt = nullptr;
     r = 0;
     if (transpose_w) {
-      r = dev_alloc_t(&wt, (size_t)tb.K * Cin * Cout, s);
+      r = workspace_t(&wt, WS_WT, (size_t)tb.K * Cin * Cout, s);
       if (!r) r = transpose_weights(W, wt, tb.K, Cout, Cin, s);   // W is [K][Cout=N][Cin=Kd] -> [K][Kd][N]
     }
     const float *w = transpose_w ? wt : W;
@@ -243,7 +243,6 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
       r = Cout <= 32 ? launch_osgemm_ffma<32>(X, w, bias, Y, Cin, Cout, tb.n_rows, tv, s)
                      : launch_osgemm_ffma<64>(X, w, bias, Y, Cin, Cout, tb.n_rows, tv, s);
     prof_end(PROF_GEMM, s, bytes, flops);
-    dev_free(wt, s);
   } else {
     r = -r;
   }
@@ -429,7 +428,7 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
   const double dw_flops = 2.0 * rb->total_pairs * cc;
   float *partial = nullptr;
   if (n_work > 0) {
-    SCN_TRY(dev_alloc_t(&partial, (size_t)n_work * cc, s));
+    SCN_TRY(workspace_t(&partial, WS_DW_PARTIAL, (size_t)n_work * cc, s));
     const int cmax = Cin < Cout ? Cout : Cin;
     int r = 1;
     if (precision != SCN_PRECISION_FP32)
@@ -439,12 +438,11 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
     else if (cmax <= 32) r = launch_dw_partial<2, 2>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
     else if (cmax <= 64) r = launch_dw_partial<4, 4>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
     else r = launch_dw_partial<8, 8>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, s);
-    if (r) { dev_free(partial, s); return 1; }
+    if (r) return 1;
   }
   dim3 grid(cdiv(cc, 256), K);
   k_dw_reduce<<<grid, 256, 0, s>>>(partial, dW, first, cc);
   SCN_LAUNCHED();
-  dev_free(partial, s);
   prof_end(PROF_DW, s, dw_bytes, dw_flops);
   return 0;
 }

@@ -488,7 +488,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   if (precision != SCN_PRECISION_TF32) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
   float *wp = nullptr;
-  if (dev_alloc_t(&wp, (size_t)K * Kd * N, s)) return -1;
+  if (workspace_t(&wp, WS_PACKED_W, (size_t)K * Kd * N, s)) return -1;
   const long long total = (long long)K * Kd * N;
   int pb = cdiv(total, 256);
   if (pb > num_sms() * 8) pb = num_sms() * 8;
@@ -507,7 +507,6 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
         cudaFuncSetAttribute(k_osgemm_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_osgemm_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
-      dev_free(wp, s);
       return -1;
     }
     attr_set = true;
@@ -527,7 +526,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   }
   float *ypart = nullptr;
   const long long n_slots = (long long)tv.n_tiles * TILE_M;
-  if (splits > 1 && dev_alloc_t(&ypart, (size_t)splits * n_slots * N, s)) { dev_free(wp, s); return -1; }
+  if (splits > 1 && workspace_t(&ypart, WS_SPLITK, (size_t)splits * n_slots * N, s)) return -1;
   const int n_items = tv.n_tiles * splits;
   int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
@@ -544,8 +543,6 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     g_launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaGetLastError();
   }
-  dev_free(ypart, s);
-  dev_free(wp, s);
   if (e != cudaSuccess) {
     set_error("k_osgemm_tf32 launch failed: %s", cudaGetErrorString(e));
     return -1;
