@@ -122,6 +122,32 @@ int workspace(void **p, int slot, size_t bytes, cudaStream_t s) {
   return 0;
 }
 
+static std::mutex g_side_mu;
+static std::vector<std::pair<cudaStream_t, SideStream *>> g_side;
+
+int side_stream(cudaStream_t s, SideStream **out) {
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  for (auto &e : g_side)
+    if (e.first == s) { *out = e.second; return 0; }
+  SideStream *ss = new SideStream();
+  SCN_CUDA(cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking));
+  SCN_CUDA(cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming));
+  SCN_CUDA(cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming));
+  g_side.emplace_back(s, ss);
+  *out = ss;
+  return 0;
+}
+int side_fork(cudaStream_t s, SideStream *ss) {
+  SCN_CUDA(cudaEventRecord(ss->fork, s));
+  SCN_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  return 0;
+}
+int side_join(cudaStream_t s, SideStream *ss) {
+  SCN_CUDA(cudaEventRecord(ss->join, ss->stream));
+  SCN_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+  return 0;
+}
+
 int64_t *host_scratch(size_t n) {
   static thread_local int64_t *buf = nullptr;
   static thread_local size_t cap = 0;

@@ -67,6 +67,14 @@ inline int workspace_t(T **p, int slot, size_t n, cudaStream_t s) {
   return workspace((void **)p, slot, (n ? n : 1) * sizeof(T), s);
 }
 
+// A companion stream of `s` for work that is independent of what `s` does next (the weight gradient
+// of a layer next to its input gradient).  fork: side waits for everything queued on s so far;
+// join: s waits for the side stream.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+int side_stream(cudaStream_t s, SideStream **out);
+int side_fork(cudaStream_t s, SideStream *ss);
+int side_join(cudaStream_t s, SideStream *ss);
+
 // pinned host scratch for count read-backs (per thread)
 int64_t *host_scratch(size_t n_int64);
 

@@ -485,9 +485,18 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
   const bool mirror = rb->kind == 0 && !rb->identity && (rb->filter[0] & rb->filter[1] & rb->filter[2] & 1);
   if (!mirror) SCN_TRY(ensure_tilebook(rb, dx_stationary_out, s));
   TileBook &tb = (dx_stationary_out || mirror) ? rb->tb_out : rb->tb_in;
+  // dX and dW are independent: the weight gradient runs on the companion stream, so the many small
+  // (latency-bound, few-CTA) launches of the coarse scales overlap instead of queueing
+  SideStream *ss = nullptr;
+  const bool fork = d_in && d_weight;
+  if (fork) {
+    SCN_TRY(side_stream(s, &ss));
+    SCN_TRY(side_fork(s, ss));
+  }
   if (d_in)
     SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s, mirror ? rb->K - 1 : -1));
-  if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, s));
+  if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, fork ? ss->stream : s));
+  if (fork) SCN_TRY(side_join(s, ss));
   SCN_TRY(bias_grad(d_out, d_bias, n_dout_rows, Cout, s));
   return 0;
 }
