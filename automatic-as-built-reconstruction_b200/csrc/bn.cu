@@ -7,6 +7,8 @@
 // the per-channel coefficients themselves (no separate finalize launch).
 #include "common.cuh"
 #include "../../include/scn_b200.h"
+#include <mutex>
+#include <vector>
 
 namespace scn {
 
@@ -152,6 +154,8 @@ __device__ __forceinline__ void bn_bwd_coef(const double *__restrict__ acc, long
 __device__ __forceinline__ float lrelu(float v, float leak) { return v > 0.f ? v : v * leak; }
 
 struct BnFwdArgs {
+  double *zero_buf;   // the OTHER ping-pong sum buffer: block 0 clears it for the next BN call
+  int zero_n;
   const double *acc;
   float *save_mean, *save_invstd, *running_mean, *running_var;
   const float *weight, *bias;
@@ -164,6 +168,8 @@ __global__ void __launch_bounds__(BN_T)
 k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, float leak,
                long long n, int C) {
   extern __shared__ float coef[];  // [2C]
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < a.zero_n; i += BN_T) a.zero_buf[i] = 0.0;
   for (int c = threadIdx.x; c < C; c += BN_T)
     bn_fwd_coef(a.acc, n, C, c, a.save_mean, a.save_invstd, a.running_mean, a.running_var, a.weight,
                 a.bias, a.eps, a.momentum, a.train, blockIdx.x == 0, coef);
@@ -199,9 +205,11 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, float *__restrict__ dX,
                const float *__restrict__ mean, const double *__restrict__ acc,
                const float *__restrict__ save_invstd, const float *__restrict__ weight,
-               float *d_weight, float *d_bias, float leak, long long n, int C) {
+               float *d_weight, float *d_bias, float leak, long long n, int C, double *zero_buf, int zero_n) {
   extern __shared__ float coef[];  // [3C] then mean [C]
   float *smean = coef + 3 * C;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < zero_n; i += BN_T) zero_buf[i] = 0.0;
   for (int c = threadIdx.x; c < C; c += BN_T) {
     bn_bwd_coef(acc, n, C, c, save_invstd, weight, d_weight, d_bias, blockIdx.x == 0, coef);
     smean[c] = mean[c];
@@ -250,6 +258,39 @@ static int stats_grid(long long n, int rows_per_iter) {
   return (int)g;
 }
 
+// Per-stream ping-pong pair of fp64 sum buffers.  A BN call accumulates into one and its apply kernel
+// clears the other (last read by the previous call's apply kernel, complete by stream order), so no
+// memset is launched per call.
+struct BnState { double *buf[2]; int used[2]; int k; };
+static std::mutex g_bn_mu;
+static std::vector<std::pair<cudaStream_t, BnState *>> g_bn;
+constexpr int BN_MAX_C = 4096;
+
+static int bn_buffers(cudaStream_t s, int C, double **cur, double **other, int *other_used) {
+  std::lock_guard<std::mutex> lk(g_bn_mu);
+  BnState *st = nullptr;
+  for (auto &e : g_bn)
+    if (e.first == s) { st = e.second; break; }
+  if (!st) {
+    st = new BnState();
+    for (int i = 0; i < 2; ++i) {
+      SCN_CUDA(cudaMalloc((void **)&st->buf[i], (size_t)2 * BN_MAX_C * sizeof(double)));
+      SCN_CUDA(cudaMemset(st->buf[i], 0, (size_t)2 * BN_MAX_C * sizeof(double)));
+      st->used[i] = 0;
+    }
+    st->k = 0;
+    g_bn.emplace_back(s, st);
+  }
+  const int a = st->k & 1, b = a ^ 1;
+  *cur = st->buf[a];
+  *other = st->buf[b];
+  *other_used = st->used[b];
+  st->used[a] = 2 * C;
+  st->used[b] = 0;
+  st->k++;
+  return 0;
+}
+
 static int apply_grid(long long work) {
   long long g = (work + BN_T - 1) / BN_T;
   const long long cap = (long long)num_sms() * 8;
@@ -275,10 +316,10 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   SCN_CHECK(in && out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, out, in, out);
   prof_begin(PROF_BN, s);
-  double *acc = nullptr;
+  double *acc = nullptr, *other = nullptr;
+  int other_used = 0;
   if (train) {
-    SCN_TRY(workspace_t(&acc, WS_BN, (size_t)2 * C, s));
-    SCN_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), s));
+    SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
     if (vec)
       k_bn_stats_vec<false><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, nullptr, nullptr, nullptr, 0.f, n, C, acc);
     else
@@ -286,7 +327,7 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
                                                                                      0.f, n, C, acc);
     SCN_LAUNCHED();
   }
-  BnFwdArgs a{acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train ? 1 : 0};
+  BnFwdArgs a{other, other_used, acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train ? 1 : 0};
   const long long total = (long long)n * C;
   const size_t sm = (size_t)2 * C * sizeof(float);
   if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
@@ -311,9 +352,9 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   SCN_CHECK(in && d_in && out && d_out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0);
   prof_begin(PROF_BN, s);
-  double *acc = nullptr;
-  SCN_TRY(workspace_t(&acc, WS_BN, (size_t)2 * C, s));
-  SCN_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), s));
+  double *acc = nullptr, *other = nullptr;
+  int other_used = 0;
+  SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
   if (vec)
     k_bn_stats_vec<true><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, acc);
   else
@@ -324,10 +365,10 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   const size_t sm = (size_t)4 * C * sizeof(float);
   if (vec)
     k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
-                                                              weight, d_weight, d_bias, leakiness, n, C);
+                                                              weight, d_weight, d_bias, leakiness, n, C, other, other_used);
   else
     k_bn_bwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
-                                                           weight, d_weight, d_bias, leakiness, n, C);
+                                                           weight, d_weight, d_bias, leakiness, n, C, other, other_used);
   SCN_LAUNCHED();
   prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;

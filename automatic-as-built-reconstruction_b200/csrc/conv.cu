@@ -219,7 +219,8 @@ TileView make_view(const TileBook &tb, int k_flip) {
 
 // Y[stationary rows] = bias + sum_k X[partner_k] @ W[k]   (W: [K,Cin,Cout] row-major)
 int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
-           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip) {
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip,
+           const int64_t *weight_tag) {
   if (tb.n_tiles == 0) return 0;
   const TileView tv = make_view(tb, k_flip);
   // algorithmic bytes: every feature row once, the weights once, 8 B per pair.  The timed
@@ -229,7 +230,7 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
   const double flops = 2.0 * tb.n_pairs * Cin * Cout;
   int r = 1;
   if (precision != SCN_PRECISION_FP32)
-    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s, bytes, flops);
+    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s, bytes, flops, weight_tag);
   if (r > 0) {  // 0 = done, negative = -(error); positive = shape outside the tensor path (e.g. Cin = 9)
     float *wt = nullptr;
     r = 0;
@@ -478,7 +479,8 @@ static double macs_of(const RuleBook *rb, int64_t cin, int64_t cout) {
 static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const float *in, float *d_in,
                                 const float *d_out, const float *weight, float *d_weight,
                                 float *d_bias, int Cin, int Cout, int xcol, int ycol,
-                                long long n_dout_rows, int precision, cudaStream_t s) {
+                                long long n_dout_rows, int precision, cudaStream_t s,
+                                const int64_t *weight_tag = nullptr) {
   // submanifold rulebooks with odd filters are their own mirror image: the out-row that in-row i
   // feeds at offset k is the site at i - delta_k = t_out[K-1-k][i], so dX runs on the forward lists
   // with the weight index flipped and no second tile book is ever built
@@ -494,7 +496,8 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
     SCN_TRY(side_fork(s, ss));
   }
   if (d_in)
-    SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s, mirror ? rb->K - 1 : -1));
+    SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s, mirror ? rb->K - 1 : -1,
+                   weight_tag));
   if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, fork ? ss->stream : s));
   if (fork) SCN_TRY(side_join(s, ss));
   SCN_TRY(bias_grad(d_out, d_bias, n_dout_rows, Cout, s));
@@ -510,7 +513,7 @@ extern "C" {
 int scn_submanifold_conv_forward(scn_metadata_t *m, const int64_t *ss, const int64_t *filter,
                                  const float *in, float *out, const float *weight,
                                  const float *bias, int64_t cin, int64_t cout, int precision,
-                                 void *stream, double *macs) {
+                                 void *stream, double *macs, const int64_t *weight_tag) {
   SCN_CHECK(m && ss && filter && weight, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RuleBook *rb = nullptr;
@@ -518,13 +521,13 @@ int scn_submanifold_conv_forward(scn_metadata_t *m, const int64_t *ss, const int
   if (macs) *macs = macs_of(rb, cin, cout);
   if (rb->n_out == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, 0, s);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, 0, s, -1, weight_tag);
 }
 
 int scn_submanifold_conv_backward(scn_metadata_t *m, const int64_t *ss, const int64_t *filter,
                                   const float *in, float *d_in, const float *d_out,
                                   const float *weight, float *d_weight, float *d_bias, int64_t cin,
-                                  int64_t cout, int precision, void *stream) {
+                                  int64_t cout, int precision, void *stream, const int64_t *weight_tag) {
   SCN_CHECK(m && ss && filter && weight, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RuleBook *rb = nullptr;
@@ -534,26 +537,26 @@ int scn_submanifold_conv_backward(scn_metadata_t *m, const int64_t *ss, const in
     return 0;
   }
   return conv_backward_common(rb, /*dx over in rows*/ false, in, d_in, d_out, weight, d_weight,
-                              d_bias, (int)cin, (int)cout, 0, 1, rb->n_out, precision, s);
+                              d_bias, (int)cin, (int)cout, 0, 1, rb->n_out, precision, s, weight_tag);
 }
 
 int scn_conv_forward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
                      const int64_t *filter, const int64_t *stride, const float *in, float *out,
                      const float *weight, const float *bias, int64_t cin, int64_t cout,
-                     int precision, void *stream, double *macs) {
+                     int precision, void *stream, double *macs, const int64_t *weight_tag) {
   SCN_CHECK(m && in_ss && out_ss && filter && stride && weight, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RuleBook *rb = nullptr;
   SCN_TRY(get_conv_rulebook(m, in_ss, out_ss, filter, stride, s, &rb));
   if (macs) *macs = macs_of(rb, cin, cout);
   if (rb->n_out == 0) return 0;
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, 0, s);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_out, precision, 0, s, -1, weight_tag);
 }
 
 int scn_conv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
                       const int64_t *filter, const int64_t *stride, const float *in, float *d_in,
                       const float *d_out, const float *weight, float *d_weight, float *d_bias,
-                      int64_t cin, int64_t cout, int precision, void *stream) {
+                      int64_t cin, int64_t cout, int precision, void *stream, const int64_t *weight_tag) {
   SCN_CHECK(m && in_ss && out_ss && filter && stride && weight, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RuleBook *rb = nullptr;
@@ -563,7 +566,7 @@ int scn_conv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *ou
     return 0;
   }
   return conv_backward_common(rb, false, in, d_in, d_out, weight, d_weight, d_bias, (int)cin,
-                              (int)cout, 0, 1, rb->n_out, precision, s);
+                              (int)cout, 0, 1, rb->n_out, precision, s, weight_tag);
 }
 
 // Deconvolution: rulebook of the matching down-convolution with roles swapped
@@ -571,7 +574,7 @@ int scn_conv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *ou
 int scn_deconv_forward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
                        const int64_t *filter, const int64_t *stride, const float *in, float *out,
                        const float *weight, const float *bias, int64_t cin, int64_t cout,
-                       int precision, void *stream, double *macs) {
+                       int precision, void *stream, double *macs, const int64_t *weight_tag) {
   SCN_CHECK(m && in_ss && out_ss && filter && stride && weight, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RuleBook *rb = nullptr;
@@ -579,13 +582,13 @@ int scn_deconv_forward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *o
   if (macs) *macs = macs_of(rb, cin, cout);
   if (rb->n_in == 0) return 0;
   SCN_TRY(ensure_tilebook(rb, false, s));
-  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_in, precision, 0, s);
+  return osgemm(in, weight, bias, out, (int)cin, (int)cout, rb->tb_in, precision, 0, s, -1, weight_tag);
 }
 
 int scn_deconv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *out_ss,
                         const int64_t *filter, const int64_t *stride, const float *in, float *d_in,
                         const float *d_out, const float *weight, float *d_weight, float *d_bias,
-                        int64_t cin, int64_t cout, int precision, void *stream) {
+                        int64_t cin, int64_t cout, int precision, void *stream, const int64_t *weight_tag) {
   SCN_CHECK(m && in_ss && out_ss && filter && stride && weight, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RuleBook *rb = nullptr;
@@ -596,7 +599,7 @@ int scn_deconv_backward(scn_metadata_t *m, const int64_t *in_ss, const int64_t *
   }
   // d_in lives on the coarse scale = the rulebook's "out" side
   return conv_backward_common(rb, true, in, d_in, d_out, weight, d_weight, d_bias, (int)cin,
-                              (int)cout, 1, 0, rb->n_in, precision, s);
+                              (int)cout, 1, 0, rb->n_in, precision, s, weight_tag);
 }
 
 int scn_nin_forward(const float *in, float *out, const float *weight, const float *bias,

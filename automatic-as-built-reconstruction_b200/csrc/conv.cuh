@@ -22,13 +22,14 @@ TileView make_view(const TileBook &tb, int k_flip = -1);
 // k_flip >= 0: the gather lists were built for the mirrored problem (submanifold dX through the
 // forward lists): table offset k pairs with weight slice k_flip - k.
 int osgemm(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
-           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip = -1);
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip = -1,
+           const int64_t *weight_tag = nullptr);
 
 // tensor-core variants. Return 0 = done, >0 = shape/precision not handled (caller uses the FFMA
 // kernels), <0 = -(error) with scn_last_error set.
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
               long long n_rows, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s,
-              double prof_bytes, double prof_flops);
+              double prof_bytes, double prof_flops, const int64_t *weight_tag);
 int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const DwWork *work, float *partial,
                   int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,
                   int precision, cudaStream_t s);

@@ -17,6 +17,9 @@
 // tf32 when packed.  Accumulation is fp32.
 #include "conv.cuh"
 #include "../../include/scn_b200.h"
+#include <algorithm>
+#include <mutex>
+#include <vector>
 
 namespace scn {
 namespace tc {
@@ -470,6 +473,91 @@ __global__ void k_splitk_reduce(const float *__restrict__ Ypart, const float *__
   *reinterpret_cast<float4 *>(Y + orow * N + c) = a;
 }
 
+// both operand images of a weight tensor in one launch: [0,total) forward layout, [total,2 total) dX layout
+__global__ void k_pack_weights_both(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wb,
+                                    int K, int Cin, int Cout, int do_f, int do_b) {
+  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
+  for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
+       i2 += (long long)gridDim.x * blockDim.x) {
+    const int transpose = i2 >= total;
+    if (transpose ? !do_b : !do_f) continue;
+    const long long i = transpose ? i2 - total : i2;
+    const int N = transpose ? Cin : Cout;
+    const int k = (int)(i / per_k);
+    long long r = i - (long long)k * per_k;
+    const int c = (int)(r / ((long long)KC * N));
+    r -= (long long)c * KC * N;
+    const int n = (int)(r >> 5), pos = (int)(r & 31);
+    const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
+    const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
+    (transpose ? Wb : Wf)[i] = to_tf32(v);
+  }
+}
+
+// Packed-operand cache, keyed by the caller's identity token of the weight tensor.
+struct PackEntry {
+  int64_t token = 0, version = -1;
+  int K = 0, Cin = 0, Cout = 0;
+  bool has_f = false, has_b = false;
+  cudaStream_t stream = 0;
+  float *wf = nullptr, *wb = nullptr;
+  uint64_t last_use = 0;
+};
+static std::mutex g_pack_mu;
+static std::vector<PackEntry *> g_pack;
+static uint64_t g_pack_clock = 0;
+
+static bool layout_ok(int Kd, int N) { return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256; }
+
+// returns the packed image for (transpose ? dX : forward), (re)building both when the version moved
+static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int Cout, int transpose, cudaStream_t s,
+                       float **out) {
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  PackEntry *e = nullptr;
+  for (PackEntry *p : g_pack)
+    if (p->token == tag[0]) { e = p; break; }
+  if (!e) {
+    if (g_pack.size() >= 1024) {   // evict the least recently used half (weights of modules long gone)
+      std::sort(g_pack.begin(), g_pack.end(), [](PackEntry *a, PackEntry *b) { return a->last_use > b->last_use; });
+      for (size_t i = 512; i < g_pack.size(); ++i) {
+        cudaFree(g_pack[i]->wf);
+        delete g_pack[i];
+      }
+      g_pack.resize(512);
+    }
+    e = new PackEntry();
+    e->token = tag[0];
+    g_pack.push_back(e);
+  }
+  const size_t total = (size_t)K * Cin * Cout;
+  if (e->K != K || e->Cin != Cin || e->Cout != Cout) {
+    cudaFree(e->wf);
+    e->wf = nullptr;
+    SCN_CUDA(cudaMalloc((void **)&e->wf, 2 * total * sizeof(float)));
+    e->wb = e->wf + total;
+    e->K = K; e->Cin = Cin; e->Cout = Cout;
+    e->version = -1;
+  }
+  // the forward pass (transpose == 0) always repacks: in-place edits through `.data` do not move the
+  // version counter, and the forward weights must never be stale; the dX pass of the same step reuses
+  // what its forward packed
+  if (!transpose || e->version != tag[1] || e->stream != s) {
+    e->has_f = layout_ok(Cin, Cout);
+    e->has_b = layout_ok(Cout, Cin);
+    int pb = cdiv(2 * (long long)total, 256);
+    if (pb > num_sms() * 8) pb = num_sms() * 8;
+    k_pack_weights_both<<<pb, 256, 0, s>>>(W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    SCN_CUDA(cudaGetLastError());
+    e->version = tag[1];
+    e->stream = s;
+  }
+  e->last_use = ++g_pack_clock;
+  if (transpose ? !e->has_b : !e->has_f) return 1;
+  *out = transpose ? e->wb : e->wf;
+  return 0;
+}
+
 int g_gemm_grid_limit = 0;   // test knob (scn_set_gemm_grid_limit): force many work items per CTA
 
 static bool tf32_shape_ok(const float *X, const float *W, const float *bias, float *Y, int Kd, int N) {
@@ -483,18 +571,23 @@ static bool tf32_shape_ok(const float *X, const float *W, const float *bias, flo
 // [K][Kd][N]) or W[k]^T (transpose_w = 1, W is [K][N][Kd]).
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N, long long n_rows,
               const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
-              double prof_flops) {
+              double prof_flops, const int64_t *weight_tag) {
   using namespace tc;
   if (precision != SCN_PRECISION_TF32) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
   float *wp = nullptr;
-  if (workspace_t(&wp, WS_PACKED_W, (size_t)K * Kd * N, s)) return -1;
-  const long long total = (long long)K * Kd * N;
-  int pb = cdiv(total, 256);
-  if (pb > num_sms() * 8) pb = num_sms() * 8;
   const int cin = transpose_w ? N : Kd, cout = transpose_w ? Kd : N;
-  k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (weight_tag) {
+    const int r = cached_pack(weight_tag, W, K, cin, cout, transpose_w, s, &wp);
+    if (r) return r > 0 ? -1 : r;
+  } else {
+    if (workspace_t(&wp, WS_PACKED_W, (size_t)K * Kd * N, s)) return -1;
+    const long long total = (long long)K * Kd * N;
+    int pb = cdiv(total, 256);
+    if (pb > num_sms() * 8) pb = num_sms() * 8;
+    k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   // pipeline stages: what fits beside the metadata slots in ~215 KB
   const int stage_bytes = A_STAGE + NCORE * N * 16;
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);

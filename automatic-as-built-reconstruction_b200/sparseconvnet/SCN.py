@@ -246,7 +246,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     macs = c_double()
     check(lib.scn_submanifold_conv_forward(m._h, ss, fs, ptr(x), ptr(output_features), ptr(w),
                                            ptr(bias), cin, cout, _lib.precision(), stream(),
-                                           byref(macs)))
+                                           byref(macs), _lib.weight_tag(weight)))
     return macs.value
 
 
@@ -260,7 +260,7 @@ def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features
     d_input_features.resize_(x.size(0), cin)
     check(lib.scn_submanifold_conv_backward(m._h, ss, fs, ptr(x), ptr(d_input_features), ptr(dy),
                                             ptr(w), ptr(d_weight), ptr(d_bias), cin, cout,
-                                            _lib.precision(), stream()))
+                                            _lib.precision(), stream(), _lib.weight_tag(weight)))
 
 
 def _strided(fwd, prepare_in, prepare_out, in_size, out_size, filter_size, filter_stride, m, x,
@@ -276,7 +276,7 @@ def _strided(fwd, prepare_in, prepare_out, in_size, out_size, filter_size, filte
     output_features.resize_(n_new.value if n_out_of is prepare_out else m.getNActive(n_out_of), cout)
     macs = c_double()
     check(fwd(m._h, i_s, o_s, fs, st, ptr(x), ptr(output_features), ptr(w), ptr(bias), cin, cout,
-              _lib.precision(), stream(), byref(macs)))
+              _lib.precision(), stream(), byref(macs), _lib.weight_tag(weight)))
     return macs.value
 
 
@@ -302,7 +302,7 @@ def _strided_backward(bwd, in_size, out_size, filter_size, filter_stride, m, inp
     i_s, o_s, fs, st = _dims(in_size, out_size, filter_size, filter_stride)
     d_input_features.resize_(x.size(0), cin)
     check(bwd(m._h, i_s, o_s, fs, st, ptr(x), ptr(d_input_features), ptr(dy), ptr(w), ptr(d_weight),
-              ptr(d_bias), cin, cout, _lib.precision(), stream()))
+              ptr(d_bias), cin, cout, _lib.precision(), stream(), _lib.weight_tag(weight)))
 
 
 def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features,

@@ -69,10 +69,10 @@ _sig = {
     "scn_sparse_to_dense_rules_copy": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_void_p]),
     "scn_submanifold_conv_forward": (c_int, [c_void_p, I64P, I64P, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int64, c_int64, c_int, c_void_p,
-                                             POINTER(c_double)]),
+                                             POINTER(c_double), I64P]),
     "scn_submanifold_conv_backward": (c_int, [c_void_p, I64P, I64P, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
-                                              c_void_p]),
+                                              c_void_p, I64P]),
     "scn_nin_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                 c_int, c_void_p, POINTER(c_double)]),
     "scn_nin_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -97,10 +97,10 @@ _sig = {
 }
 for _name in ("scn_conv_forward", "scn_deconv_forward"):
     _sig[_name] = (c_int, [c_void_p, I64P, I64P, I64P, I64P, c_void_p, c_void_p, c_void_p, c_void_p,
-                           c_int64, c_int64, c_int, c_void_p, POINTER(c_double)])
+                           c_int64, c_int64, c_int, c_void_p, POINTER(c_double), I64P])
 for _name in ("scn_conv_backward", "scn_deconv_backward"):
     _sig[_name] = (c_int, [c_void_p, I64P, I64P, I64P, I64P, c_void_p, c_void_p, c_void_p, c_void_p,
-                           c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p])
+                           c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, I64P])
 
 EXPORTS = sorted(_sig)
 for _name, (_res, _args) in _sig.items():
@@ -125,6 +125,24 @@ def i64x3(t):
             t._scn_i64x3 = c
         return c
     return (c_int64 * 3)(int(t[0]), int(t[1]), int(t[2]))
+
+
+_next_token = [1]
+
+
+def weight_tag(w):
+    """{identity token, in-place version} of a weight tensor for the library's packed-operand cache.  The
+    token is minted once per tensor OBJECT (never reused, unlike data_ptr / id()); optimizers and
+    load_state_dict update parameters in place, which bumps `_version`."""
+    t = getattr(w, "_scn_token", None)
+    if t is None:
+        t = _next_token[0]
+        _next_token[0] += 1
+        try:
+            w._scn_token = t
+        except AttributeError:
+            return None
+    return (c_int64 * 2)(t, w._version)
 
 
 def stream():

@@ -142,37 +142,43 @@ int scn_sparse_to_dense_rules_copy(scn_metadata_t *m, const int64_t *spatial_siz
  * in [nIn,n_in_planes]; out [nOut,n_out_planes] (fully written: zero + bias + sum);
  * bias may be NULL.  *macs receives sum_k pairs_k*nIn*nOut like the reference's return.
  * backward: d_in fully written; d_weight [K,1,nIn,nOut] fully written (matmul_out
- * overwrites, CPU/Convolution.cpp:110); d_bias (may be NULL) = column sums of d_out. */
+ * overwrites, CPU/Convolution.cpp:110); d_bias (may be NULL) = column sums of d_out.
+ * weight_tag (may be NULL): {identity token of the weight tensor, its in-place version counter}.
+ * With a tag the tensor-core forward pass packs the weights' operand images for BOTH passes in one
+ * launch and the dX pass of the same version reuses them; without it every call packs its own. */
 int scn_submanifold_conv_forward(scn_metadata_t *m, const int64_t *spatial_size,
                                  const int64_t *filter_size, const float *in, float *out,
                                  const float *weight, const float *bias, int64_t n_in_planes,
-                                 int64_t n_out_planes, int precision, void *stream, double *macs);
+                                 int64_t n_out_planes, int precision, void *stream, double *macs,
+    const int64_t *weight_tag);
 int scn_submanifold_conv_backward(scn_metadata_t *m, const int64_t *spatial_size,
                                   const int64_t *filter_size, const float *in, float *d_in,
                                   const float *d_out, const float *weight, float *d_weight,
                                   float *d_bias, int64_t n_in_planes, int64_t n_out_planes,
-                                  int precision, void *stream);
+                                  int precision, void *stream, const int64_t *weight_tag);
 int scn_conv_forward(scn_metadata_t *m, const int64_t *in_spatial_size,
                      const int64_t *out_spatial_size, const int64_t *filter_size,
                      const int64_t *filter_stride, const float *in, float *out,
                      const float *weight, const float *bias, int64_t n_in_planes,
-                     int64_t n_out_planes, int precision, void *stream, double *macs);
+                     int64_t n_out_planes, int precision, void *stream, double *macs,
+    const int64_t *weight_tag);
 int scn_conv_backward(scn_metadata_t *m, const int64_t *in_spatial_size,
                       const int64_t *out_spatial_size, const int64_t *filter_size,
                       const int64_t *filter_stride, const float *in, float *d_in,
                       const float *d_out, const float *weight, float *d_weight, float *d_bias,
-                      int64_t n_in_planes, int64_t n_out_planes, int precision, void *stream);
+                      int64_t n_in_planes, int64_t n_out_planes, int precision, void *stream, const int64_t *weight_tag);
 /* in lives on the COARSE scale (in_spatial_size), out on the FINE scale (out_spatial_size) */
 int scn_deconv_forward(scn_metadata_t *m, const int64_t *in_spatial_size,
                        const int64_t *out_spatial_size, const int64_t *filter_size,
                        const int64_t *filter_stride, const float *in, float *out,
                        const float *weight, const float *bias, int64_t n_in_planes,
-                       int64_t n_out_planes, int precision, void *stream, double *macs);
+                       int64_t n_out_planes, int precision, void *stream, double *macs,
+    const int64_t *weight_tag);
 int scn_deconv_backward(scn_metadata_t *m, const int64_t *in_spatial_size,
                         const int64_t *out_spatial_size, const int64_t *filter_size,
                         const int64_t *filter_stride, const float *in, float *d_in,
                         const float *d_out, const float *weight, float *d_weight, float *d_bias,
-                        int64_t n_in_planes, int64_t n_out_planes, int precision, void *stream);
+                        int64_t n_in_planes, int64_t n_out_planes, int precision, void *stream, const int64_t *weight_tag);
 
 /* ---- NetworkInNetwork (replaces NetworkInNetwork_updateOutput / _updateGradInput /
  *      _accGradParameters, sparseconvnet.h:50-60, CPU/NetworkInNetwork.cpp:8-46) ------ */
