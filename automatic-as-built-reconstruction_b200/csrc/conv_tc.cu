@@ -136,19 +136,20 @@ __global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // the gather-GEMM kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int MS = 4;                        // tile-metadata slots (producers may run ~3 tiles ahead of the epilogue)
+constexpr int MS = 3;                        // tile-metadata slots (producers may run ~2 tiles ahead of the epilogue)
+constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) / B (weight slices)
 constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight loader, 4 epilogue, metadata loader
 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
   int a, b, meta, meta_bytes, bars, tmem_slot, total;
-  __host__ __device__ Smem(int N, int K, int ns) {
+  __host__ __device__ Smem(int N, int K, int nsa, int nsb) {
     a = 0;
-    b = a + ns * A_STAGE;
-    meta = b + ns * NCORE * N * 16;
+    b = a + nsa * A_STAGE;
+    meta = b + nsb * NCORE * N * 16;
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
     bars = meta + MS * meta_bytes;
-    tmem_slot = bars + (3 * ns + 2 * MS + 4) * 8;
+    tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4) * 8;
     total = tmem_slot + 16;
   }
 };
@@ -185,30 +186,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // current one and the write-back of the previous one overlap:
 //   warp 10      metadata loader: tile's gather lists / row permutation / offset list -> smem slot
 //   warps 0-3    A producers: 16-byte cp.async gathers of the partner rows (zero-fill), one commit group
-//                per step; the arrival for a step is posted NSTAGE-1 steps later, after
+//                per step; the arrival for a step is posted DEPTH steps later, after
 //                cp.async.wait_group + fence.proxy.async - a producer never waits for fresh data
 //   warp 5       weight loader: one cp.async.bulk (TMA) per step of the packed B slice
 //   warp 4       MMA issuer: tcgen05.mma.kind::tf32 into one of two TMEM accumulators
 //   warps 6-9    epilogue: tcgen05.ld -> (+bias) -> each stationary row written once
-// Rings: fullA/fullB/empty per smem stage, meta_full/meta_empty per metadata slot,
-// tmem_full/tmem_empty per accumulator.
-template <int NSTAGE>
+// Rings: fullA/emptyA per gathered-row stage (DEPTH+2 deep: the gathers are latency-bound, so what
+// counts is bytes in flight), fullB/emptyB per weight-slice stage (2-3 deep: bulk copies of L2-resident
+// weights), meta_full/meta_empty per metadata slot, tmem_full/tmem_empty per accumulator.
+template <int DEPTH>
 __global__ void __launch_bounds__(NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t acc_cols,
-              float *__restrict__ Ypart, int n_items, int splits) {
-  // a producer posts step g-DEPTH while issuing step g.  DEPTH steps of gathers cover the memory
-  // latency; the other NSTAGE-DEPTH stages are slack between the MMA warp and the producers - with
-  // DEPTH = NSTAGE-1 every MMA would wait for a full producer round trip after the previous one
-  constexpr int DEPTH = NSTAGE >= 6 ? NSTAGE - 2 : NSTAGE / 2;
+              float *__restrict__ Ypart, int n_items, int splits, int NSB) {
+  // a producer posts step g-DEPTH while issuing step g: DEPTH steps of gathers (16 KB each) are in
+  // flight per CTA; the 2 extra A stages are slack between the MMA warp and the producers (with none,
+  // every MMA would wait for a full producer round trip after the previous one)
+  constexpr int NSA = DEPTH + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Smem L(N, K, NSTAGE);
+  const Smem L(N, K, NSA, NSB);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_fullA = smem_u32(smem + L.bars);
-  const uint32_t bar_fullB = bar_fullA + NSTAGE * 8;
-  const uint32_t bar_empty = bar_fullB + NSTAGE * 8;
-  const uint32_t bar_mfull = bar_empty + NSTAGE * 8;
+  const uint32_t bar_emptyA = bar_fullA + NSA_MAX * 8;
+  const uint32_t bar_fullB = bar_emptyA + NSA_MAX * 8;
+  const uint32_t bar_emptyB = bar_fullB + NSB_MAX * 8;
+  const uint32_t bar_mfull = bar_emptyB + NSB_MAX * 8;
   const uint32_t bar_mempty = bar_mfull + MS * 8;
   const uint32_t bar_tfull = bar_mempty + MS * 8;
   const uint32_t bar_tempty = bar_tfull + 2 * 8;
@@ -227,10 +230,13 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   };
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) {
+    for (int i = 0; i < NSA; ++i) {
       mbar_init(bar_fullA + i * 8, 128);
+      mbar_init(bar_emptyA + i * 8, 1);
+    }
+    for (int i = 0; i < NSB; ++i) {
       mbar_init(bar_fullB + i * 8, 1);
-      mbar_init(bar_empty + i * 8, 1);
+      mbar_init(bar_emptyB + i * 8, 1);
     }
     for (int i = 0; i < MS; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
@@ -287,7 +293,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     auto flush = [&]() {                     // post everything issued so far
       cp_async_wait<0>();
       fence_proxy_async();
-      for (; arrived < g; ++arrived) mbar_arrive(bar_fullA + (arrived % NSTAGE) * 8);
+      for (; arrived < g; ++arrived) mbar_arrive(bar_fullA + (arrived % NSA) * 8);
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int slot = it % MS;
@@ -301,8 +307,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       const int split = item / n_tiles;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
       for (int lst = 0; lst < steps; ++lst, ++g) {
-        const int stage = g % NSTAGE, use = g / NSTAGE;
-        if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+        const int stage = g % NSA, use = g / NSA;
+        if (use > 0) mbar_wait(bar_emptyA + stage * 8, (use - 1) & 1);
         const int st = split + lst * splits;
         const int e = st / kchunks, c = st - e * kchunks;
         {
@@ -320,7 +326,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         if (g - arrived >= DEPTH) {
           cp_async_wait<DEPTH>();             // this thread's gathers of steps <= g-DEPTH have landed
           fence_proxy_async();                // generic-proxy writes -> visible to the tensor core
-          for (; arrived <= g - DEPTH; ++arrived) mbar_arrive(bar_fullA + (arrived % NSTAGE) * 8);
+          for (; arrived <= g - DEPTH; ++arrived) mbar_arrive(bar_fullA + (arrived % NSA) * 8);
         }
       }
       __syncwarp();                           // the tile's lists are no longer needed by this warp
@@ -344,16 +350,18 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
         for (int lst = 0; lst < steps; ++lst, ++g) {
-          const int stage = g % NSTAGE, use = g / NSTAGE;
-          mbar_wait(bar_fullB + stage * 8, use & 1);
+          const int stage = g % NSA, use = g / NSA;
+          const int stb = g % NSB, useb = g / NSB;
+          mbar_wait(bar_fullB + stb * 8, useb & 1);
           mbar_wait(bar_fullA + stage * 8, use & 1);
           tc_fence_after();
-          const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stage * B_STAGE;
+          const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
 #pragma unroll
           for (int kk = 0; kk < KC / 8; ++kk)   // K = 8 per instruction: 32 bytes further along the 128-byte rows
             mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
                      (lst > 0 || kk > 0) ? 1u : 0u);
-          tc_commit(bar_empty + stage * 8);
+          tc_commit(bar_emptyA + stage * 8);
+          tc_commit(bar_emptyB + stb * 8);
         }
         tc_commit(bar_tfull + acc * 8);
         ++accn;
@@ -370,8 +378,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         const int8_t *sK = reinterpret_cast<const int8_t *>(meta_hdr(slot) + 2);
         for (int lst = 0; lst < steps; ++lst, ++g) {
-          const int stage = g % NSTAGE, use = g / NSTAGE;
-          if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+          const int stage = g % NSB, use = g / NSB;
+          if (use > 0) mbar_wait(bar_emptyB + stage * 8, (use - 1) & 1);
           const int st = split + lst * splits;
           const int e = st / kchunks, c = st - e * kchunks;
           const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
@@ -588,15 +596,18 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  // pipeline stages: what fits beside the metadata slots in ~215 KB
-  const int stage_bytes = A_STAGE + NCORE * N * 16;
+  // ring depths: 2-3 weight-slice stages, then as many gathered-row stages as fit beside the metadata
+  // slots in ~218 KB (the gathers are latency-bound: depth = bytes in flight)
+  const int b_stage = NCORE * N * 16;
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
-  int ns = (215 * 1024 - meta_total) / stage_bytes;
-  ns = ns >= 6 ? 6 : (ns >= 4 ? 4 : 3);
-  const Smem L(N, K, ns);
+  const int nsb = b_stage > 16384 ? 2 : 3;
+  const int nsa_fit = (218 * 1024 - meta_total - nsb * b_stage) / A_STAGE;
+  const int depth = nsa_fit >= 8 ? 6 : (nsa_fit >= 6 ? 4 : (nsa_fit >= 4 ? 2 : 1));
+  const Smem L(N, K, depth + 2, nsb);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_osgemm_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_osgemm_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_osgemm_tf32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_osgemm_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_osgemm_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -624,9 +635,10 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
   prof_begin(PROF_GEMM, s);
-  if (ns == 3) k_osgemm_tf32<3><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
-  else if (ns == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
-  else k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits);
+  if (depth == 6) k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
+  else if (depth == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
+  else if (depth == 2) k_osgemm_tf32<2><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
+  else k_osgemm_tf32<1><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
   prof_end(PROF_GEMM, s, prof_bytes, prof_flops);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
