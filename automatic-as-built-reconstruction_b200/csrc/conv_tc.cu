@@ -38,6 +38,11 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, int s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// arrive on `bar` once all cp.async issued so far by this thread have landed (pending count +1 now, -1
+// then: pair it with a plain mbar_arrive, as cutlass::PipelineAsync's cp.async producers do)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -185,9 +190,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // roles run decoupled through mbarrier rings, so the gathers of the next tiles, the MMAs of the
 // current one and the write-back of the previous one overlap:
 //   warp 10      metadata loader: tile's gather lists / row permutation / offset list -> smem slot
-//   warps 0-3    A producers: 16-byte cp.async gathers of the partner rows (zero-fill), one commit group
-//                per step; the arrival for a step is posted DEPTH steps later, after
-//                cp.async.wait_group + fence.proxy.async - a producer never waits for fresh data
+//   warps 0-3    A producers: 16-byte cp.async gathers of the partner rows (zero-fill) followed by
+//                cp.async.mbarrier.arrive: the stage's barrier completes when the copies have landed,
+//                the producer never waits for them and runs up to DEPTH+2 steps ahead of the MMA
 //   warp 5       weight loader: one cp.async.bulk (TMA) per step of the packed B slice
 //   warp 4       MMA issuer: tcgen05.mma.kind::tf32 into one of two TMEM accumulators
 //   warps 6-9    epilogue: tcgen05.ld -> (+bias) -> each stationary row written once
@@ -199,9 +204,7 @@ __global__ void __launch_bounds__(NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t acc_cols,
               float *__restrict__ Ypart, int n_items, int splits, int NSB) {
-  // a producer posts step g-DEPTH while issuing step g: DEPTH steps of gathers (16 KB each) are in
-  // flight per CTA; the 2 extra A stages are slack between the MMA warp and the producers (with none,
-  // every MMA would wait for a full producer round trip after the previous one)
+  // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L(N, K, NSA, NSB);
@@ -289,20 +292,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
     const int j = tid & 7, r0 = tid >> 3;
     int g = 0, it = 0;                       // global step / item counters of this CTA
-    int arrived = 0;                         // steps this thread has posted on fullA
-    auto flush = [&]() {                     // post everything issued so far
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (; arrived < g; ++arrived) mbar_arrive(bar_fullA + (arrived % NSA) * 8);
-    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int slot = it % MS;
-      // never block with arrivals pending: the metadata slot may only be recycled once the items
-      // whose last steps are still unposted here have drained (deadlock with 1-step items otherwise)
-      if (!mbar_test(bar_mfull + slot * 8, (it / MS) & 1)) {
-        flush();
-        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
-      }
+      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
       const int split = item / n_tiles;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
@@ -322,17 +314,14 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
             cp_async_16(dst + i * 2048, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
           }
         }
-        cp_async_commit();
-        if (g - arrived >= DEPTH) {
-          cp_async_wait<DEPTH>();             // this thread's gathers of steps <= g-DEPTH have landed
-          fence_proxy_async();                // generic-proxy writes -> visible to the tensor core
-          for (; arrived <= g - DEPTH; ++arrived) mbar_arrive(bar_fullA + (arrived % NSA) * 8);
-        }
+        // the stage's barrier completes when every producer thread has passed here AND its copies have
+        // landed - the thread itself never waits for them
+        cp_async_mbar_arrive(bar_fullA + stage * 8);
+        mbar_arrive(bar_fullA + stage * 8);
       }
       __syncwarp();                           // the tile's lists are no longer needed by this warp
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
     }
-    flush();
   } else if (warp == 4) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -695,7 +684,6 @@ __global__ void __launch_bounds__(NT_DW)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
           long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
-  constexpr int DEPTH = NSTAGE >= 6 ? NSTAGE - 2 : NSTAGE / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
   const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)
@@ -788,7 +776,6 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     const int j8 = tid & 7, p4 = (tid >> 3) & 3;
     // byte offset of this thread's 16-byte piece inside an atom: row p4, 32B chunk (j8/2)^p4, half j8&1
     const uint32_t piece = p4 * 128 + ((((uint32_t)j8 >> 1) ^ (uint32_t)p4) << 5) + (j8 & 1) * 16;
-    int arrived = 0;
     for (int st = 0; st < steps; ++st) {
       const int stage = st % NSTAGE, use = st / NSTAGE;
       const int slot = st % DW_NPS;
@@ -808,18 +795,11 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
         const int yi = ycol ? pr.y : pr.x;
         cp_async_16(sb + ka * sbo_b + ni * 512, dY + (long long)(yi < 0 ? 0 : yi) * Cout + ni * 32 + j8 * 4, yi < 0 ? 0 : 16);
       }
-      cp_async_commit();
+      cp_async_mbar_arrive(bar_full + stage * 8);   // completes when this thread's copies have landed
+      mbar_arrive(bar_full + stage * 8);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pempty + slot * 8);
-      if (st - arrived >= DEPTH) {
-        cp_async_wait<DEPTH>();
-        fence_proxy_async();
-        for (; arrived <= st - DEPTH; ++arrived) mbar_arrive(bar_full + (arrived % NSTAGE) * 8);
-      }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (; arrived < steps; ++arrived) mbar_arrive(bar_full + (arrived % NSTAGE) * 8);
   } else if (warp == 4) {
     // ===== MMA issuer =====
     if (lane == 0) {
