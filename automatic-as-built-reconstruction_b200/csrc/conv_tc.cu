@@ -147,11 +147,12 @@ constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight 
 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
-  int a, b, meta, meta_bytes, bars, tmem_slot, total;
+  int a, b, stage, meta, meta_bytes, bars, tmem_slot, total;
   __host__ __device__ Smem(int N, int K, int nsa, int nsb) {
     a = 0;
     b = a + nsa * A_STAGE;
-    meta = b + nsb * NCORE * N * 16;
+    stage = b + nsb * NCORE * N * 16;       // 4 epilogue warps x 4 KB transpose tiles
+    meta = stage + 4 * 4096;
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
     bars = meta + MS * meta_bytes;
     tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4) * 8;
@@ -303,6 +304,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         if (use > 0) mbar_wait(bar_emptyA + stage * 8, (use - 1) & 1);
         const int st = split + lst * splits;
         const int e = st / kchunks, c = st - e * kchunks;
+#ifdef SCN_EXPERIMENT_NO_A          // timing experiment only (wrong results): what if the gathers were free?
+        if (use == 0)
+#endif
         {
           // row r lives at (r/8)*1024 + (r%8)*128, its piece j at chunk j ^ (r%8): the 8 lanes of a row
           // fill one 128-byte line of shared memory - no bank conflicts, no padding
@@ -373,6 +377,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const int e = st / kchunks, c = st - e * kchunks;
           const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
           const uint32_t bytes = (uint32_t)B_STAGE;
+#ifdef SCN_EXPERIMENT_NO_B          // timing experiment only (wrong results): what if weight slices were free?
+          if (use > 0) { mbar_arrive(bar_fullB + stage * 8); continue; }
+#endif
           mbar_expect_tx(bar_fullB + stage * 8, bytes);
           bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
                         bar_fullB + stage * 8);
@@ -428,19 +435,43 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        if (orow >= 0) {
-          const int nc = min(32, N - c0);
+        if (N - c0 >= 32) {
+          // Transpose through this warp's 4 KB staging tile so that a store instruction covers whole
+          // 128-byte row segments (8 lanes x 16 B per row, 4 rows per instruction).  Writing the
+          // registers out directly (thread = row) issues 32 x 16 B requests to 32 different lines per
+          // instruction - measured: the kernel was epilogue-bound on exactly that.
+          float4 *st = reinterpret_cast<float4 *>(smem + L.stage + q * 4096);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            if (i < nc) {
-              float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                     __uint_as_float(v[i + 3]));
-              if (bs) {
-                const float4 b4 = *reinterpret_cast<const float4 *>(bs + c0 + i);
-                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-              }
-              *reinterpret_cast<float4 *>(yp + c0 + i) = o;
+          for (int jc = 0; jc < 8; ++jc)      // row `lane`, chunk jc -> slot jc ^ (lane & 7): conflict-free
+            st[lane * 8 + (jc ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * jc]), __uint_as_float(v[4 * jc + 1]),
+                                                           __uint_as_float(v[4 * jc + 2]), __uint_as_float(v[4 * jc + 3]));
+          __syncwarp();
+          const int jc = lane & 7;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bs) b4 = *reinterpret_cast<const float4 *>(bs + c0 + 4 * jc);
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int r = itr * 4 + (lane >> 3);
+            const int dst_row = __shfl_sync(0xffffffffu, orow, r);
+            float4 o = st[r * 8 + (jc ^ (r & 7))];
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (dst_row >= 0) {
+              float *p = splits > 1 ? Ypart + (((long long)split * n_tiles + tile) * TILE_M + q * 32 + r) * N
+                                    : Y + (long long)dst_row * N;
+              *reinterpret_cast<float4 *>(p + c0 + 4 * jc) = o;
             }
+          }
+          __syncwarp();
+        } else if (orow >= 0) {             // 16-column tail (N = 16 mod 32): thread = row
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                   __uint_as_float(v[i + 3]));
+            if (bs) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(bs + c0 + i);
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            *reinterpret_cast<float4 *>(yp + c0 + i) = o;
           }
         }
       }
@@ -590,7 +621,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int b_stage = NCORE * N * 16;
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
   const int nsb = b_stage > 16384 ? 2 : 3;
-  const int nsa_fit = (218 * 1024 - meta_total - nsb * b_stage) / A_STAGE;
+  const int nsa_fit = (218 * 1024 - meta_total - 4 * 4096 - nsb * b_stage) / A_STAGE;
   const int depth = nsa_fit >= 8 ? 6 : (nsa_fit >= 6 ? 4 : (nsa_fit >= 4 ? 2 : 1));
   const Smem L(N, K, depth + 2, nsb);
   static bool attr_set = false;

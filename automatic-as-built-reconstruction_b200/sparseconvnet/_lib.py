@@ -11,7 +11,7 @@ from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int6
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libscn_b200.so")
+LIB_PATH = os.environ.get("SCN_B200_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libscn_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
