@@ -119,43 +119,27 @@ __device__ __forceinline__ float to_tf32(float x) {
 // chunks are XOR-ed with n%8.  transpose=0: reduction dim = Cin, n = Cout (forward);
 // transpose=1: reduction dim = Cout, n = Cin (dX = dY @ W[k]^T).  Values are rounded to tf32.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pack_weights(const float *__restrict__ W, float *__restrict__ Wp, int K, int Cin, int Cout,
-                               int transpose) {
-  const int Kd = transpose ? Cout : Cin, N = transpose ? Cin : Cout;
-  const long long per_k = (long long)Kd * N;
-  const long long total = (long long)K * per_k;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i / per_k);
-    long long r = i - (long long)k * per_k;
-    // destination order inside offset k: chunk c, row n, 32 floats (swizzled)
-    const int c = (int)(r / ((long long)KC * N));
-    r -= (long long)c * KC * N;
-    const int n = (int)(r >> 5), pos = (int)(r & 31);
-    const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
-    const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
-    Wp[i] = to_tf32(v);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // the gather-GEMM kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int MS = 3;                        // tile-metadata slots (producers may run ~2 tiles ahead of the epilogue)
 constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) / B (weight slices)
 constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight loader, 4 epilogue, metadata loader
+constexpr int NT_P3 = 480;                   // 3xTF32 mode: + 4 converter warps (low-order halves of the gathered rows)
+constexpr int NLO = 2;                       // stages of low-order halves (3xTF32 mode)
 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
-  int a, b, stage, meta, meta_bytes, bars, tmem_slot, total;
-  __host__ __device__ Smem(int N, int K, int nsa, int nsb) {
+  int a, alo, b, stage, meta, meta_bytes, bars, tmem_slot, total;
+  __host__ __device__ Smem(int N, int K, int nsa, int nsb, int x3) {
     a = 0;
-    b = a + nsa * A_STAGE;
-    stage = b + nsb * NCORE * N * 16;       // 4 epilogue warps x 4 KB transpose tiles
-    meta = stage + 4 * 4096;
+    alo = a + nsa * A_STAGE;                // 3xTF32: NLO stages of low-order halves
+    b = alo + (x3 ? NLO * A_STAGE : 0);
+    stage = b + nsb * NCORE * N * 16 * (x3 ? 2 : 1);    // 3xTF32: a weight stage = hi slice + lo slice
+    meta = stage + 4 * 4096;                // 4 epilogue warps x 4 KB transpose tiles
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
     bars = meta + MS * meta_bytes;
-    tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4) * 8;
+    tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4 + 2 * NLO) * 8;
     total = tmem_slot + 16;
   }
 };
@@ -200,15 +184,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // Rings: fullA/emptyA per gathered-row stage (DEPTH+2 deep: the gathers are latency-bound, so what
 // counts is bytes in flight), fullB/emptyB per weight-slice stage (2-3 deep: bulk copies of L2-resident
 // weights), meta_full/meta_empty per metadata slot, tmem_full/tmem_empty per accumulator.
-template <int DEPTH>
-__global__ void __launch_bounds__(NT_P, 1)
+//
+// X3 (3xTF32, the library's fp32 mode): x = hi + lo with hi = the 19 bits kind::tf32 reads, lo = x - hi
+// (exact), w = whi + wlo (both rounded to tf32 when packed); Y += hi*whi + lo*whi + hi*wlo - the
+// dropped lo*wlo term is 2^-20 relative.  Warps 11-14 (converters) compute lo from every landed
+// stage into a 2-stage side ring; the MMA warp issues three instructions per K = 8 slice.  N is the
+// column width of a work item (<= 128 in X3 mode: wider outputs are split over work items), ldn the
+// row stride of Y.
+template <int DEPTH, bool X3>
+__global__ void __launch_bounds__(X3 ? NT_P3 : NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
-              float *__restrict__ Y, int Kd, int N, int K, long long n_rows, TileView tb, uint32_t acc_cols,
+              float *__restrict__ Y, int Kd, int N, int ldn, int K, long long n_rows, TileView tb, uint32_t acc_cols,
               float *__restrict__ Ypart, int n_items, int splits, int NSB) {
   // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Smem L(N, K, NSA, NSB);
+  const Smem L(N, K, NSA, NSB, X3 ? 1 : 0);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_fullA = smem_u32(smem + L.bars);
@@ -219,7 +210,12 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   const uint32_t bar_mempty = bar_mfull + MS * 8;
   const uint32_t bar_tfull = bar_mempty + MS * 8;
   const uint32_t bar_tempty = bar_tfull + 2 * 8;
-  const int B_STAGE = NCORE * N * 16;
+  const uint32_t bar_fullL = bar_tempty + 2 * 8;
+  const uint32_t bar_emptyL = bar_fullL + NLO * 8;
+  const uint32_t alo_base = smem_u32(smem + L.alo);
+  const int B_SLICE = NCORE * N * 16;               // one packed weight slice (hi or lo)
+  const int B_STAGE = X3 ? 2 * B_SLICE : B_SLICE;
+  const int item_stride = tb.n_tiles * splits;      // work items per column block
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = tb.n_tiles;
   const int kchunks = Kd / KC;
@@ -229,7 +225,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   auto meta_hdr = [&](int slot) { return reinterpret_cast<int32_t *>(smem + L.meta + slot * L.meta_bytes + (K + 1) * TILE_M * 4); };
   // steps of work item `item` given the tile's entry count
   auto item_steps = [&](int item, int nE) {
-    const int split = item / n_tiles, all_steps = nE * kchunks;
+    const int split = (item % item_stride) / n_tiles, all_steps = nE * kchunks;
     return all_steps > split ? (all_steps - split + splits - 1) / splits : 0;
   };
 
@@ -244,8 +240,13 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     }
     for (int i = 0; i < MS; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
-      mbar_init(bar_mempty + i * 8, 10);     // 4 producer warps + 4 epilogue warps + MMA + weight loader
+      mbar_init(bar_mempty + i * 8, X3 ? 14 : 10);   // 4 producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
     }
+    if (X3)
+      for (int i = 0; i < NLO; ++i) {
+        mbar_init(bar_fullL + i * 8, 128);
+        mbar_init(bar_emptyL + i * 8, 1);
+      }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
       mbar_init(bar_tempty + i * 8, 4);      // 4 epilogue warps
@@ -297,7 +298,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       const int slot = it % MS;
       mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
-      const int split = item / n_tiles;
+      const int split = (item % item_stride) / n_tiles;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
       for (int lst = 0; lst < steps; ++lst, ++g) {
         const int stage = g % NSA, use = g / NSA;
@@ -334,7 +335,6 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int slot = it % MS;
         mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
-        const int split = item / n_tiles;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         mbar_arrive(bar_mempty + slot * 8);
         if (steps == 0) continue;
@@ -347,14 +347,23 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const int stb = g % NSB, useb = g / NSB;
           mbar_wait(bar_fullB + stb * 8, useb & 1);
           mbar_wait(bar_fullA + stage * 8, use & 1);
+          const int stl = g % NLO;
+          if (X3) mbar_wait(bar_fullL + stl * 8, (g / NLO) & 1);
           tc_fence_after();
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
+          const uint32_t sl = alo_base + stl * A_STAGE;
 #pragma unroll
-          for (int kk = 0; kk < KC / 8; ++kk)   // K = 8 per instruction: 32 bytes further along the 128-byte rows
+          for (int kk = 0; kk < KC / 8; ++kk) { // K = 8 per instruction: 32 bytes further along the 128-byte rows
             mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
                      (lst > 0 || kk > 0) ? 1u : 0u);
+            if (X3) {
+              mma_tf32(tmem_d, make_desc_sw128(sl + kk * 32), make_desc_sw128(sb + kk * 32), idesc, 1u);
+              mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + B_SLICE + kk * 32), idesc, 1u);
+            }
+          }
           tc_commit(bar_emptyA + stage * 8);
           tc_commit(bar_emptyB + stb * 8);
+          if (X3) tc_commit(bar_emptyL + stl * 8);
         }
         tc_commit(bar_tfull + acc * 8);
         ++accn;
@@ -367,7 +376,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int slot = it % MS;
         mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
-        const int split = item / n_tiles;
+        const int split = (item % item_stride) / n_tiles, col0 = (item / item_stride) * N;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         const int8_t *sK = reinterpret_cast<const int8_t *>(meta_hdr(slot) + 2);
         for (int lst = 0; lst < steps; ++lst, ++g) {
@@ -381,10 +390,50 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (use > 0) { mbar_arrive(bar_fullB + stage * 8); continue; }
 #endif
           mbar_expect_tx(bar_fullB + stage * 8, bytes);
-          bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
-                        bar_fullB + stage * 8);
+          if (X3) {   // slices [k][c][hi|lo][ldn][32]: rows col0 .. col0+N of the hi and of the lo slice
+            const float *src = Wp + (((long long)kw * kchunks + c) * 2 * ldn + col0) * KC;
+            bulk_copy_g2s(b_base + stage * B_STAGE, src, (uint32_t)B_SLICE, bar_fullB + stage * 8);
+            bulk_copy_g2s(b_base + stage * B_STAGE + B_SLICE, src + (long long)ldn * KC, (uint32_t)B_SLICE,
+                          bar_fullB + stage * 8);
+          } else {
+            bulk_copy_g2s(b_base + stage * B_STAGE, Wp + ((long long)kw * Kd + (long long)c * KC) * N, bytes,
+                          bar_fullB + stage * 8);
+          }
         }
         mbar_arrive(bar_mempty + slot * 8);
+      }
+    }
+  } else if (warp >= 11) {
+    // ===== converters (3xTF32 only): lo = x - (x & ~0x1fff) of every landed stage, same swizzled
+    // positions, into the low-order ring; generic-proxy writes are fenced for the tensor core =====
+    if (X3) {
+      const int ct = tid - 11 * 32;
+      int g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int slot = it % MS;
+        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int steps = item_steps(item, meta_hdr(slot)[0]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
+        for (int lst = 0; lst < steps; ++lst, ++g) {
+          const int stage = g % NSA, stl = g % NLO;
+          mbar_wait(bar_fullA + stage * 8, (g / NSA) & 1);
+          if (g >= NLO) mbar_wait(bar_emptyL + stl * 8, ((g / NLO) - 1) & 1);
+          const float4 *src = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE);
+          float4 *dst = reinterpret_cast<float4 *>(smem + L.alo + stl * A_STAGE);
+#pragma unroll
+          for (int u = 0; u < A_STAGE / 16 / 128; ++u) {
+            const float4 v = src[ct + u * 128];
+            float4 o;
+            o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            dst[ct + u * 128] = o;
+          }
+          fence_proxy_async();
+          mbar_arrive(bar_fullL + stl * 8);
+        }
       }
     }
   } else {
@@ -395,17 +444,17 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int slot = it % MS;
       mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
-      const int tile = item % n_tiles, split = item / n_tiles;
+      const int tile = item % n_tiles, split = (item % item_stride) / n_tiles, col0 = (item / item_stride) * N;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
       int orow = meta_perm(slot)[row];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
-      const float *bs = bias;
-      float *yp = Y + (long long)(orow < 0 ? 0 : orow) * N;
+      const float *bs = bias ? bias + col0 : nullptr;
+      float *yp = Y + (long long)(orow < 0 ? 0 : orow) * ldn + col0;
       if (splits > 1) {                     // partial tile, slot order, no bias
         orow = 0;
         bs = nullptr;
-        yp = Ypart + (((long long)split * n_tiles + tile) * TILE_M + row) * N;
+        yp = Ypart + (((long long)split * n_tiles + tile) * TILE_M + row) * ldn + col0;
       }
       const int acc = accn & 1;
       if (steps > 0) {
@@ -456,9 +505,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
             float4 o = st[r * 8 + (jc ^ (r & 7))];
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             if (dst_row >= 0) {
-              float *p = splits > 1 ? Ypart + (((long long)split * n_tiles + tile) * TILE_M + q * 32 + r) * N
-                                    : Y + (long long)dst_row * N;
-              *reinterpret_cast<float4 *>(p + c0 + 4 * jc) = o;
+              float *p = splits > 1 ? Ypart + (((long long)split * n_tiles + tile) * TILE_M + q * 32 + r) * ldn
+                                    : Y + (long long)dst_row * ldn;
+              *reinterpret_cast<float4 *>(p + col0 + c0 + 4 * jc) = o;
             }
           }
           __syncwarp();
@@ -501,9 +550,11 @@ __global__ void k_splitk_reduce(const float *__restrict__ Ypart, const float *__
   *reinterpret_cast<float4 *>(Y + orow * N + c) = a;
 }
 
-// both operand images of a weight tensor in one launch: [0,total) forward layout, [total,2 total) dX layout
+// both operand images of a weight tensor in one launch: [0,total) forward layout, [total,2 total) dX layout.
+// x3 = 1 (3xTF32 mode): every (k, chunk) slice is stored twice, [k][c][hi|lo][n][32] with
+// hi = tf32(w), lo = tf32(w - hi); an image then holds 2 total floats.
 __global__ void k_pack_weights_both(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wb,
-                                    int K, int Cin, int Cout, int do_f, int do_b) {
+                                    int K, int Cin, int Cout, int do_f, int do_b, int x3) {
   const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
   for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
        i2 += (long long)gridDim.x * blockDim.x) {
@@ -518,14 +569,23 @@ __global__ void k_pack_weights_both(const float *__restrict__ W, float *__restri
     const int n = (int)(r >> 5), pos = (int)(r & 31);
     const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
     const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
-    (transpose ? Wb : Wf)[i] = to_tf32(v);
+    const float hi = to_tf32(v);
+    float *dst = transpose ? Wb : Wf;
+    if (x3) {
+      const long long slice = (long long)KC * N;                 // floats of one (k, chunk) slice
+      const long long base = (i - r) * 2;                        // slices before this one, doubled
+      dst[base + r] = hi;
+      dst[base + slice + r] = to_tf32(v - hi);
+    } else {
+      dst[i] = hi;
+    }
   }
 }
 
 // Packed-operand cache, keyed by the caller's identity token of the weight tensor.
 struct PackEntry {
   int64_t token = 0, version = -1;
-  int K = 0, Cin = 0, Cout = 0;
+  int K = 0, Cin = 0, Cout = 0, x3 = 0;
   bool has_f = false, has_b = false;
   cudaStream_t stream = 0;
   float *wf = nullptr, *wb = nullptr;
@@ -538,8 +598,8 @@ static uint64_t g_pack_clock = 0;
 static bool layout_ok(int Kd, int N) { return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256; }
 
 // returns the packed image for (transpose ? dX : forward), (re)building both when the version moved
-static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int Cout, int transpose, cudaStream_t s,
-                       float **out) {
+static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int Cout, int transpose, int x3,
+                       cudaStream_t s, float **out) {
   std::lock_guard<std::mutex> lk(g_pack_mu);
   PackEntry *e = nullptr;
   for (PackEntry *p : g_pack)
@@ -558,12 +618,13 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     g_pack.push_back(e);
   }
   const size_t total = (size_t)K * Cin * Cout;
-  if (e->K != K || e->Cin != Cin || e->Cout != Cout) {
+  const size_t image = total * (x3 ? 2 : 1);         // 3xTF32: hi and lo slices
+  if (e->K != K || e->Cin != Cin || e->Cout != Cout || e->x3 != x3) {
     cudaFree(e->wf);
     e->wf = nullptr;
-    SCN_CUDA(cudaMalloc((void **)&e->wf, 2 * total * sizeof(float)));
-    e->wb = e->wf + total;
-    e->K = K; e->Cin = Cin; e->Cout = Cout;
+    SCN_CUDA(cudaMalloc((void **)&e->wf, 2 * image * sizeof(float)));
+    e->wb = e->wf + image;
+    e->K = K; e->Cin = Cin; e->Cout = Cout; e->x3 = x3;
     e->version = -1;
   }
   // the forward pass (transpose == 0) always repacks: in-place edits through `.data` do not move the
@@ -574,7 +635,7 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     e->has_b = layout_ok(Cout, Cin);
     int pb = cdiv(2 * (long long)total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
-    k_pack_weights_both<<<pb, 256, 0, s>>>(W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b);
+    k_pack_weights_both<<<pb, 256, 0, s>>>(W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SCN_CUDA(cudaGetLastError());
     e->version = tag[1];
@@ -601,48 +662,60 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
               const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
               double prof_flops, const int64_t *weight_tag) {
   using namespace tc;
-  if (precision != SCN_PRECISION_TF32) return 1;
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
+  const int x3 = precision == SCN_PRECISION_FP32_3XTF32;
+  // 3xTF32: a work item covers <= 128 output columns (its weight stage holds a hi and a lo slice)
+  const int ncb = (x3 && N > 128) ? N / 128 : 1;
+  const int NW = N / ncb;
+  if (NW * ncb != N || NW % 16) return 1;
   float *wp = nullptr;
   const int cin = transpose_w ? N : Kd, cout = transpose_w ? Kd : N;
   if (weight_tag) {
-    const int r = cached_pack(weight_tag, W, K, cin, cout, transpose_w, s, &wp);
+    const int r = cached_pack(weight_tag, W, K, cin, cout, transpose_w, x3, s, &wp);
     if (r) return r > 0 ? -1 : r;
   } else {
-    if (workspace_t(&wp, WS_PACKED_W, (size_t)K * Kd * N, s)) return -1;
     const long long total = (long long)K * Kd * N;
-    int pb = cdiv(total, 256);
+    if (workspace_t(&wp, WS_PACKED_W, (size_t)total * (x3 ? 2 : 1), s)) return -1;
+    int pb = cdiv(2 * total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
-    k_pack_weights<<<pb, 256, 0, s>>>(W, wp, K, cin, cout, transpose_w);
+    k_pack_weights_both<<<pb, 256, 0, s>>>(W, wp, wp, K, cin, cout, !transpose_w, transpose_w, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   // ring depths: 2-3 weight-slice stages, then as many gathered-row stages as fit beside the metadata
-  // slots in ~218 KB (the gathers are latency-bound: depth = bytes in flight)
-  const int b_stage = NCORE * N * 16;
+  // slots (the gathers are latency-bound: depth = bytes in flight)
+  const int b_stage = NCORE * NW * 16 * (x3 ? 2 : 1);
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
   const int nsb = b_stage > 16384 ? 2 : 3;
-  const int nsa_fit = (218 * 1024 - meta_total - 4 * 4096 - nsb * b_stage) / A_STAGE;
+  const int budget = x3 ? 226 * 1024 : 218 * 1024;
+  const int nsa_fit = (budget - meta_total - 4 * 4096 - nsb * b_stage - (x3 ? NLO * A_STAGE : 0)) / A_STAGE;
   const int depth = nsa_fit >= 8 ? 6 : (nsa_fit >= 6 ? 4 : (nsa_fit >= 4 ? 2 : 1));
-  const Smem L(N, K, depth + 2, nsb);
+  if (nsa_fit < 3) return 1;
+  const Smem L(NW, K, depth + 2, nsb, x3);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_osgemm_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_osgemm_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaError_t ae = cudaSuccess;
+    auto setattr = [&](const void *f) {
+      if (ae == cudaSuccess) ae = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    };
+    setattr((const void *)k_osgemm_tf32<1, false>); setattr((const void *)k_osgemm_tf32<2, false>);
+    setattr((const void *)k_osgemm_tf32<4, false>); setattr((const void *)k_osgemm_tf32<6, false>);
+    setattr((const void *)k_osgemm_tf32<1, true>);  setattr((const void *)k_osgemm_tf32<2, true>);
+    setattr((const void *)k_osgemm_tf32<4, true>);  setattr((const void *)k_osgemm_tf32<6, true>);
+    if (ae != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(ae));
       return -1;
     }
     attr_set = true;
   }
   uint32_t cols = 32;
-  while ((int)cols < N) cols <<= 1;
+  while ((int)cols < NW) cols <<= 1;
   // small grids leave most SMs idle while one CTA walks K * Kd/32 latency-bound steps: split the
   // steps over up to 32 work items per tile (each keeps >= 4 steps even for one active offset)
   int splits = 1;
   const int kchunks = (Kd + KC - 1) / KC;
-  if (tv.n_tiles * 2 <= num_sms() && !tv.identity) {
-    splits = num_sms() / tv.n_tiles;
+  if (tv.n_tiles * ncb * 2 <= num_sms() && !tv.identity) {
+    splits = num_sms() / (tv.n_tiles * ncb);
     const int max_split = (K * kchunks + 3) / 4;
     if (splits > max_split) splits = max_split;
     if (splits > 32) splits = 32;
@@ -651,14 +724,25 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   float *ypart = nullptr;
   const long long n_slots = (long long)tv.n_tiles * TILE_M;
   if (splits > 1 && workspace_t(&ypart, WS_SPLITK, (size_t)splits * n_slots * N, s)) return -1;
-  const int n_items = tv.n_tiles * splits;
+  const int n_items = tv.n_tiles * splits * ncb;
   int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
   prof_begin(PROF_GEMM, s);
-  if (depth == 6) k_osgemm_tf32<6><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
-  else if (depth == 4) k_osgemm_tf32<4><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
-  else if (depth == 2) k_osgemm_tf32<2><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
-  else k_osgemm_tf32<1><<<grid, NT_P, L.total, s>>>(X, wp, bias, Y, Kd, N, K, n_rows, tv, cols, ypart, n_items, splits, nsb);
+#define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
+  k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, K, n_rows, tv, cols, ypart, \
+                                                                n_items, splits, nsb)
+  if (x3) {
+    if (depth == 6) SCN_OSGEMM_LAUNCH(6, true);
+    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, true);
+    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, true);
+    else SCN_OSGEMM_LAUNCH(1, true);
+  } else {
+    if (depth == 6) SCN_OSGEMM_LAUNCH(6, false);
+    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, false);
+    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, false);
+    else SCN_OSGEMM_LAUNCH(1, false);
+  }
+#undef SCN_OSGEMM_LAUNCH
   prof_end(PROF_GEMM, s, prof_bytes, prof_flops);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
@@ -688,21 +772,23 @@ namespace tc {
 
 constexpr int DW_NPS = 8;          // pair-list slots
 constexpr int NT_DW = 192;         // 4 gather/epilogue warps, MMA warp, pair-list loader warp
+constexpr int NT_DW3 = 320;        // 3xTF32 mode: + 4 converter warps
 
 __device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return make_desc(saddr, lbo, sbo) | (1ull << 61);   // layout_type 1 = SWIZZLE_128B_BASE32B
 }
 
 struct DwSmem {
+  // 3xTF32: stages [ns, ns + NLO) of both operand rings hold the low-order halves
   int a, b, pairs, bars, tmem_slot, total, a_stage, b_stage;
-  __host__ __device__ DwSmem(int MA, int NA, int KP, int ns) {
+  __host__ __device__ DwSmem(int MA, int NA, int KP, int ns, int x3) {
     a_stage = KP * MA * 128;
     b_stage = KP * NA * 128;
     a = 0;
-    b = a + ns * a_stage;
-    pairs = b + ns * b_stage;
+    b = a + (ns + (x3 ? NLO : 0)) * a_stage;
+    pairs = b + (ns + (x3 ? NLO : 0)) * b_stage;
     bars = pairs + DW_NPS * KP * 8;
-    tmem_slot = bars + (2 * ns + 2 * DW_NPS + 1) * 8;
+    tmem_slot = bars + (2 * ns + 2 * DW_NPS + 1 + 2 * NLO) * 8;
     total = tmem_slot + 16;
   }
 };
@@ -710,8 +796,8 @@ struct DwSmem {
 // Warp-specialised like the gather-GEMM: warp 5 streams the work item's (in,out) pair list into a
 // ring of shared-memory slots, warps 0-3 gather both operands' rows with cp.async (arrivals lag
 // NSTAGE/2 steps behind the issue, so nobody waits for fresh data), warp 4 issues the MMAs.
-template <int NSTAGE>
-__global__ void __launch_bounds__(NT_DW)
+template <int NSTAGE, bool X3>
+__global__ void __launch_bounds__(X3 ? NT_DW3 : NT_DW)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
           long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
@@ -719,13 +805,15 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
   const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)
   const int halves = Cin > 128 ? 2 : 1;
-  const DwSmem L(MA, CB, KP, NSTAGE);
+  const DwSmem L(MA, CB, KP, NSTAGE, X3 ? 1 : 0);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_full = smem_u32(smem + L.bars);
   const uint32_t bar_empty = bar_full + NSTAGE * 8;
   const uint32_t bar_pfull = bar_empty + NSTAGE * 8;
   const uint32_t bar_pempty = bar_pfull + DW_NPS * 8;
   const uint32_t bar_done = bar_pempty + DW_NPS * 8;
+  const uint32_t bar_fullL = bar_done + 8;
+  const uint32_t bar_emptyL = bar_fullL + NLO * 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   int2 *sPairs = reinterpret_cast<int2 *>(smem + L.pairs);      // [DW_NPS][KP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -746,8 +834,8 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   // zero the atoms that pad M up to 128 (never written by the gathers)
   if (CA < MA) {
     const int per_ka = (MA - CA) * 32;             // 16-byte units per k-atom
-    const int total16 = NSTAGE * KA * per_ka;
-    for (int i = tid; i < total16; i += NT_DW) {
+    const int total16 = (NSTAGE + (X3 ? NLO : 0)) * KA * per_ka;
+    for (int i = tid; i < total16; i += (X3 ? NT_DW3 : NT_DW)) {
       const int ka = i / per_ka, r = i - ka * per_ka;   // ka counts over all stages
       *reinterpret_cast<float4 *>(smem + L.a + (ka / KA) * L.a_stage + (ka % KA) * sbo_a + CA * 512 + r * 16) =
           make_float4(0.f, 0.f, 0.f, 0.f);
@@ -763,6 +851,11 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       mbar_init(bar_pempty + i * 8, 4);
     }
     mbar_init(bar_done, 1);
+    if (X3)
+      for (int i = 0; i < NLO; ++i) {
+        mbar_init(bar_fullL + i * 8, 128);
+        mbar_init(bar_emptyL + i * 8, 1);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
@@ -793,7 +886,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
         if (st < steps) {
           const int slot = st % DW_NPS, use = st / DW_NPS;
           if (use > 0) mbar_wait(bar_pempty + slot * 8, (use - 1) & 1);
-          sPairs[slot * KP + lane] = ra[u];
+          if (lane < KP) sPairs[slot * KP + lane] = ra[u];
           if (KP > 32) sPairs[slot * KP + lane + 32] = rb[u];
           ra[u] = load_pair(st + 4, lane);
           rb[u] = load_pair(st + 4, lane + 32);
@@ -838,18 +931,54 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       for (int st = 0; st < steps; ++st) {
         const int stage = st % NSTAGE, use = st / NSTAGE;
         mbar_wait(bar_full + stage * 8, use & 1);
+        const int stl = st % NLO;
+        if (X3) mbar_wait(bar_fullL + stl * 8, (st / NLO) & 1);
         tc_fence_after();
         const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
+        const uint32_t la = a_base + (NSTAGE + stl) * L.a_stage, lb = b_base + (NSTAGE + stl) * L.b_stage;
         for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
           const uint64_t bd = make_desc_b32(sb + kb * 2 * sbo_b, 512, sbo_b);
+          const uint64_t bl = make_desc_b32(lb + kb * 2 * sbo_b, 512, sbo_b);
           for (int h = 0; h < halves; ++h) {
             const uint64_t ad = make_desc_b32(sa + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
             mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
+            if (X3) {   // + lo(x) * dy + x * lo(dy)
+              const uint64_t al = make_desc_b32(la + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
+              mma_tf32(tmem_d + (uint32_t)(h * Cout), al, bd, idesc, 1u);
+              mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bl, idesc, 1u);
+            }
           }
         }
         tc_commit(bar_empty + stage * 8);
+        if (X3) tc_commit(bar_emptyL + stl * 8);
       }
       if (steps > 0) tc_commit(bar_done);
+    }
+  }
+  if (X3 && warp >= 6) {
+    // ===== converters (3xTF32): low-order halves of both operand stages, same positions =====
+    const int ct = tid - 6 * 32;
+    const int a16 = L.a_stage >> 4, b16 = L.b_stage >> 4;
+    for (int st = 0; st < steps; ++st) {
+      const int stage = st % NSTAGE, stl = st % NLO;
+      mbar_wait(bar_full + stage * 8, (st / NSTAGE) & 1);
+      if (st >= NLO) mbar_wait(bar_emptyL + stl * 8, ((st / NLO) - 1) & 1);
+      auto lo4 = [](const float4 v) {
+        float4 o;
+        o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        return o;
+      };
+      const float4 *srca = reinterpret_cast<const float4 *>(smem + L.a + stage * L.a_stage);
+      float4 *dsta = reinterpret_cast<float4 *>(smem + L.a + (NSTAGE + stl) * L.a_stage);
+      for (int i = ct; i < a16; i += 128) dsta[i] = lo4(srca[i]);
+      const float4 *srcb = reinterpret_cast<const float4 *>(smem + L.b + stage * L.b_stage);
+      float4 *dstb = reinterpret_cast<float4 *>(smem + L.b + (NSTAGE + stl) * L.b_stage);
+      for (int i = ct; i < b16; i += 128) dstb[i] = lo4(srcb[i]);
+      fence_proxy_async();
+      mbar_arrive(bar_fullL + stl * 8);
     }
   }
   // ===== epilogue (warps 0-3): accumulator row = input channel, columns = output channels =====
@@ -900,30 +1029,48 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
                   int precision, cudaStream_t s) {
   using namespace tc;
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
-  if (precision != SCN_PRECISION_TF32) return 1;
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32) return 1;
+  const bool x3 = precision == SCN_PRECISION_FP32_3XTF32;
   if (Cin < 32 || Cin % 32 || (Cin > 128 && Cin != 256) || Cout < 32 || Cout % 32 || Cout > 256) return 1;
   if (!al(X) || !al(dY) || !al(partial)) return 1;
   const int MA = Cin > 128 ? Cin >> 5 : 4, NA = Cout >> 5;
-  const int KP = (MA + NA) <= 5 ? 64 : 32;
+  int KP = (MA + NA) <= 5 ? 64 : 32;
+  if (x3 && KP * (MA + NA) * 128 > 40 * 1024) KP = 16;     // 3xTF32 keeps raw + low-order stages: smaller steps
   const int stage_bytes = KP * (MA + NA) * 128;
-  int ns = (205 * 1024) / stage_bytes;
+  int ns = (205 * 1024 - (x3 ? NLO * stage_bytes : 0)) / stage_bytes;
   ns = ns >= 6 ? 6 : (ns >= 4 ? 4 : 3);
-  const DwSmem L(MA, NA, KP, ns);
+  const DwSmem L(MA, NA, KP, ns, x3 ? 1 : 0);
+  if (L.total > 227 * 1024) return 1;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_dw_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_dw_tf32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(k_dw_tf32<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(k_dw_tf32) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaError_t ae = cudaSuccess;
+    auto setattr = [&](const void *f) {
+      if (ae == cudaSuccess) ae = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    };
+    setattr((const void *)k_dw_tf32<3, false>); setattr((const void *)k_dw_tf32<4, false>);
+    setattr((const void *)k_dw_tf32<6, false>); setattr((const void *)k_dw_tf32<3, true>);
+    setattr((const void *)k_dw_tf32<4, true>);  setattr((const void *)k_dw_tf32<6, true>);
+    if (ae != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(k_dw_tf32) failed: %s", cudaGetErrorString(ae));
       return -1;
     }
     attr_set = true;
   }
   uint32_t cols = 32;
   while ((int)cols < Cout * (Cin > 128 ? 2 : 1)) cols <<= 1;
-  if (ns == 3) k_dw_tf32<3><<<n_work, NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
-  else if (ns == 4) k_dw_tf32<4><<<n_work, NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
-  else k_dw_tf32<6><<<n_work, NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, ident_n, ident_chunk, KP, cols);
+#define SCN_DW_LAUNCH(NS, T3)                                                                                       \
+  k_dw_tf32<NS, T3><<<n_work, T3 ? NT_DW3 : NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, \
+                                                                 ident_n, ident_chunk, KP, cols)
+  if (x3) {
+    if (ns == 3) SCN_DW_LAUNCH(3, true);
+    else if (ns == 4) SCN_DW_LAUNCH(4, true);
+    else SCN_DW_LAUNCH(6, true);
+  } else {
+    if (ns == 3) SCN_DW_LAUNCH(3, false);
+    else if (ns == 4) SCN_DW_LAUNCH(4, false);
+    else SCN_DW_LAUNCH(6, false);
+  }
+#undef SCN_DW_LAUNCH
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
