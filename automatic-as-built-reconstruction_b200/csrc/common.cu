@@ -122,6 +122,20 @@ int workspace(void **p, int slot, size_t bytes, cudaStream_t s) {
   return 0;
 }
 
+static std::vector<std::pair<cudaStream_t, int *>> g_sched;
+
+int sched_counters(int **p, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  for (auto &e : g_sched)
+    if (e.first == s) { *p = e.second; return 0; }
+  int *d = nullptr;
+  SCN_CUDA(cudaMalloc((void **)&d, 64));
+  SCN_CUDA(cudaMemset(d, 0, 64));          // synchronous: visible to every stream that follows
+  g_sched.emplace_back(s, d);
+  *p = d;
+  return 0;
+}
+
 static std::mutex g_side_mu;
 static std::vector<std::pair<cudaStream_t, SideStream *>> g_side;
 

@@ -67,6 +67,10 @@ inline int workspace_t(T **p, int slot, size_t n, cudaStream_t s) {
   return workspace((void **)p, slot, (n ? n : 1) * sizeof(T), s);
 }
 
+// Two zero-initialised ints per stream for the persistent kernels' dynamic work distribution (the
+// kernels leave them zero on exit).
+int sched_counters(int **p, cudaStream_t s);
+
 // A companion stream of `s` for work that is independent of what `s` does next (the weight gradient
 // of a layer next to its input gradient).  fork: side waits for everything queued on s so far;
 // join: s waits for the side stream.

@@ -122,6 +122,20 @@ __device__ __forceinline__ float to_tf32(float x) {
 // ---------------------------------------------------------------------------------------------
 // the gather-GEMM kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef SCN_EXPERIMENT_TRACE
+// per-role clock64 trace of CTA 0 (developer experiment, tools/gemm_trace.py): role r appends to g_trace[r]
+__device__ unsigned long long g_trace[5][8192];
+__device__ int g_trace_n[5];
+#define SCN_TRACE(role, tag)                                                                      \
+  do {                                                                                            \
+    if (blockIdx.x == 0) {                                                                        \
+      const int _i = g_trace_n[role];                                                             \
+      if (_i < 8190) { g_trace[role][_i] = ((unsigned long long)(tag) << 56) | (clock64() & 0xffffffffffffffull); g_trace_n[role] = _i + 1; } \
+    }                                                                                             \
+  } while (0)
+#else
+#define SCN_TRACE(role, tag) do { } while (0)
+#endif
 constexpr int MS = 3;                        // tile-metadata slots (producers may run ~2 tiles ahead of the epilogue)
 constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) / B (weight slices)
 constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight loader, 4 epilogue, metadata loader
@@ -195,7 +209,7 @@ template <int DEPTH, bool X3>
 __global__ void __launch_bounds__(X3 ? NT_P3 : NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int ldn, int K, long long n_rows, TileView tb, uint32_t acc_cols,
-              float *__restrict__ Ypart, int n_items, int splits, int NSB) {
+              float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched) {
   // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -244,7 +258,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     }
     if (X3)
       for (int i = 0; i < NLO; ++i) {
-        mbar_init(bar_fullL + i * 8, 128);
+        mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
         mbar_init(bar_emptyL + i * 8, 1);
       }
     for (int i = 0; i < 2; ++i) {
@@ -261,13 +275,27 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 
   if (warp == 10) {
     // ===== metadata loader =====
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    // Work items are handed out dynamically (one atomic per item on the launch's counter), heaviest
+    // tiles first: rows are sorted by neighbour mask, so the tiles with the most active offsets sit at
+    // the end of the tile book - a static round-robin left the SMs idle 35 % of the kernel (ncu:
+    // smsp__cycles_active vs sm__cycles_elapsed).  sched = {next item, CTAs done}; the last CTA to
+    // finish resets both for the next launch on this stream.
+    for (int it = 0;; ++it) {
       const int slot = it % MS, use = it / MS;
       if (use > 0) mbar_wait(bar_mempty + slot * 8, (use - 1) & 1);
-      const int tile = item % n_tiles;
+      int q = 0;
+      if (lane == 0) SCN_TRACE(0, 1);
+      if (lane == 0) q = atomicAdd(sched, 1);
+      q = __shfl_sync(0xffffffffu, q, 0);
+      if (lane == 0) SCN_TRACE(0, 2);
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
       int32_t *sPerm = meta_perm(slot), *hdr = meta_hdr(slot);
+      if (q >= n_items) {                     // end marker for the other roles
+        if (lane == 0) { hdr[1] = -1; mbar_arrive(bar_mfull + slot * 8); }
+        break;
+      }
+      const int tile = n_tiles - 1 - q % n_tiles;
+      if (lane == 0) hdr[1] = q - q % n_tiles + tile;
       if (tb.identity) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -277,29 +305,41 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           sIdx[0][lane * 4 + i] = v;
         }
         if (lane == 0) { hdr[0] = 1; reinterpret_cast<int8_t *>(hdr + 2)[0] = 0; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_mfull + slot * 8);
       } else {
+        // the tile's row permutation (512 B) and its nE gather lists (nE x 512 B, contiguous in the tile
+        // book) come in as two bulk copies that complete the slot's barrier - the loader never waits for
+        // them (a per-list load loop cost ~2 us per list and paced the whole CTA)
         const uint32_t mask = tb.tile_mask[tile];
         const int e0 = tb.tile_off[tile];
         const int nE = __popc(mask);
-        reinterpret_cast<int4 *>(sPerm)[lane] = __ldg(reinterpret_cast<const int4 *>(tb.perm + (long long)tile * TILE_M) + lane);
-        for (int e = 0; e < nE; ++e)
-          reinterpret_cast<int4 *>(sIdx[e])[lane] = __ldg(reinterpret_cast<const int4 *>(tb.entries + (long long)(e0 + e) * TILE_M) + lane);
         if (mask & (1u << lane)) reinterpret_cast<int8_t *>(hdr + 2)[__popc(mask & ((1u << lane) - 1u))] = (int8_t)lane;
         if (lane == 0) hdr[0] = nE;
+        __syncwarp();
+        if (lane == 0) {
+          mbar_expect_tx(bar_mfull + slot * 8, (uint32_t)(nE + 1) * TILE_M * 4);
+          bulk_copy_g2s(smem_u32(sPerm), tb.perm + (long long)tile * TILE_M, TILE_M * 4, bar_mfull + slot * 8);
+          if (nE > 0)
+            bulk_copy_g2s(smem_u32(&sIdx[0][0]), tb.entries + (long long)e0 * TILE_M, (uint32_t)nE * TILE_M * 4,
+                          bar_mfull + slot * 8);
+          SCN_TRACE(0, 3);
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_mfull + slot * 8);
     }
   } else if (warp < 4) {
     // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
     const int j = tid & 7, r0 = tid >> 3;
-    int g = 0, it = 0;                       // global step / item counters of this CTA
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    int g = 0;                               // global step counter of this CTA
+    for (int it = 0;; ++it) {
       const int slot = it % MS;
       mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      const int item = meta_hdr(slot)[1];
+      if (item < 0) break;
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
       const int split = (item % item_stride) / n_tiles;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
+      if (tid == 0) SCN_TRACE(1, 1);
       for (int lst = 0; lst < steps; ++lst, ++g) {
         const int stage = g % NSA, use = g / NSA;
         if (use > 0) mbar_wait(bar_emptyA + stage * 8, (use - 1) & 1);
@@ -324,6 +364,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         cp_async_mbar_arrive(bar_fullA + stage * 8);
         mbar_arrive(bar_fullA + stage * 8);
       }
+      if (tid == 0) SCN_TRACE(1, 2);
       __syncwarp();                           // the tile's lists are no longer needed by this warp
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
     }
@@ -331,16 +372,21 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
-      int g = 0, it = 0, accn = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int g = 0, accn = 0;
+      for (int it = 0;; ++it) {
         const int slot = it % MS;
         mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int item = meta_hdr(slot)[1];
+        if (item < 0) break;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         mbar_arrive(bar_mempty + slot * 8);
+        SCN_TRACE(2, 1);
+        SCN_TRACE(4, steps);
         if (steps == 0) continue;
         const int acc = accn & 1;
         if (accn >= 2) mbar_wait(bar_tempty + acc * 8, ((accn >> 1) - 1) & 1);
         tc_fence_after();
+        SCN_TRACE(2, 2);
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
         for (int lst = 0; lst < steps; ++lst, ++g) {
           const int stage = g % NSA, use = g / NSA;
@@ -350,10 +396,16 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const int stl = g % NLO;
           if (X3) mbar_wait(bar_fullL + stl * 8, (g / NLO) & 1);
           tc_fence_after();
+          if (lst == 0) SCN_TRACE(2, 3);
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
           const uint32_t sl = alo_base + stl * A_STAGE;
 #pragma unroll
+#ifdef SCN_EXPERIMENT_NO_MMA     // timing experiment only (wrong results): one MMA per step instead of 4 / 12
+          if (lst == 0) mma_tf32(tmem_d, make_desc_sw128(sa), make_desc_sw128(sb), idesc, 0u);
+          for (int kk = 0; kk < 0; ++kk) {
+#else
           for (int kk = 0; kk < KC / 8; ++kk) { // K = 8 per instruction: 32 bytes further along the 128-byte rows
+#endif
             mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
                      (lst > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
@@ -361,33 +413,38 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
               mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + B_SLICE + kk * 32), idesc, 1u);
             }
           }
+          // ONE commit per step: emptyA[g % NSA] completing means "the MMAs of step g are done"; the
+          // weight loader and the converters wait on the same barrier for the step that last used the
+          // stage they are about to refill (their rings are no deeper than NSA, so the barrier cannot
+          // run two phases ahead of them)
           tc_commit(bar_emptyA + stage * 8);
-          tc_commit(bar_emptyB + stb * 8);
-          if (X3) tc_commit(bar_emptyL + stl * 8);
         }
         tc_commit(bar_tfull + acc * 8);
+        SCN_TRACE(2, 4);
         ++accn;
       }
     }
   } else if (warp == 5) {
     // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
     if (lane == 0) {
-      int g = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int g = 0;
+      for (int it = 0;; ++it) {
         const int slot = it % MS;
         mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int item = meta_hdr(slot)[1];
+        if (item < 0) break;
         const int split = (item % item_stride) / n_tiles, col0 = (item / item_stride) * N;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         const int8_t *sK = reinterpret_cast<const int8_t *>(meta_hdr(slot) + 2);
         for (int lst = 0; lst < steps; ++lst, ++g) {
-          const int stage = g % NSB, use = g / NSB;
-          if (use > 0) mbar_wait(bar_emptyB + stage * 8, (use - 1) & 1);
+          const int stage = g % NSB;
+          if (g >= NSB) mbar_wait(bar_emptyA + ((g - NSB) % NSA) * 8, ((g - NSB) / NSA) & 1);
           const int st = split + lst * splits;
           const int e = st / kchunks, c = st - e * kchunks;
           const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
           const uint32_t bytes = (uint32_t)B_STAGE;
 #ifdef SCN_EXPERIMENT_NO_B          // timing experiment only (wrong results): what if weight slices were free?
-          if (use > 0) { mbar_arrive(bar_fullB + stage * 8); continue; }
+          if (g >= NSB) { mbar_arrive(bar_fullB + stage * 8); continue; }
 #endif
           mbar_expect_tx(bar_fullB + stage * 8, bytes);
           if (X3) {   // slices [k][c][hi|lo][ldn][32]: rows col0 .. col0+N of the hi and of the lo slice
@@ -408,17 +465,19 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // positions, into the low-order ring; generic-proxy writes are fenced for the tensor core =====
     if (X3) {
       const int ct = tid - 11 * 32;
-      int g = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int g = 0;
+      for (int it = 0;; ++it) {
         const int slot = it % MS;
         mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int item = meta_hdr(slot)[1];
+        if (item < 0) break;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
         for (int lst = 0; lst < steps; ++lst, ++g) {
           const int stage = g % NSA, stl = g % NLO;
           mbar_wait(bar_fullA + stage * 8, (g / NSA) & 1);
-          if (g >= NLO) mbar_wait(bar_emptyL + stl * 8, ((g / NLO) - 1) & 1);
+          if (g >= NLO) mbar_wait(bar_emptyA + ((g - NLO) % NSA) * 8, ((g - NLO) / NSA) & 1);
           const float4 *src = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE);
           float4 *dst = reinterpret_cast<float4 *>(smem + L.alo + stl * A_STAGE);
 #pragma unroll
@@ -432,7 +491,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
             dst[ct + u * 128] = o;
           }
           fence_proxy_async();
-          mbar_arrive(bar_fullL + stl * 8);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_fullL + stl * 8);
         }
       }
     }
@@ -440,15 +500,18 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // ===== epilogue (warps 6-9): TMEM lanes 32*(warp%4).. -> registers -> global =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    int it = 0, accn = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    int accn = 0;
+    for (int it = 0;; ++it) {
       const int slot = it % MS;
       mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      const int item = meta_hdr(slot)[1];
+      if (item < 0) break;
       const int tile = item % n_tiles, split = (item % item_stride) / n_tiles, col0 = (item / item_stride) * N;
       const int steps = item_steps(item, meta_hdr(slot)[0]);
       int orow = meta_perm(slot)[row];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
+      if (warp == 6 && lane == 0) SCN_TRACE(3, 1);
       const float *bs = bias ? bias + col0 : nullptr;
       float *yp = Y + (long long)(orow < 0 ? 0 : orow) * ldn + col0;
       if (splits > 1) {                     // partial tile, slot order, no bias
@@ -461,6 +524,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         mbar_wait(bar_tfull + acc * 8, (accn >> 1) & 1);
         tc_fence_after();
       }
+      if (warp == 6 && lane == 0) SCN_TRACE(3, 2);
       const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
@@ -504,7 +568,11 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
             const int dst_row = __shfl_sync(0xffffffffu, orow, r);
             float4 o = st[r * 8 + (jc ^ (r & 7))];
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+#ifdef SCN_EXPERIMENT_NO_EPI     // timing experiment only (wrong results): no global stores in the epilogue
+            if (dst_row >= 0 && o.x == 12345.678f) {
+#else
             if (dst_row >= 0) {
+#endif
               float *p = splits > 1 ? Ypart + (((long long)split * n_tiles + tile) * TILE_M + q * 32 + r) * ldn
                                     : Y + (long long)dst_row * ldn;
               *reinterpret_cast<float4 *>(p + col0 + c0 + 4 * jc) = o;
@@ -525,11 +593,16 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         }
       }
       if (steps > 0) ++accn;
+      if (warp == 6 && lane == 0) SCN_TRACE(3, 3);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 2 * acc_cols);
+  if (tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {   // last CTA out: rearm the counters
+    sched[0] = 0;
+    sched[1] = 0;
+  }
 }
 
 // Y[perm[slot]] = bias + sum_s Ypart[s][slot]   (fixed summation order)
@@ -726,11 +799,15 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   if (splits > 1 && workspace_t(&ypart, WS_SPLITK, (size_t)splits * n_slots * N, s)) return -1;
   const int n_items = tv.n_tiles * splits * ncb;
   int grid = n_items < num_sms() ? n_items : num_sms();            // persistent: one CTA per SM
+  static const int env_limit = getenv("SCN_B200_GEMM_GRID") ? atoi(getenv("SCN_B200_GEMM_GRID")) : 0;   // experiments
+  if (env_limit > 0 && grid > env_limit) grid = env_limit;
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
+  int *sched = nullptr;
+  if (sched_counters(&sched, s)) return -1;
   prof_begin(PROF_GEMM, s);
 #define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
   k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, K, n_rows, tv, cols, ypart, \
-                                                                n_items, splits, nsb)
+                                                                n_items, splits, nsb, sched)
   if (x3) {
     if (depth == 6) SCN_OSGEMM_LAUNCH(6, true);
     else if (depth == 4) SCN_OSGEMM_LAUNCH(4, true);
@@ -853,7 +930,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     mbar_init(bar_done, 1);
     if (X3)
       for (int i = 0; i < NLO; ++i) {
-        mbar_init(bar_fullL + i * 8, 128);
+        mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
         mbar_init(bar_emptyL + i * 8, 1);
       }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -949,8 +1026,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
             }
           }
         }
-        tc_commit(bar_empty + stage * 8);
-        if (X3) tc_commit(bar_emptyL + stl * 8);
+        tc_commit(bar_empty + stage * 8);            // one commit per step (the converters wait on it too)
       }
       if (steps > 0) tc_commit(bar_done);
     }
@@ -962,7 +1038,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     for (int st = 0; st < steps; ++st) {
       const int stage = st % NSTAGE, stl = st % NLO;
       mbar_wait(bar_full + stage * 8, (st / NSTAGE) & 1);
-      if (st >= NLO) mbar_wait(bar_emptyL + stl * 8, ((st / NLO) - 1) & 1);
+      if (st >= NLO) mbar_wait(bar_empty + ((st - NLO) % NSTAGE) * 8, ((st - NLO) / NSTAGE) & 1);
       auto lo4 = [](const float4 v) {
         float4 o;
         o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
@@ -978,7 +1054,8 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       float4 *dstb = reinterpret_cast<float4 *>(smem + L.b + (NSTAGE + stl) * L.b_stage);
       for (int i = ct; i < b16; i += 128) dstb[i] = lo4(srcb[i]);
       fence_proxy_async();
-      mbar_arrive(bar_fullL + stl * 8);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_fullL + stl * 8);
     }
   }
   // ===== epilogue (warps 0-3): accumulator row = input channel, columns = output channels =====
@@ -1018,6 +1095,18 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
 
 // partial[w] (w < n_work) = X[rows]^T @ dY[rows] over the pairs of work item w.  >0: shape not handled.
 }  // namespace scn
+#ifdef SCN_EXPERIMENT_TRACE
+extern "C" int scn_debug_trace_read(unsigned long long *out, int *counts, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, scn::tc::g_trace, sizeof(unsigned long long) * 5 * 8192);
+  cudaMemcpyFromSymbol(counts, scn::tc::g_trace_n, sizeof(int) * 5);
+  if (reset) {
+    int z[5] = {0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(scn::tc::g_trace_n, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 extern "C" int scn_set_gemm_grid_limit(int max_ctas) {
   scn::tc::g_gemm_grid_limit = max_ctas;
   return 0;

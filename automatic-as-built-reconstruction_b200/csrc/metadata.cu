@@ -584,6 +584,14 @@ int ensure_dw_work(RuleBook *rb, cudaStream_t s) {
   long long chunk = (rb->total_pairs + 2LL * num_sms() - 1) / (2LL * num_sms());
   chunk = (chunk + 63) / 64 * 64;
   chunk = std::min<long long>(std::max<long long>(chunk, 512), 16384);
+  // every offset rounds its item count up: grow the chunk until the total fits 2 full waves (the kernel
+  // holds one CTA per SM; 2 x 148 + 12 items ran as three waves, the last one almost empty)
+  for (;;) {
+    long long items = 0;
+    for (int k = 0; k < rb->K; ++k) items += (rb->counts[k] + chunk - 1) / chunk;
+    if (items <= 2LL * num_sms() || chunk >= 16384) break;
+    chunk += 64;
+  }
   std::vector<DwWork> &w = rb->dw_host;
   w.clear();
   for (int k = 0; k < rb->K; ++k) {

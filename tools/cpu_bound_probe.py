@@ -11,7 +11,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 import sparseconvnet as scn  # noqa: E402
 
-scn.set_conv_precision("tf32")
+scn.set_conv_precision(sys.argv[1] if len(sys.argv) > 1 else "fp32")
 dev = torch.device("cuda", 0)
 net = scn.FPN_Net(bench.FULL_SCALE, 3, ["xyz", "color", "normal"], 1, bench.PLANES, nPlaneM=128, residual_blocks=True,
                   fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
