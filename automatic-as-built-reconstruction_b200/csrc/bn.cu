@@ -202,10 +202,11 @@ k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, 
 template <bool VEC>
 __global__ void __launch_bounds__(BN_T)
 k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
-               const float *__restrict__ dY, float *__restrict__ dX,
+               const float *__restrict__ dY, float *dX /* may alias R */,
                const float *__restrict__ mean, const double *__restrict__ acc,
                const float *__restrict__ save_invstd, const float *__restrict__ weight,
-               float *d_weight, float *d_bias, float leak, long long n, int C, double *zero_buf, int zero_n) {
+               float *d_weight, float *d_bias, float leak, long long n, int C, double *zero_buf, int zero_n,
+               const float *R) {
   extern __shared__ float coef[];  // [3C] then mean [C]
   float *smean = coef + 3 * C;
   if (blockIdx.x == 0)
@@ -234,13 +235,17 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
       o.y = (d.y * (y.y > 0.f ? 1.f : leak) - gm.y - (x.y - mu.y) * kk.y) * sc.y;
       o.z = (d.z * (y.z > 0.f ? 1.f : leak) - gm.z - (x.z - mu.z) * kk.z) * sc.z;
       o.w = (d.w * (y.w > 0.f ? 1.f : leak) - gm.w - (x.w - mu.w) * kk.w) * sc.w;
+      if (R) {   // second gradient of the same value (skip connection), may alias dX
+        const float4 r = reinterpret_cast<const float4 *>(R)[i];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
       reinterpret_cast<float4 *>(dX)[i] = o;
     }
   } else {
     for (; i < total; i += st) {
       const int c = (int)(i % C);
       const float d = dY[i] * (Yo[i] > 0.f ? 1.f : leak);
-      dX[i] = (d - coef[c] - (X[i] - smean[c]) * coef[C + c]) * coef[2 * C + c];
+      dX[i] = (d - coef[c] - (X[i] - smean[c]) * coef[C + c]) * coef[2 * C + c] + (R ? R[i] : 0.f);
     }
   }
 }
@@ -341,6 +346,14 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
                            const float *save_mean, const float *save_invstd, const float *weight,
                            float *d_weight, float *d_bias, float leakiness, int64_t n, int64_t C64,
                            void *stream) {
+  return scn_batchnorm_backward_add(in, d_in, out, d_out, save_mean, save_invstd, weight, d_weight, d_bias,
+                                    leakiness, n, C64, nullptr, stream);
+}
+
+int scn_batchnorm_backward_add(const float *in, float *d_in, const float *out, const float *d_out,
+                               const float *save_mean, const float *save_invstd, const float *weight,
+                               float *d_weight, float *d_bias, float leakiness, int64_t n, int64_t C64,
+                               const float *residual, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)C64;
   SCN_CHECK(C > 0 && C <= 4096 && save_mean && save_invstd, "bad BN arguments");
@@ -350,7 +363,8 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
     return 0;
   }
   SCN_CHECK(in && d_in && out && d_out, "null feature pointer");
-  const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0);
+  const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0) &&
+                   (((uintptr_t)residual & 15) == 0);
   prof_begin(PROF_BN, s);
   double *acc = nullptr, *other = nullptr;
   int other_used = 0;
@@ -365,10 +379,10 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
   const size_t sm = (size_t)4 * C * sizeof(float);
   if (vec)
     k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
-                                                              weight, d_weight, d_bias, leakiness, n, C, other, other_used);
+                                                              weight, d_weight, d_bias, leakiness, n, C, other, other_used, residual);
   else
     k_bn_bwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
-                                                           weight, d_weight, d_bias, leakiness, n, C, other, other_used);
+                                                           weight, d_weight, d_bias, leakiness, n, C, other, other_used, residual);
   SCN_LAUNCHED();
   prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;

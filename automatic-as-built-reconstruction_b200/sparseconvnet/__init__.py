@@ -17,6 +17,7 @@ from .modules import (  # noqa: E402
 from . import (batchNormalization, convolution, deconvolution, identity, ioLayers, metadata,  # noqa: E402
                networkInNetwork, sequential, sparseConvNetTensor, sparseToDense,
                submanifoldConvolution, tables, utils)
+from .graph import GraphFunction, LayerGraph  # noqa: E402
 from .fpn_net import FPN_Net  # noqa: E402
 from . import tools_3d_2d  # noqa: E402
 from .voxelize import quantize_points  # noqa: E402

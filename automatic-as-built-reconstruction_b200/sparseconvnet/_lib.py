@@ -87,6 +87,14 @@ _sig = {
     "scn_batchnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64,
                                        c_void_p]),
+    "scn_batchnorm_backward_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64,
+                                           c_void_p, c_void_p]),
+    "scn_graph_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_void_p, POINTER(c_double)]),
+    "scn_graph_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                   c_void_p]),
     "scn_sparse_to_dense_forward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                             c_void_p]),
     "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,

@@ -7,11 +7,14 @@ top-down steps with 3^3 merge convs (all 8 are executed, as in the reference), a
 [1,1,Z] z-collapse convolutions that make the 2-D RPN maps.  Debug printing / pdb hooks of the
 reference are not reproduced.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
 
 import sparseconvnet as scn
+from . import graph as _graph
 
 CHECK_NAN = False  # the reference syncs on isnan(weight) every forward (fpn_net.py:141-145)
 
@@ -101,7 +104,61 @@ class FPN_Net(torch.nn.Module):
         net = self.layers_in[0](net0)                  # InputLayer: voxel hashing (or a PreparedInput)
         if not getattr(net, "rulebooks_built", False):
             self._prebuild_rulebooks(net)
+        g = self._layer_graph() if self.use_layer_graph else None
+        if g is not None and g.bn_modules_use_running_buffers(self.training, self):
+            return self.forward_fpn_graph(net, g)
         return self.forward_fpn(self.layers_in[1](net))
+
+    # ---- one-call execution of the whole graph (sparseconvnet/graph.py) ----------------------
+    use_layer_graph = os.environ.get("SCN_B200_LAYER_GRAPH", "1") != "0"
+
+    def _apply(self, fn, *args, **kwargs):
+        self._graph_cache = None          # .to() / .cuda() replace the BN buffers the compiled graph points at
+        return super(FPN_Net, self)._apply(fn, *args, **kwargs)
+
+    def _layer_graph(self):
+        """the ops of layers_in[1] + forward_fpn as a flat list, compiled once (None if a layer is not
+        supported by the executor - the per-layer path below then runs)"""
+        g = getattr(self, "_graph_cache", None)
+        if g is None:
+            try:
+                il = self.layers_in[0]
+                g = _graph.LayerGraph(self.layers_in[1].nIn, il.spatial_size.tolist())
+                v = g.emit(self.layers_in[1], 0)
+                n_scales = len(self.m_downs)
+                downs = []
+                for m in self.m_downs:
+                    v = g.emit(m, v)
+                    downs.append(v)
+                v = g.emit(self.m_shortcuts[-1], v)
+                ups = [v]
+                for k in range(n_scales - 1):
+                    j = n_scales - 2 - k
+                    v = g.emit(self.m_ups[k], v)
+                    v = g.add(v, g.emit(self.m_shortcuts[j], downs[j]))
+                    ups.append(g.emit(self.m_mergeds[k], v))     # the top-down path continues from the SUM
+                rpn3d = [ups[i] for i in self.fpn_scales_from_top]
+                for i, v3 in enumerate(rpn3d):
+                    assert list(g.values[v3][1]) == [int(x) for x in self.rpn_map_sizes[i]]
+                rpn2d = [g.emit(self.convs_pro2d[i], rpn3d[i]) for i in range(len(rpn3d))]
+                both = rpn3d + rpn2d
+                self._graph_rpn = [both[i] for i in self.rpn_3d_2d_selector]
+                self._graph_roi = [ups[i] for i in self.roi_scales_from_top]
+                g.finalize(self._graph_rpn + self._graph_roi)
+            except _graph.Unsupported:
+                g = False
+            self._graph_cache = g
+        return g or None
+
+    def forward_fpn_graph(self, net, g):
+        feats = _graph.GraphFunction.apply(g, net.metadata, self.training, net.features, *g.grad_params)
+        by_value = dict(zip(g.outputs, feats))
+
+        def wrap(v):
+            t = scn.SparseConvNetTensor(metadata=net.metadata, spatial_size=torch.tensor(g.values[v][1]))
+            t.features = by_value[v]
+            return t
+        return [wrap(v) for v in self._graph_rpn], [wrap(v) for v in self._graph_roi]
 
     def prepare(self, coords, batch_size=0):
         """All integer work of a batch - input grid, the 12 coarser grids and every rulebook - on the

@@ -206,6 +206,13 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, const
                            const float *save_mean, const float *save_invstd,
                            const float *weight, float *d_weight, float *d_bias,
                            float leakiness, int64_t n_rows, int64_t n_planes, void *stream);
+/* same, with d_in = BN gradient + residual (residual [n_rows,n_planes] may be NULL or alias d_in): the
+ * second gradient of a value that feeds both a BatchNorm and a skip connection, added in the same pass */
+int scn_batchnorm_backward_add(const float *in, float *d_in, const float *out, const float *d_out,
+                               const float *save_mean, const float *save_invstd,
+                               const float *weight, float *d_weight, float *d_bias,
+                               float leakiness, int64_t n_rows, int64_t n_planes,
+                               const float *residual, void *stream);
 
 /* ---- SparseToDense (replaces SparseToDense_updateOutput / _updateGradInput,
  *      pybind.cpp:124-133, CPU/SparseToDense.cpp:35-87) --------------------------------
@@ -215,6 +222,44 @@ int scn_sparse_to_dense_forward(scn_metadata_t *m, const int64_t *spatial_size, 
 int scn_sparse_to_dense_backward(scn_metadata_t *m, const int64_t *spatial_size, float *d_in,
                                  const float *d_out, int64_t n_planes, int64_t batch_size,
                                  void *stream);
+
+/* ---- layer-graph executor (B200 extension) -------------------------------------------
+ * The reference runs the backbone as ~130 Python autograd Functions per direction
+ * (sparseconvnet/{submanifoldConvolution,convolution,deconvolution,batchNormalization}.py, fpn_net.py:168-265);
+ * at batch 1 the enqueue work of that Python layer, not the GPU, bounds the step.  A graph is the same
+ * sequence of layer ops as a flat array, executed by ONE call per direction through exactly the entry
+ * points above (same kernels, same results).  Values are feature matrices [rows, planes] identified by
+ * index; the caller owns every buffer (torch allocates them: values, gradients, parameter gradients).
+ *   kind 1 submanifold conv, 2 convolution, 3 deconvolution (in0 -> out; p0 weight, p1 bias or -1)
+ *   kind 4 BatchNorm(Leaky)ReLU (in0 -> out; p0 gamma, p1 beta, p2 running_mean, p3 running_var;
+ *          save_off = float offset of this op's {mean[C], invstd[C]} in bn_save)
+ *   kind 5 add (out = in0 + in1) */
+typedef struct scn_graph_op {
+  int32_t kind, in0, in1, out;
+  int32_t n_in_planes, n_out_planes;
+  int32_t p0, p1, p2, p3;
+  int64_t in_ss[3], out_ss[3], filter[3], stride[3];
+  int64_t save_off;
+  float eps, momentum, leakiness, pad_;
+} scn_graph_op_t;
+/* values[v]: device pointer of value v (read for inputs, fully written for outputs); rows[v] its row count.
+ * params[p]: device pointer of parameter / buffer p; param_tags[2p..2p+1]: weight tag or {0,0}.
+ * *macs (may be NULL) receives the summed multiply-add count of the convolutions. */
+int scn_graph_forward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_ops, float *const *values,
+                      const int64_t *rows, float *const *params, const int64_t *param_tags, float *bn_save,
+                      int train, int precision, void *stream, double *macs);
+/* Reverse sweep.  out_grads[v] (NULL if none): gradient arriving from outside for value v (read only).
+ * grads[v]: caller-provided buffer [rows[v], planes] for the gradient of value v, NULL if that gradient is
+ * not wanted (then nothing flows further back through v).  Ops whose output receives no gradient are
+ * skipped.  param_grads[p]: buffer for the gradient of parameter p (fully written if the op runs);
+ * param_written[p] (host) is set to 1 for every parameter gradient written.  scratch: device buffer of
+ * scratch_floats >= max rows*planes over the values (used when a convolution's input gradient has to be
+ * added to an existing one). */
+int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_ops, int32_t n_values,
+                       float *const *values, const int64_t *rows, float *const *params,
+                       const int64_t *param_tags, const float *bn_save, float *const *grads,
+                       const float *const *out_grads, float *const *param_grads, uint8_t *param_written,
+                       float *scratch, int64_t scratch_floats, int precision, void *stream);
 
 /* ---- elementwise helper used by the data-parallel gradient bucket ------------------- */
 /* y[i] *= alpha over n fp32 values (scale the all-reduced gradient bucket by 1/world) */

@@ -553,3 +553,53 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
     for i, m in enumerate(list(rpn) + list(roi)):
         order = np.argsort(O.canonical_rank(m.get_spatial_locations().numpy(), m.spatial_size.tolist()))
         assert rel(m.features.cpu()[order], ge["out%d_feat" % i]) <= feat_tol
+
+
+def test_layer_graph_equals_per_layer_path(scn):
+    """the one-call graph executor (sparseconvnet/graph.py, csrc/graph.cu) runs the same kernels as the
+    per-layer autograd Functions: outputs, input gradient, every parameter gradient and the BN running
+    statistics must agree (fp64 atomics in the BN sums may reorder: bound 1e-6), dead branches included"""
+    planes = [32, 64, 64, 128, 128, 128, 256, 256, 256]
+    torch.manual_seed(3)
+    net = scn.FPN_Net([512] * 3, 3, ["xyz", "color", "normal"], 1, planes, nPlaneM=128, residual_blocks=True,
+                      fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
+                      downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8],
+                      rpn_map_sizes=[[32] * 3, [16] * 3, [8] * 3, [4] * 3], voxel_scale=50,
+                      rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95, track_running_stats=False).cuda().train()
+    rng = np.random.RandomState(5)
+    pts = rng.rand(30000, 3) * [400, 300, 1]
+    pts[:, 2] = rng.randint(0, 3, 30000) * 40 + 10
+    pts[10000:20000, 0] = rng.randint(0, 4, 10000) * 100 + 5          # walls
+    pts[10000:20000, 2] = rng.rand(10000) * 120
+    locs = torch.from_numpy(np.concatenate([pts, np.zeros((30000, 1))], 1)).long()
+    feats = torch.randn(30000, 9).cuda()
+    state0 = {k: v.clone() for k, v in net.state_dict().items()}
+    res = {}
+    for mode in (True, False):
+        net.load_state_dict(state0)
+        net.use_layer_graph = mode
+        net.zero_grad(set_to_none=True)
+        x = feats.clone().requires_grad_(True)
+        rpn, roi = net([locs, x])
+        assert (net._layer_graph() is not None) and mode or not mode
+        w = [torch.full_like(m.features, 0.5 + 0.1 * i) for i, m in enumerate(list(rpn) + list(roi))]
+        sum((m.features * wi).sum() + (m.features ** 2).sum() for m, wi in zip(list(rpn) + list(roi), w)).backward()
+        res[mode] = ([m.features.detach().clone() for m in list(rpn) + list(roi)], x.grad.clone(),
+                     {k: (None if p.grad is None else p.grad.clone()) for k, p in net.named_parameters()},
+                     {k: v.clone() for k, v in net.state_dict().items() if "running_" in k})
+    net.use_layer_graph = True
+    (fa, xa, ga, ra), (fb, xb, gb, rb) = res[True], res[False]
+    for a, b in zip(fa, fb):
+        assert rel(a, b) <= 1e-6
+    assert rel(xa, xb) <= 1e-6
+    n_live = 0
+    for k in gb:
+        if gb[k] is None or float(gb[k].abs().max()) == 0.0:
+            assert ga[k] is None or float(ga[k].abs().max()) == 0.0, k
+        else:
+            assert ga[k] is not None, k
+            assert rel(ga[k], gb[k]) <= 1e-6, k
+            n_live += 1
+    assert n_live > 60
+    for k in rb:
+        assert rel(ra[k], rb[k]) <= 1e-6, k
