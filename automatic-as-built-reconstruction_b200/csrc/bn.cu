@@ -44,6 +44,7 @@ k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
   float4 mu = make_float4(0, 0, 0, 0);
   if (BWD) mu = reinterpret_cast<const float4 *>(mean)[cq];
   if (rs < rpb) {
+#pragma unroll 4   // independent 128-bit loads of 4 row slots in flight per thread
     for (long long r = (long long)blockIdx.x * rpb + rs; r < n; r += (long long)gridDim.x * rpb) {
       const long long o = r * qpr + cq;
       const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + o);
@@ -257,7 +258,7 @@ static bool vec_ok(long long n, int C, const void *a, const void *b, const void 
 
 static int stats_grid(long long n, int rows_per_iter) {
   long long g = (n + (long long)rows_per_iter * 4 - 1) / ((long long)rows_per_iter * 4);
-  const long long cap = (long long)num_sms() * 2;
+  const long long cap = (long long)num_sms() * 4;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;

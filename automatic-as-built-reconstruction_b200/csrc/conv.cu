@@ -295,11 +295,12 @@ k_dw_partial(const float *__restrict__ X, const float *__restrict__ dY,
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int ci0 = blockIdx.y * CI, co0 = blockIdx.z * CO;
   long long start;
-  int len;
+  int len, out_slot = blockIdx.x;
   if (work) {
     const DwWork w = work[blockIdx.x];
     start = w.start;
     len = w.len;
+    out_slot = w.slot;
   } else {
     start = (long long)blockIdx.x * ident_chunk;
     len = (int)min((long long)ident_chunk, ident_n - start);
@@ -351,7 +352,7 @@ k_dw_partial(const float *__restrict__ X, const float *__restrict__ dY,
     }
     __syncthreads();
   }
-  float *out = partial + (long long)blockIdx.x * Cin * Cout;
+  float *out = partial + (long long)out_slot * Cin * Cout;
 #pragma unroll
   for (int i = 0; i < TI; ++i) {
     const int ci = ci0 + ty * TI + i;

@@ -122,24 +122,36 @@ __device__ __forceinline__ float to_tf32(float x) {
 // ---------------------------------------------------------------------------------------------
 // the gather-GEMM kernel
 // ---------------------------------------------------------------------------------------------
-#ifdef SCN_EXPERIMENT_TRACE
+#if defined(SCN_EXPERIMENT_TRACE) || defined(SCN_EXPERIMENT_TRACE_DW)
 // per-role clock64 trace of CTA 0 (developer experiment, tools/gemm_trace.py): role r appends to g_trace[r]
 __device__ unsigned long long g_trace[5][8192];
 __device__ int g_trace_n[5];
-#define SCN_TRACE(role, tag)                                                                      \
+#define SCN_TRACE_(role, tag)                                                                     \
   do {                                                                                            \
     if (blockIdx.x == 0) {                                                                        \
       const int _i = g_trace_n[role];                                                             \
       if (_i < 8190) { g_trace[role][_i] = ((unsigned long long)(tag) << 56) | (clock64() & 0xffffffffffffffull); g_trace_n[role] = _i + 1; } \
     }                                                                                             \
   } while (0)
+#endif
+#ifdef SCN_EXPERIMENT_TRACE
+#define SCN_TRACE(role, tag) SCN_TRACE_(role, tag)
 #else
 #define SCN_TRACE(role, tag) do { } while (0)
 #endif
+#ifdef SCN_EXPERIMENT_TRACE_DW
+#define SCN_TRACE_DW(role, tag) SCN_TRACE_(role, tag)
+#else
+#define SCN_TRACE_DW(role, tag) do { } while (0)
+#endif
 constexpr int MS = 3;                        // tile-metadata slots (producers may run ~2 tiles ahead of the epilogue)
 constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) / B (weight slices)
-constexpr int NT_P = 352;                    // 11 warps: 4 gather, MMA, weight loader, 4 epilogue, metadata loader
-constexpr int NT_P3 = 480;                   // 3xTF32 mode: + 4 converter warps (low-order halves of the gathered rows)
+// warp roles: 0-7 gather (one warp issues its cp.async chain at ~105 cycles per copy, so the ISSUE rate of
+// four warps bounded the step - tools/gemm_trace.py, dw_trace.py), 8 MMA, 9 weight loader, 10 metadata
+// loader, 11 idle, 12-15 epilogue (TMEM lanes 32*(warp%4)), 16-19 converters (3xTF32 only)
+constexpr int GP_W = 8, MMA_W = 8, WL_W = 9, META_W = 10, EPI_W = 12, CONV_W = 16;
+constexpr int NT_P = 16 * 32;
+constexpr int NT_P3 = 20 * 32;
 constexpr int NLO = 2;                       // stages of low-order halves (3xTF32 mode)
 
 struct Smem {
@@ -245,7 +257,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 
   if (tid == 0) {
     for (int i = 0; i < NSA; ++i) {
-      mbar_init(bar_fullA + i * 8, 128);
+      mbar_init(bar_fullA + i * 8, GP_W * 32);
       mbar_init(bar_emptyA + i * 8, 1);
     }
     for (int i = 0; i < NSB; ++i) {
@@ -254,7 +266,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     }
     for (int i = 0; i < MS; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
-      mbar_init(bar_mempty + i * 8, X3 ? 14 : 10);   // 4 producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
+      mbar_init(bar_mempty + i * 8, GP_W + 6 + (X3 ? 4 : 0));   // producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
     }
     if (X3)
       for (int i = 0; i < NLO; ++i) {
@@ -273,7 +285,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 10) {
+  if (warp == META_W) {
     // ===== metadata loader =====
     // Work items are handed out dynamically (one atomic per item on the launch's counter), heaviest
     // tiles first: rows are sorted by neighbour mask, so the tiles with the most active offsets sit at
@@ -327,9 +339,10 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         }
       }
     }
-  } else if (warp < 4) {
-    // ===== A producers: thread (j = k-core, rows r0 + 16 i) =====
+  } else if (warp < GP_W) {
+    // ===== A producers: thread (j = k-core, rows r0 + 32 i) =====
     const int j = tid & 7, r0 = tid >> 3;
+    constexpr int RSTEP = GP_W * 4;          // rows covered by one pass of the producer threads
     int g = 0;                               // global step counter of this CTA
     for (int it = 0;; ++it) {
       const int slot = it % MS;
@@ -354,9 +367,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const uint32_t dst = a_base + stage * A_STAGE + (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4);
           const float *colp = X + c * KC + j * 4;
 #pragma unroll
-          for (int i = 0; i < TILE_M / 16; ++i) {
-            const int idx = sIdx[e][r0 + 16 * i];     // rows r0 + 16 i share r0 % 8
-            cp_async_16(dst + i * 2048, colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
+          for (int i = 0; i < TILE_M / RSTEP; ++i) {
+            const int idx = sIdx[e][r0 + RSTEP * i];  // rows r0 + RSTEP i share r0 % 8
+            cp_async_16(dst + i * (RSTEP * 128), colp + (long long)(idx < 0 ? 0 : idx) * Kd, idx < 0 ? 0 : 16);
           }
         }
         // the stage's barrier completes when every producer thread has passed here AND its copies have
@@ -368,7 +381,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       __syncwarp();                           // the tile's lists are no longer needed by this warp
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_W) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
@@ -424,7 +437,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         ++accn;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == WL_W) {
     // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
     if (lane == 0) {
       int g = 0;
@@ -460,11 +473,11 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         mbar_arrive(bar_mempty + slot * 8);
       }
     }
-  } else if (warp >= 11) {
+  } else if (warp >= CONV_W) {
     // ===== converters (3xTF32 only): lo = x - (x & ~0x1fff) of every landed stage, same swizzled
     // positions, into the low-order ring; generic-proxy writes are fenced for the tensor core =====
     if (X3) {
-      const int ct = tid - 11 * 32;
+      const int ct = tid - CONV_W * 32;
       int g = 0;
       for (int it = 0;; ++it) {
         const int slot = it % MS;
@@ -496,8 +509,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         }
       }
     }
-  } else {
-    // ===== epilogue (warps 6-9): TMEM lanes 32*(warp%4).. -> registers -> global =====
+  } else if (warp >= EPI_W && warp < EPI_W + 4) {
+    // ===== epilogue (warps 12-15): TMEM lanes 32*(warp%4).. -> registers -> global =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int accn = 0;
@@ -511,7 +524,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       int orow = meta_perm(slot)[row];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
-      if (warp == 6 && lane == 0) SCN_TRACE(3, 1);
+      if (warp == EPI_W && lane == 0) SCN_TRACE(3, 1);
       const float *bs = bias ? bias + col0 : nullptr;
       float *yp = Y + (long long)(orow < 0 ? 0 : orow) * ldn + col0;
       if (splits > 1) {                     // partial tile, slot order, no bias
@@ -524,7 +537,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         mbar_wait(bar_tfull + acc * 8, (accn >> 1) & 1);
         tc_fence_after();
       }
-      if (warp == 6 && lane == 0) SCN_TRACE(3, 2);
+      if (warp == EPI_W && lane == 0) SCN_TRACE(3, 2);
       const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
@@ -593,7 +606,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         }
       }
       if (steps > 0) ++accn;
-      if (warp == 6 && lane == 0) SCN_TRACE(3, 3);
+      if (warp == EPI_W && lane == 0) SCN_TRACE(3, 3);
     }
   }
   tc_fence_before();
@@ -848,8 +861,11 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
 namespace tc {
 
 constexpr int DW_NPS = 8;          // pair-list slots
-constexpr int NT_DW = 192;         // 4 gather/epilogue warps, MMA warp, pair-list loader warp
-constexpr int NT_DW3 = 320;        // 3xTF32 mode: + 4 converter warps
+constexpr int DW_PW = 8;                       // producer (gather) warps; warps 0-3 also run the epilogue
+constexpr int DW_MMA_W = DW_PW, DW_LOAD_W = DW_PW + 1, DW_CONV_W = DW_PW + 2;
+constexpr int NT_DW = (DW_PW + 2) * 32;        // + MMA warp + pair-list loader warp
+constexpr int DW_CW = 8;                       // converter warps (3xTF32 mode)
+constexpr int NT_DW3 = (DW_PW + 2 + DW_CW) * 32;
 
 __device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return make_desc(saddr, lbo, sbo) | (1ull << 61);   // layout_type 1 = SWIZZLE_128B_BASE32B
@@ -898,11 +914,12 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   const uint32_t sbo_a = MA * 512, sbo_b = CB * 512;
 
   long long start;
-  int len;
+  int len, out_slot = blockIdx.x;
   if (work) {
     const DwWork w = work[blockIdx.x];
     start = w.start;
     len = w.len;
+    out_slot = w.slot;                               // launch order != partial order (ensure_dw_work)
   } else {
     start = (long long)blockIdx.x * ident_chunk;
     len = (int)min((long long)ident_chunk, ident_n - start);
@@ -920,17 +937,17 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   }
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(bar_full + i * 8, 128);
+      mbar_init(bar_full + i * 8, DW_PW * 32);
       mbar_init(bar_empty + i * 8, 1);
     }
     for (int i = 0; i < DW_NPS; ++i) {
       mbar_init(bar_pfull + i * 8, 1);
-      mbar_init(bar_pempty + i * 8, 4);
+      mbar_init(bar_pempty + i * 8, DW_PW);
     }
     mbar_init(bar_done, 1);
     if (X3)
       for (int i = 0; i < NLO; ++i) {
-        mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
+        mbar_init(bar_fullL + i * 8, DW_CW);     // one arrival per converter warp
         mbar_init(bar_emptyL + i * 8, 1);
       }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -942,7 +959,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == DW_LOAD_W) {
     // ===== pair-list loader: lane l carries pairs l and l+32 of a step, 4 steps ahead in registers =====
     auto load_pair = [&](int st, int i) -> int2 {
       const int p = st * KP + i;
@@ -963,6 +980,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
         if (st < steps) {
           const int slot = st % DW_NPS, use = st / DW_NPS;
           if (use > 0) mbar_wait(bar_pempty + slot * 8, (use - 1) & 1);
+          if (lane == 0) SCN_TRACE_DW(0, 1);
           if (lane < KP) sPairs[slot * KP + lane] = ra[u];
           if (KP > 32) sPairs[slot * KP + lane + 32] = rb[u];
           ra[u] = load_pair(st + 4, lane);
@@ -972,68 +990,84 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
         }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < DW_PW) {
     // ===== operand producers =====
     const int j8 = tid & 7, p4 = (tid >> 3) & 3;
     // byte offset of this thread's 16-byte piece inside an atom: row p4, 32B chunk (j8/2)^p4, half j8&1
     const uint32_t piece = p4 * 128 + ((((uint32_t)j8 >> 1) ^ (uint32_t)p4) << 5) + (j8 & 1) * 16;
+    const int ca_sh = __ffs(CA) - 1, cb_sh = __ffs(CB) - 1;
+    const float *Xl = X + j8 * 4, *Yl = dY + j8 * 4;
     for (int st = 0; st < steps; ++st) {
       const int stage = st % NSTAGE, use = st / NSTAGE;
       const int slot = st % DW_NPS;
       mbar_wait(bar_pfull + slot * 8, (st / DW_NPS) & 1);
+      if (tid == 0) SCN_TRACE_DW(1, 1);
       if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+      if (tid == 0) SCN_TRACE_DW(1, 2);
       const int2 *sp = sPairs + slot * KP;
       const uint32_t sa = a_base + stage * L.a_stage + piece, sb = b_base + stage * L.b_stage + piece;
-      for (int c = warp; c < KA * CA; c += 4) {
-        const int ka = c / CA, mi = c - ka * CA;
+      // CA, CB are powers of two (host check): shifts instead of divisions, and a 4-way unroll so that the
+      // pair load -> address -> cp.async chains of consecutive pieces overlap (one chain at a time made the
+      // ISSUE of a step's 16 copies take 1.2 us - the kernel's bottleneck, tools/dw_trace.py)
+#pragma unroll 4
+      for (int c = warp; c < (KA << ca_sh); c += DW_PW) {
+        const int ka = c >> ca_sh, mi = c & (CA - 1);
         const int2 pr = sp[ka * 4 + p4];
         const int xi = xcol ? pr.y : pr.x;
-        cp_async_16(sa + ka * sbo_a + mi * 512, X + (long long)(xi < 0 ? 0 : xi) * Cin + mi * 32 + j8 * 4, xi < 0 ? 0 : 16);
+        cp_async_16(sa + ka * sbo_a + mi * 512, Xl + (size_t)((unsigned)max(xi, 0) * (unsigned)Cin + mi * 32), xi < 0 ? 0 : 16);
       }
-      for (int c = warp; c < KA * CB; c += 4) {
-        const int ka = c / CB, ni = c - ka * CB;
+#pragma unroll 4
+      for (int c = warp; c < (KA << cb_sh); c += DW_PW) {
+        const int ka = c >> cb_sh, ni = c & (CB - 1);
         const int2 pr = sp[ka * 4 + p4];
         const int yi = ycol ? pr.y : pr.x;
-        cp_async_16(sb + ka * sbo_b + ni * 512, dY + (long long)(yi < 0 ? 0 : yi) * Cout + ni * 32 + j8 * 4, yi < 0 ? 0 : 16);
+        cp_async_16(sb + ka * sbo_b + ni * 512, Yl + (size_t)((unsigned)max(yi, 0) * (unsigned)Cout + ni * 32), yi < 0 ? 0 : 16);
       }
       cp_async_mbar_arrive(bar_full + stage * 8);   // completes when this thread's copies have landed
       mbar_arrive(bar_full + stage * 8);
+      if (tid == 0) SCN_TRACE_DW(1, 3);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pempty + slot * 8);
     }
-  } else if (warp == 4) {
+  } else if (warp == DW_MMA_W) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, Cout, 1, 1);
       for (int st = 0; st < steps; ++st) {
         const int stage = st % NSTAGE, use = st / NSTAGE;
         mbar_wait(bar_full + stage * 8, use & 1);
+        SCN_TRACE_DW(2, 1);
         const int stl = st % NLO;
         if (X3) mbar_wait(bar_fullL + stl * 8, (st / NLO) & 1);
         tc_fence_after();
         const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
         const uint32_t la = a_base + (NSTAGE + stl) * L.a_stage, lb = b_base + (NSTAGE + stl) * L.b_stage;
+        // descriptors differ only in the start address (bits 0-13, 16-byte units; the stages lie below
+        // 256 KB, so adding to the low word never carries into the next field)
+        uint64_t bd = make_desc_b32(sb, 512, sbo_b), bl = make_desc_b32(lb, 512, sbo_b);
+        uint64_t ad0 = make_desc_b32(sa, 512, sbo_a), al0 = make_desc_b32(la, 512, sbo_a);
+        const uint64_t da = (2 * sbo_a) >> 4, db = (2 * sbo_b) >> 4, dh = (4 * 512) >> 4;
+#pragma unroll 2
         for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
-          const uint64_t bd = make_desc_b32(sb + kb * 2 * sbo_b, 512, sbo_b);
-          const uint64_t bl = make_desc_b32(lb + kb * 2 * sbo_b, 512, sbo_b);
           for (int h = 0; h < halves; ++h) {
-            const uint64_t ad = make_desc_b32(sa + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
+            const uint64_t ad = ad0 + h * dh;
             mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
             if (X3) {   // + lo(x) * dy + x * lo(dy)
-              const uint64_t al = make_desc_b32(la + kb * 2 * sbo_a + h * 4 * 512, 512, sbo_a);
-              mma_tf32(tmem_d + (uint32_t)(h * Cout), al, bd, idesc, 1u);
+              mma_tf32(tmem_d + (uint32_t)(h * Cout), al0 + h * dh, bd, idesc, 1u);
               mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bl, idesc, 1u);
             }
           }
+          ad0 += da; al0 += da; bd += db; bl += db;
         }
         tc_commit(bar_empty + stage * 8);            // one commit per step (the converters wait on it too)
+        SCN_TRACE_DW(2, 2);
       }
       if (steps > 0) tc_commit(bar_done);
     }
   }
-  if (X3 && warp >= 6) {
+  if (X3 && warp >= DW_CONV_W) {
     // ===== converters (3xTF32): low-order halves of both operand stages, same positions =====
-    const int ct = tid - 6 * 32;
+    const int ct = tid - DW_CONV_W * 32;
     const int a16 = L.a_stage >> 4, b16 = L.b_stage >> 4;
     for (int st = 0; st < steps; ++st) {
       const int stage = st % NSTAGE, stl = st % NLO;
@@ -1049,10 +1083,10 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       };
       const float4 *srca = reinterpret_cast<const float4 *>(smem + L.a + stage * L.a_stage);
       float4 *dsta = reinterpret_cast<float4 *>(smem + L.a + (NSTAGE + stl) * L.a_stage);
-      for (int i = ct; i < a16; i += 128) dsta[i] = lo4(srca[i]);
+      for (int i = ct; i < a16; i += DW_CW * 32) dsta[i] = lo4(srca[i]);
       const float4 *srcb = reinterpret_cast<const float4 *>(smem + L.b + stage * L.b_stage);
       float4 *dstb = reinterpret_cast<float4 *>(smem + L.b + (NSTAGE + stl) * L.b_stage);
-      for (int i = ct; i < b16; i += 128) dstb[i] = lo4(srcb[i]);
+      for (int i = ct; i < b16; i += DW_CW * 32) dstb[i] = lo4(srcb[i]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_fullL + stl * 8);
@@ -1064,7 +1098,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       mbar_wait(bar_done, 0);
       tc_fence_after();
     }
-    float *out = partial + (long long)blockIdx.x * Cin * Cout;
+    float *out = partial + (long long)out_slot * Cin * Cout;
     for (int h = 0; h < halves; ++h) {
       const int ci = h * 128 + warp * 32 + lane;
       for (int c0 = 0; c0 < Cout; c0 += 32) {
@@ -1095,7 +1129,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
 
 // partial[w] (w < n_work) = X[rows]^T @ dY[rows] over the pairs of work item w.  >0: shape not handled.
 }  // namespace scn
-#ifdef SCN_EXPERIMENT_TRACE
+#if defined(SCN_EXPERIMENT_TRACE) || defined(SCN_EXPERIMENT_TRACE_DW)
 extern "C" int scn_debug_trace_read(unsigned long long *out, int *counts, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, scn::tc::g_trace, sizeof(unsigned long long) * 5 * 8192);
@@ -1121,6 +1155,7 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32) return 1;
   const bool x3 = precision == SCN_PRECISION_FP32_3XTF32;
   if (Cin < 32 || Cin % 32 || (Cin > 128 && Cin != 256) || Cout < 32 || Cout % 32 || Cout > 256) return 1;
+  if (((Cin >> 5) & ((Cin >> 5) - 1)) || ((Cout >> 5) & ((Cout >> 5) - 1))) return 1;   // 32-channel atoms: power of two
   if (!al(X) || !al(dY) || !al(partial)) return 1;
   const int MA = Cin > 128 ? Cin >> 5 : 4, NA = Cout >> 5;
   int KP = (MA + NA) <= 5 ? 64 : 32;
