@@ -92,6 +92,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
+// A operand from tensor memory (row i of A in TMEM lane i, the K = 8 values in 8 consecutive columns)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start>>4 [0,14),
@@ -152,7 +172,17 @@ constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) /
 constexpr int GP_W = 8, MMA_W = 8, WL_W = 9, META_W = 10, EPI_W = 12, CONV_W = 16;
 constexpr int NT_P = 16 * 32;
 constexpr int NT_P3 = 20 * 32;
-constexpr int NLO = 2;                       // stages of low-order halves (3xTF32 mode)
+constexpr int NLO = 2;                       // stages of low-order halves (3xTF32 mode, weight-gradient kernel: shared memory)
+// 3xTF32 gather-GEMM: the low-order halves of the gathered rows live in TENSOR MEMORY (row r in lane r, the
+// 32 values of a step in 32 columns; tools/tmem_a_probe.cu) and feed tcgen05.mma as its A operand from there.
+// Against a shared-memory side ring this frees 32 KB (a third weight stage: the weight ring's depth bounded
+// the step) and a quarter of the step's shared-memory traffic.
+#ifndef SCN_X3_LO_SMEM
+constexpr bool LO_TMEM = true;
+#else
+constexpr bool LO_TMEM = false;
+#endif
+constexpr int LO_COLS = 128;                 // TMEM columns reserved for the low-order stages (4 x 32)
 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
@@ -160,12 +190,12 @@ struct Smem {
   __host__ __device__ Smem(int N, int K, int nsa, int nsb, int x3) {
     a = 0;
     alo = a + nsa * A_STAGE;                // 3xTF32: NLO stages of low-order halves
-    b = alo + (x3 ? NLO * A_STAGE : 0);
+    b = alo + ((x3 && !LO_TMEM) ? NLO * A_STAGE : 0);
     stage = b + nsb * NCORE * N * 16 * (x3 ? 2 : 1);    // 3xTF32: a weight stage = hi slice + lo slice
     meta = stage + 4 * 4096;                // 4 epilogue warps x 4 KB transpose tiles
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
     bars = meta + MS * meta_bytes;
-    tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4 + 2 * NLO) * 8;
+    tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4 + 4) * 8;
     total = tmem_slot + 16;
   }
 };
@@ -237,7 +267,6 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   const uint32_t bar_tfull = bar_mempty + MS * 8;
   const uint32_t bar_tempty = bar_tfull + 2 * 8;
   const uint32_t bar_fullL = bar_tempty + 2 * 8;
-  const uint32_t bar_emptyL = bar_fullL + NLO * 8;
   const uint32_t alo_base = smem_u32(smem + L.alo);
   const int B_SLICE = NCORE * N * 16;               // one packed weight slice (hi or lo)
   const int B_STAGE = X3 ? 2 * B_SLICE : B_SLICE;
@@ -269,17 +298,17 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       mbar_init(bar_mempty + i * 8, GP_W + 6 + (X3 ? 4 : 0));   // producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
     }
     if (X3)
-      for (int i = 0; i < NLO; ++i) {
-        mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
-        mbar_init(bar_emptyL + i * 8, 1);
-      }
+      for (int i = 0; i < 4; ++i) mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
       mbar_init(bar_tempty + i * 8, 4);      // 4 epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
+  // accumulators: 2 x acc_cols; 3xTF32 with the low-order halves in TMEM: the whole 512 columns
+  const uint32_t tmem_cols = (X3 && LO_TMEM) ? 512u : 2 * acc_cols;
+  constexpr int NLT = LO_TMEM ? (NSA >= 4 ? 4 : 2) : NLO;      // low-order stages (never deeper than the A ring)
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -406,8 +435,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const int stb = g % NSB, useb = g / NSB;
           mbar_wait(bar_fullB + stb * 8, useb & 1);
           mbar_wait(bar_fullA + stage * 8, use & 1);
-          const int stl = g % NLO;
-          if (X3) mbar_wait(bar_fullL + stl * 8, (g / NLO) & 1);
+          const int stl = g % NLT;
+          if (X3) mbar_wait(bar_fullL + stl * 8, (g / NLT) & 1);
           tc_fence_after();
           if (lst == 0) SCN_TRACE(2, 3);
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
@@ -422,7 +451,11 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
             mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
                      (lst > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
-              mma_tf32(tmem_d, make_desc_sw128(sl + kk * 32), make_desc_sw128(sb + kk * 32), idesc, 1u);
+              if (LO_TMEM)
+                mma_tf32_ts(tmem_d, tmem_base + 2 * acc_cols + (uint32_t)(stl * KC + kk * 8), make_desc_sw128(sb + kk * 32),
+                            idesc, 1u);
+              else
+                mma_tf32(tmem_d, make_desc_sw128(sl + kk * 32), make_desc_sw128(sb + kk * 32), idesc, 1u);
               mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + B_SLICE + kk * 32), idesc, 1u);
             }
           }
@@ -488,22 +521,40 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
         for (int lst = 0; lst < steps; ++lst, ++g) {
-          const int stage = g % NSA, stl = g % NLO;
+          const int stage = g % NSA, stl = g % NLT;
           mbar_wait(bar_fullA + stage * 8, (g / NSA) & 1);
-          if (g >= NLO) mbar_wait(bar_emptyA + ((g - NLO) % NSA) * 8, ((g - NLO) / NSA) & 1);
-          const float4 *src = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE);
-          float4 *dst = reinterpret_cast<float4 *>(smem + L.alo + stl * A_STAGE);
+          if (g >= NLT) mbar_wait(bar_emptyA + ((g - NLT) % NSA) * 8, ((g - NLT) / NSA) & 1);
+          if (LO_TMEM) {
+            // thread = row ct: its 8 chunks (un-swizzled by index) -> lo -> 32 columns of TMEM lane ct
+            tc_fence_after();
+            const float4 *row = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE + (ct >> 3) * 1024 + (ct & 7) * 128);
+            uint32_t w[32];
 #pragma unroll
-          for (int u = 0; u < A_STAGE / 16 / 128; ++u) {
-            const float4 v = src[ct + u * 128];
-            float4 o;
-            o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-            dst[ct + u * 128] = o;
+            for (int jc = 0; jc < 8; ++jc) {
+              const float4 v = row[jc ^ (ct & 7)];
+              w[4 * jc + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+              w[4 * jc + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+              w[4 * jc + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+              w[4 * jc + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+            }
+            tmem_st32(tmem_base + 2 * acc_cols + (uint32_t)(stl * KC) + ((uint32_t)((warp & 3) * 32) << 16), w);
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            const float4 *src = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE);
+            float4 *dst = reinterpret_cast<float4 *>(smem + L.alo + stl * A_STAGE);
+#pragma unroll
+            for (int u = 0; u < A_STAGE / 16 / 128; ++u) {
+              const float4 v = src[ct + u * 128];
+              float4 o;
+              o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+              o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+              o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+              o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+              dst[ct + u * 128] = o;
+            }
+            fence_proxy_async();
           }
-          fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_fullL + stl * 8);
         }
@@ -611,7 +662,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 2 * acc_cols);
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
   if (tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {   // last CTA out: rearm the counters
     sched[0] = 0;
     sched[1] = 0;
@@ -772,9 +823,11 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   // slots (the gathers are latency-bound: depth = bytes in flight)
   const int b_stage = NCORE * NW * 16 * (x3 ? 2 : 1);
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
-  const int nsb = b_stage > 16384 ? 2 : 3;
+  // 3xTF32 with the low-order halves in TMEM: three weight stages (the weight ring is latency-bound: a TMA
+  // bulk copy takes ~1.2 us, so two 32 KB stages paced the step at 0.7 us)
+  const int nsb = (x3 && LO_TMEM) ? 3 : (b_stage > 16384 ? 2 : 3);
   const int budget = x3 ? 226 * 1024 : 218 * 1024;
-  const int nsa_fit = (budget - meta_total - 4 * 4096 - nsb * b_stage - (x3 ? NLO * A_STAGE : 0)) / A_STAGE;
+  const int nsa_fit = (budget - meta_total - 4 * 4096 - nsb * b_stage - ((x3 && !LO_TMEM) ? NLO * A_STAGE : 0)) / A_STAGE;
   const int depth = nsa_fit >= 8 ? 6 : (nsa_fit >= 6 ? 4 : (nsa_fit >= 4 ? 2 : 1));
   if (nsa_fit < 3) return 1;
   const Smem L(NW, K, depth + 2, nsb, x3);
