@@ -217,6 +217,37 @@ TileView make_view(const TileBook &tb, int k_flip) {
   return v;
 }
 
+// dst[r][0..cp) = src[r][0..c), zero beyond: narrow feature rows (the 9-channel stem input) padded to one
+// 32-channel slice so that they take the tensor-core kernels
+__global__ void k_pad_cols(const float *__restrict__ src, float *__restrict__ dst, long long rows, int c, int cp) {
+  const long long total = rows * cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cp;
+    const int j = (int)(i - r * cp);
+    dst[i] = j < c ? src[r * c + j] : 0.f;
+  }
+}
+// Wp[k][0..cp)[co] = W[k][0..c)[co], zero rows beyond
+__global__ void k_pad_w_rows(const float *__restrict__ W, float *__restrict__ Wp, int K, int c, int cp, int cout) {
+  const int total = K * cp * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / (cp * cout), r = i - k * cp * cout, ci = r / cout, co = r - ci * cout;
+    Wp[i] = ci < c ? W[((long long)k * c + ci) * cout + co] : 0.f;
+  }
+}
+constexpr int PAD_C = 32;
+static bool pad_ok(int Cin, int Cout, int precision) {
+  return precision != SCN_PRECISION_FP32 && Cin < PAD_C && Cout >= 16 && Cout % 16 == 0 && Cout <= 256;
+}
+static int pad_rows(const float *X, long long rows, int Cin, float **out, cudaStream_t s) {
+  SCN_TRY(workspace_t(out, WS_PAD_X, (size_t)rows * PAD_C, s));
+  long long blocks = (rows * PAD_C + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  k_pad_cols<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, s>>>(X, *out, rows, Cin, PAD_C);
+  SCN_LAUNCHED();
+  return 0;
+}
+
 // Y[stationary rows] = bias + sum_k X[partner_k] @ W[k]   (W: [K,Cin,Cout] row-major)
 int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
            const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip,
@@ -229,7 +260,14 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
                        4.0 * tb.K * Cin * Cout + (tb.identity ? 0.0 : 8.0 * tb.n_pairs);
   const double flops = 2.0 * tb.n_pairs * Cin * Cout;
   int r = 1;
-  if (precision != SCN_PRECISION_FP32)
+  if (!transpose_w && !tb.identity && pad_ok(Cin, Cout, precision)) {
+    float *xp = nullptr, *wp = nullptr;
+    SCN_TRY(pad_rows(X, tb.n_partner, Cin, &xp, s));
+    SCN_TRY(workspace_t(&wp, WS_PAD_W, (size_t)tb.K * PAD_C * Cout, s));
+    k_pad_w_rows<<<cdiv((long long)tb.K * PAD_C * Cout, 256), 256, 0, s>>>(W, wp, tb.K, Cin, PAD_C, Cout);
+    SCN_LAUNCHED();
+    r = osgemm_tc(xp, wp, bias, Y, PAD_C, Cout, tb.n_rows, tv, tb.K, precision, 0, s, bytes, flops, nullptr);
+  } else if (precision != SCN_PRECISION_FP32)
     r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s, bytes, flops, weight_tag);
   if (r > 0) {  // 0 = done, negative = -(error); positive = shape outside the tensor path (e.g. Cin = 9)
     float *wt = nullptr;
@@ -367,13 +405,15 @@ k_dw_partial(const float *__restrict__ X, const float *__restrict__ dY,
 
 struct KFirst { int v[MAX_K + 1]; };
 
+// cc = Cin*Cout elements of dW[k]; ccp = elements of one partial (Cin padded up for narrow inputs: the
+// first Cin rows of a partial are the real ones)
 __global__ void k_dw_reduce(const float *__restrict__ partial, float *__restrict__ dW, KFirst first,
-                            int cc /* Cin*Cout */) {
+                            int cc /* Cin*Cout */, int ccp) {
   const int k = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cc) return;
   float s = 0.f;
-  for (int w = first.v[k]; w < first.v[k + 1]; ++w) s += partial[(long long)w * cc + e];
+  for (int w = first.v[k]; w < first.v[k + 1]; ++w) s += partial[(long long)w * ccp + e];
   dW[(long long)k * cc + e] = s;
 }
 
@@ -429,11 +469,22 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
                           4.0 * K * cc + (rb->identity ? 0.0 : 8.0 * rb->total_pairs);
   const double dw_flops = 2.0 * rb->total_pairs * cc;
   float *partial = nullptr;
+  int ccp = cc;
   if (n_work > 0) {
-    SCN_TRY(workspace_t(&partial, WS_DW_PARTIAL, (size_t)n_work * cc, s));
     const int cmax = Cin < Cout ? Cout : Cin;
     int r = 1;
-    if (precision != SCN_PRECISION_FP32)
+    // narrow inputs (the 9-channel stem): X padded to 32 channels, tensor-core partials of 32 x Cout
+    if (!rb->identity && pad_ok(Cin, Cout, precision) && Cout % 32 == 0) {
+      float *xp = nullptr;
+      const long long xrows = xcol ? rb->n_out : rb->n_in;
+      SCN_TRY(pad_rows(X, xrows, Cin, &xp, s));
+      ccp = PAD_C * Cout;
+      SCN_TRY(workspace_t(&partial, WS_DW_PARTIAL, (size_t)n_work * ccp, s));
+      r = dw_partial_tc(xp, dY, pairs, work, partial, PAD_C, Cout, xcol, ycol, n_work, ident_n, ident_chunk, precision, s);
+      if (r > 0) ccp = cc;
+    }
+    if (r > 0) SCN_TRY(workspace_t(&partial, WS_DW_PARTIAL, (size_t)n_work * cc, s));
+    if (r > 0 && precision != SCN_PRECISION_FP32)
       r = dw_partial_tc(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, n_work, ident_n, ident_chunk, precision, s);
     if (r < 0) r = 1000;   // error already recorded
     else if (r == 0) r = 0;
@@ -443,7 +494,7 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
     if (r) return 1;
   }
   dim3 grid(cdiv(cc, 256), K);
-  k_dw_reduce<<<grid, 256, 0, s>>>(partial, dW, first, cc);
+  k_dw_reduce<<<grid, 256, 0, s>>>(partial, dW, first, cc, ccp);
   SCN_LAUNCHED();
   prof_end(PROF_DW, s, dw_bytes, dw_flops);
   return 0;
