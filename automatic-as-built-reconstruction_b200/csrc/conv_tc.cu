@@ -17,6 +17,7 @@
 // tf32 when packed.  Accumulation is fp32.
 #include "conv.cuh"
 #include "../../include/scn_b200.h"
+#include <cuda_bf16.h>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -111,6 +112,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
@@ -187,11 +203,13 @@ constexpr int LO_COLS = 128;                 // TMEM columns reserved for the lo
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
   int a, alo, b, stage, meta, meta_bytes, bars, tmem_slot, total;
-  __host__ __device__ Smem(int N, int K, int nsa, int nsb, int x3) {
+  // mode 0: tf32, 1: 3xTF32 (a weight stage = hi slice + lo slice), 2: bf16 (a weight stage = N x 32 bf16)
+  __host__ __device__ static int b_stage_bytes(int N, int mode) { return mode == 1 ? 2 * NCORE * N * 16 : (mode == 2 ? N * 64 : NCORE * N * 16); }
+  __host__ __device__ Smem(int N, int K, int nsa, int nsb, int mode) {
     a = 0;
-    alo = a + nsa * A_STAGE;                // 3xTF32: NLO stages of low-order halves
-    b = alo + ((x3 && !LO_TMEM) ? NLO * A_STAGE : 0);
-    stage = b + nsb * NCORE * N * 16 * (x3 ? 2 : 1);    // 3xTF32: a weight stage = hi slice + lo slice
+    alo = a + nsa * A_STAGE;                // 3xTF32 with the low-order halves in shared memory: NLO stages
+    b = alo + ((mode == 1 && !LO_TMEM) ? NLO * A_STAGE : 0);
+    stage = b + nsb * b_stage_bytes(N, mode);
     meta = stage + 4 * 4096;                // 4 epilogue warps x 4 KB transpose tiles
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
     bars = meta + MS * meta_bytes;
@@ -247,15 +265,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // stage into a 2-stage side ring; the MMA warp issues three instructions per K = 8 slice.  N is the
 // column width of a work item (<= 128 in X3 mode: wider outputs are split over work items), ldn the
 // row stride of Y.
-template <int DEPTH, bool X3>
-__global__ void __launch_bounds__(X3 ? NT_P3 : NT_P, 1)
+//
+// MODE 2 (bf16 operands, fp32 accumulation): the converter warps turn every landed stage into bf16 pairs in
+// tensor memory (row r -> lane r, 32 values -> 16 columns) and the MMA warp issues two kind::f16 instructions
+// (K = 16) per step with that A operand from TMEM; the weight stage is the no-swizzle K-major bf16 image
+// (core matrices of 8 rows x 16 B, N x 64 bytes per step) - layouts confirmed by tools/tmem_a_bf16_probe.cu.
+template <int DEPTH, int MODE>
+__global__ void __launch_bounds__(MODE ? NT_P3 : NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int ldn, int K, long long n_rows, TileView tb, uint32_t acc_cols,
               float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched) {
   // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Smem L(N, K, NSA, NSB, X3 ? 1 : 0);
+  constexpr bool X3 = MODE == 1, BF = MODE == 2, CONV = MODE != 0;
+  const Smem L(N, K, NSA, NSB, MODE);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_fullA = smem_u32(smem + L.bars);
@@ -269,7 +293,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   const uint32_t bar_fullL = bar_tempty + 2 * 8;
   const uint32_t alo_base = smem_u32(smem + L.alo);
   const int B_SLICE = NCORE * N * 16;               // one packed weight slice (hi or lo)
-  const int B_STAGE = X3 ? 2 * B_SLICE : B_SLICE;
+  const int B_STAGE = Smem::b_stage_bytes(N, MODE);
   const int item_stride = tb.n_tiles * splits;      // work items per column block
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = tb.n_tiles;
@@ -295,9 +319,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     }
     for (int i = 0; i < MS; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
-      mbar_init(bar_mempty + i * 8, GP_W + 6 + (X3 ? 4 : 0));   // producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
+      mbar_init(bar_mempty + i * 8, GP_W + 6 + (CONV ? 4 : 0));   // producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
     }
-    if (X3)
+    if (CONV)
       for (int i = 0; i < 4; ++i) mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
@@ -306,8 +330,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   // accumulators: 2 x acc_cols; 3xTF32 with the low-order halves in TMEM: the whole 512 columns
-  const uint32_t tmem_cols = (X3 && LO_TMEM) ? 512u : 2 * acc_cols;
-  constexpr int NLT = LO_TMEM ? (NSA >= 4 ? 4 : 2) : NLO;      // low-order stages (never deeper than the A ring)
+  const uint32_t tmem_cols = ((X3 && LO_TMEM) || BF) ? 512u : 2 * acc_cols;
+  constexpr int NLT = (LO_TMEM || BF) ? (NSA >= 4 ? 4 : 2) : NLO;      // low-order stages (never deeper than the A ring)
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -414,6 +438,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
+      // kind::f16, bf16 operands: D = f32 (bit 4), A = B = bf16 (1 at bits 7 and 10)
+      const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       int g = 0, accn = 0;
       for (int it = 0;; ++it) {
         const int slot = it % MS;
@@ -436,17 +462,25 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           mbar_wait(bar_fullB + stb * 8, useb & 1);
           mbar_wait(bar_fullA + stage * 8, use & 1);
           const int stl = g % NLT;
-          if (X3) mbar_wait(bar_fullL + stl * 8, (g / NLT) & 1);
+          if (CONV) mbar_wait(bar_fullL + stl * 8, (g / NLT) & 1);
           tc_fence_after();
           if (lst == 0) SCN_TRACE(2, 3);
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
           const uint32_t sl = alo_base + stl * A_STAGE;
+          if (BF) {
+            // A (bf16 pairs) from TMEM: 16 columns per step, 8 per K = 16 instruction; B: no-swizzle K-major,
+            // core matrices N*16 B apart along K (LBO), 8-row groups 128 B apart (SBO)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              mma_bf16_ts(tmem_d, tmem_base + 2 * acc_cols + (uint32_t)(stl * 16 + kk * 8),
+                          make_desc(sb + kk * 2 * N * 16, (uint32_t)N * 16, 128), idesc_bf, (lst > 0 || kk > 0) ? 1u : 0u);
+          }
 #pragma unroll
 #ifdef SCN_EXPERIMENT_NO_MMA     // timing experiment only (wrong results): one MMA per step instead of 4 / 12
           if (lst == 0) mma_tf32(tmem_d, make_desc_sw128(sa), make_desc_sw128(sb), idesc, 0u);
           for (int kk = 0; kk < 0; ++kk) {
 #else
-          for (int kk = 0; kk < KC / 8; ++kk) { // K = 8 per instruction: 32 bytes further along the 128-byte rows
+          for (int kk = 0; kk < (BF ? 0 : KC / 8); ++kk) { // K = 8 per instruction: 32 bytes further along the 128-byte rows
 #endif
             mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
                      (lst > 0 || kk > 0) ? 1u : 0u);
@@ -493,7 +527,12 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (g >= NSB) { mbar_arrive(bar_fullB + stage * 8); continue; }
 #endif
           mbar_expect_tx(bar_fullB + stage * 8, bytes);
-          if (X3) {   // slices [k][c][hi|lo][ldn][32]: rows col0 .. col0+N of the hi and of the lo slice
+          if (BF) {   // bf16 image [k][c][column block][core j][N][8]: one contiguous slice per (k, c, block)
+            const int ncb = ldn / N;
+            const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(Wp) +
+                                       (((long long)kw * kchunks + c) * ncb + col0 / N) * (long long)N * KC;
+            bulk_copy_g2s(b_base + stage * B_STAGE, src, bytes, bar_fullB + stage * 8);
+          } else if (X3) {   // slices [k][c][hi|lo][ldn][32]: rows col0 .. col0+N of the hi and of the lo slice
             const float *src = Wp + (((long long)kw * kchunks + c) * 2 * ldn + col0) * KC;
             bulk_copy_g2s(b_base + stage * B_STAGE, src, (uint32_t)B_SLICE, bar_fullB + stage * 8);
             bulk_copy_g2s(b_base + stage * B_STAGE + B_SLICE, src + (long long)ldn * KC, (uint32_t)B_SLICE,
@@ -509,7 +548,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   } else if (warp >= CONV_W) {
     // ===== converters (3xTF32 only): lo = x - (x & ~0x1fff) of every landed stage, same swizzled
     // positions, into the low-order ring; generic-proxy writes are fenced for the tensor core =====
-    if (X3) {
+    if (CONV) {
       const int ct = tid - CONV_W * 32;
       int g = 0;
       for (int it = 0;; ++it) {
@@ -524,7 +563,22 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const int stage = g % NSA, stl = g % NLT;
           mbar_wait(bar_fullA + stage * 8, (g / NSA) & 1);
           if (g >= NLT) mbar_wait(bar_emptyA + ((g - NLT) % NSA) * 8, ((g - NLT) / NSA) & 1);
-          if (LO_TMEM) {
+          if (BF) {
+            // thread = row ct: its 8 chunks (un-swizzled by index) -> 16 bf16 pairs -> 16 columns of TMEM lane ct
+            tc_fence_after();
+            const float4 *row = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE + (ct >> 3) * 1024 + (ct & 7) * 128);
+            uint32_t w[16];
+#pragma unroll
+            for (int jc = 0; jc < 8; ++jc) {
+              const float4 v = row[jc ^ (ct & 7)];
+              const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+              w[2 * jc] = *reinterpret_cast<const uint32_t *>(&p0);
+              w[2 * jc + 1] = *reinterpret_cast<const uint32_t *>(&p1);
+            }
+            tmem_st16(tmem_base + 2 * acc_cols + (uint32_t)(stl * 16) + ((uint32_t)((warp & 3) * 32) << 16), w);
+            tmem_st_wait();
+            tc_fence_before();
+          } else if (LO_TMEM) {
             // thread = row ct: its 8 chunks (un-swizzled by index) -> lo -> 32 columns of TMEM lane ct
             tc_fence_after();
             const float4 *row = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE + (ct >> 3) * 1024 + (ct & 7) * 128);
@@ -719,6 +773,29 @@ __global__ void k_pack_weights_both(const float *__restrict__ W, float *__restri
   }
 }
 
+// bf16 operand images (mode 2): [k][chunk c][column block][core j = 4][NW rows][8 bf16] - the no-swizzle K-major
+// layout of tcgen05 (core matrix = 8 rows x 16 bytes), one contiguous NW x 32 slice per (k, c, column block);
+// NW = min(N, 128).  Forward image at Wf, dX image (W[k]^T) at Wb.
+__global__ void k_pack_weights_bf16(const float *__restrict__ W, __nv_bfloat16 *__restrict__ Wf, __nv_bfloat16 *__restrict__ Wb,
+                                    int K, int Cin, int Cout, int do_f, int do_b) {
+  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
+  for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
+       i2 += (long long)gridDim.x * blockDim.x) {
+    const int transpose = i2 >= total;
+    if (transpose ? !do_b : !do_f) continue;
+    const long long i = transpose ? i2 - total : i2;
+    const int k = (int)(i / per_k);
+    const long long r = i - (long long)k * per_k;
+    const int ci = (int)(r / Cout), co = (int)(r - (long long)ci * Cout);
+    const int kd = transpose ? co : ci, n = transpose ? ci : co;          // reduction index, operand row
+    const int Kd = transpose ? Cout : Cin, N = transpose ? Cin : Cout;
+    const int NW = N > 128 ? 128 : N, ncb = N / NW, kch = Kd / KC;
+    const int c = kd / KC, kin = kd % KC, j = kin >> 3, e = kin & 7, cb = n / NW, nb = n % NW;
+    const long long idx = (((((long long)k * kch + c) * ncb + cb) * 4 + j) * NW + nb) * 8 + e;
+    (transpose ? Wb : Wf)[idx] = __float2bfloat16(W[i]);
+  }
+}
+
 // Packed-operand cache, keyed by the caller's identity token of the weight tensor.
 struct PackEntry {
   int64_t token = 0, version = -1;
@@ -735,6 +812,7 @@ static uint64_t g_pack_clock = 0;
 static bool layout_ok(int Kd, int N) { return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256; }
 
 // returns the packed image for (transpose ? dX : forward), (re)building both when the version moved
+// mode: 0 tf32, 1 3xTF32 (hi + lo slices), 2 bf16
 static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int Cout, int transpose, int x3,
                        cudaStream_t s, float **out) {
   std::lock_guard<std::mutex> lk(g_pack_mu);
@@ -755,7 +833,7 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     g_pack.push_back(e);
   }
   const size_t total = (size_t)K * Cin * Cout;
-  const size_t image = total * (x3 ? 2 : 1);         // 3xTF32: hi and lo slices
+  const size_t image = x3 == 2 ? (total + 1) / 2 : total * (x3 ? 2 : 1);   // floats: bf16 halves, 3xTF32 doubles
   if (e->K != K || e->Cin != Cin || e->Cout != Cout || e->x3 != x3) {
     cudaFree(e->wf);
     e->wf = nullptr;
@@ -772,7 +850,11 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     e->has_b = layout_ok(Cout, Cin);
     int pb = cdiv(2 * (long long)total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
-    k_pack_weights_both<<<pb, 256, 0, s>>>(W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b, x3);
+    if (x3 == 2)
+      k_pack_weights_bf16<<<pb, 256, 0, s>>>(W, reinterpret_cast<__nv_bfloat16 *>(e->wf), reinterpret_cast<__nv_bfloat16 *>(e->wb),
+                                             K, Cin, Cout, e->has_f, e->has_b);
+    else
+      k_pack_weights_both<<<pb, 256, 0, s>>>(W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SCN_CUDA(cudaGetLastError());
     e->version = tag[1];
@@ -799,10 +881,11 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
               const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
               double prof_flops, const int64_t *weight_tag) {
   using namespace tc;
-  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32) return 1;
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
-  const int x3 = precision == SCN_PRECISION_FP32_3XTF32;
-  // 3xTF32: a work item covers <= 128 output columns (its weight stage holds a hi and a lo slice)
+  // kernel mode: 0 tf32, 1 3xTF32, 2 bf16
+  const int x3 = precision == SCN_PRECISION_FP32_3XTF32 ? 1 : (precision == SCN_PRECISION_BF16 ? 2 : 0);
+  // 3xTF32 / bf16: a work item covers <= 128 output columns (TMEM also holds converted A stages)
   const int ncb = (x3 && N > 128) ? N / 128 : 1;
   const int NW = N / ncb;
   if (NW * ncb != N || NW % 16) return 1;
@@ -813,21 +896,25 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     if (r) return r > 0 ? -1 : r;
   } else {
     const long long total = (long long)K * Kd * N;
-    if (workspace_t(&wp, WS_PACKED_W, (size_t)total * (x3 ? 2 : 1), s)) return -1;
+    if (workspace_t(&wp, WS_PACKED_W, (size_t)total * (x3 == 1 ? 2 : 1), s)) return -1;
     int pb = cdiv(2 * total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
-    k_pack_weights_both<<<pb, 256, 0, s>>>(W, wp, wp, K, cin, cout, !transpose_w, transpose_w, x3);
+    if (x3 == 2)
+      k_pack_weights_bf16<<<pb, 256, 0, s>>>(W, reinterpret_cast<__nv_bfloat16 *>(wp), reinterpret_cast<__nv_bfloat16 *>(wp), K,
+                                             cin, cout, !transpose_w, transpose_w);
+    else
+      k_pack_weights_both<<<pb, 256, 0, s>>>(W, wp, wp, K, cin, cout, !transpose_w, transpose_w, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   // ring depths: 2-3 weight-slice stages, then as many gathered-row stages as fit beside the metadata
   // slots (the gathers are latency-bound: depth = bytes in flight)
-  const int b_stage = NCORE * NW * 16 * (x3 ? 2 : 1);
+  const int b_stage = Smem::b_stage_bytes(NW, x3);
   const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
   // 3xTF32 with the low-order halves in TMEM: three weight stages (the weight ring is latency-bound: a TMA
   // bulk copy takes ~1.2 us, so two 32 KB stages paced the step at 0.7 us)
-  const int nsb = (x3 && LO_TMEM) ? 3 : (b_stage > 16384 ? 2 : 3);
+  const int nsb = x3 == 2 ? 4 : ((x3 && LO_TMEM) ? 3 : (b_stage > 16384 ? 2 : 3));
   const int budget = x3 ? 226 * 1024 : 218 * 1024;
-  const int nsa_fit = (budget - meta_total - 4 * 4096 - nsb * b_stage - ((x3 && !LO_TMEM) ? NLO * A_STAGE : 0)) / A_STAGE;
+  const int nsa_fit = (budget - meta_total - 4 * 4096 - nsb * b_stage - ((x3 == 1 && !LO_TMEM) ? NLO * A_STAGE : 0)) / A_STAGE;
   const int depth = nsa_fit >= 8 ? 6 : (nsa_fit >= 6 ? 4 : (nsa_fit >= 4 ? 2 : 1));
   if (nsa_fit < 3) return 1;
   const Smem L(NW, K, depth + 2, nsb, x3);
@@ -837,10 +924,12 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     auto setattr = [&](const void *f) {
       if (ae == cudaSuccess) ae = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     };
-    setattr((const void *)k_osgemm_tf32<1, false>); setattr((const void *)k_osgemm_tf32<2, false>);
-    setattr((const void *)k_osgemm_tf32<4, false>); setattr((const void *)k_osgemm_tf32<6, false>);
-    setattr((const void *)k_osgemm_tf32<1, true>);  setattr((const void *)k_osgemm_tf32<2, true>);
-    setattr((const void *)k_osgemm_tf32<4, true>);  setattr((const void *)k_osgemm_tf32<6, true>);
+    setattr((const void *)k_osgemm_tf32<1, 0>); setattr((const void *)k_osgemm_tf32<2, 0>);
+    setattr((const void *)k_osgemm_tf32<4, 0>); setattr((const void *)k_osgemm_tf32<6, 0>);
+    setattr((const void *)k_osgemm_tf32<1, 1>); setattr((const void *)k_osgemm_tf32<2, 1>);
+    setattr((const void *)k_osgemm_tf32<4, 1>); setattr((const void *)k_osgemm_tf32<6, 1>);
+    setattr((const void *)k_osgemm_tf32<1, 2>); setattr((const void *)k_osgemm_tf32<2, 2>);
+    setattr((const void *)k_osgemm_tf32<4, 2>); setattr((const void *)k_osgemm_tf32<6, 2>);
     if (ae != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(ae));
       return -1;
@@ -874,16 +963,21 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
 #define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
   k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, K, n_rows, tv, cols, ypart, \
                                                                 n_items, splits, nsb, sched)
-  if (x3) {
-    if (depth == 6) SCN_OSGEMM_LAUNCH(6, true);
-    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, true);
-    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, true);
-    else SCN_OSGEMM_LAUNCH(1, true);
+  if (x3 == 2) {
+    if (depth == 6) SCN_OSGEMM_LAUNCH(6, 2);
+    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, 2);
+    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, 2);
+    else SCN_OSGEMM_LAUNCH(1, 2);
+  } else if (x3 == 1) {
+    if (depth == 6) SCN_OSGEMM_LAUNCH(6, 1);
+    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, 1);
+    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, 1);
+    else SCN_OSGEMM_LAUNCH(1, 1);
   } else {
-    if (depth == 6) SCN_OSGEMM_LAUNCH(6, false);
-    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, false);
-    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, false);
-    else SCN_OSGEMM_LAUNCH(1, false);
+    if (depth == 6) SCN_OSGEMM_LAUNCH(6, 0);
+    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, 0);
+    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, 0);
+    else SCN_OSGEMM_LAUNCH(1, 0);
   }
 #undef SCN_OSGEMM_LAUNCH
   prof_end(PROF_GEMM, s, prof_bytes, prof_flops);
@@ -1205,7 +1299,8 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
                   int precision, cudaStream_t s) {
   using namespace tc;
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
-  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32) return 1;
+  // bf16 mode: the weight gradient runs on the single-pass tf32 kernel (both operands are gathered fp32 rows)
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 1;
   const bool x3 = precision == SCN_PRECISION_FP32_3XTF32;
   if (Cin < 32 || Cin % 32 || (Cin > 128 && Cin != 256) || Cout < 32 || Cout % 32 || Cout > 256) return 1;
   if (((Cin >> 5) & ((Cin >> 5) - 1)) || ((Cout >> 5) & ((Cout >> 5) - 1))) return 1;   // 32-channel atoms: power of two

@@ -23,13 +23,14 @@ lib = ctypes.CDLL(LIB_PATH)
 # include/scn_b200.h SCN_PRECISION_*.  "fp32" is the library's fp32 mode: 3xTF32 on the tcgen05 tensor
 # cores (hi/lo operand split, fp32 accumulation, error ~2^-20 relative - inside the 1e-4 parity bound),
 # with the exact FFMA tiles for the shapes the tensor path does not take (Cin = 9 stem).
-PRECISIONS = {"fp32_ffma": 0, "tf32": 1, "fp32": 2}
+# "bf16": forward / input-gradient contractions with bf16 operands (fp32 accumulation), weight gradient in tf32.
+PRECISIONS = {"fp32_ffma": 0, "tf32": 1, "fp32": 2, "bf16": 3}
 _precision = PRECISIONS[os.environ.get("SCN_B200_PRECISION", "fp32")]
 
 
 def set_conv_precision(name):
-    """'fp32' (3xTF32 on the tensor cores, fp32-accurate), 'fp32_ffma' (exact FFMA tiles everywhere) or
-    'tf32' (single-pass tf32 operands, fp32 accumulate)."""
+    """'fp32' (3xTF32 on the tensor cores, fp32-accurate), 'fp32_ffma' (exact FFMA tiles everywhere),
+    'tf32' (single-pass tf32 operands, fp32 accumulate) or 'bf16' (bf16 operands, fp32 accumulate)."""
     global _precision
     _precision = PRECISIONS[name]
 

@@ -348,7 +348,8 @@ def run_b200(args, rank, local_rank, world):
             "metric": "active_voxels_per_sec", "value": na_total / sec, "unit": "active voxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32 (3xTF32 on tcgen05, fp32 accumulate)", "fp32_ffma": "f32", "tf32": "tf32"}[args.precision],
+            "dtype": {"fp32": "f32 (3xTF32 on tcgen05, fp32 accumulate)", "fp32_ffma": "f32", "tf32": "tf32",
+                      "bf16": "bf16 (operands; fp32 accumulate, tf32 weight gradient)"}[args.precision],
             "data": "synthetic",
             "buildings_per_sec": args.batch * world / sec, "active_voxels_per_building": na_local / args.batch,
             "config": workload_config(args),
@@ -391,7 +392,7 @@ def main():
     ap.add_argument("--points", type=int, default=300000)
     ap.add_argument("--floors", type=int, default=1)
     ap.add_argument("--precision", default=os.environ.get("SCN_B200_PRECISION", "fp32"),
-                    choices=["fp32", "fp32_ffma", "tf32"])
+                    choices=["fp32", "fp32_ffma", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

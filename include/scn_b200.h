@@ -37,9 +37,12 @@ typedef struct scn_metadata scn_metadata_t;
 enum {
   SCN_PRECISION_FP32 = 0,   /* exact fp32 FFMA tiles (parity mode)                               */
   SCN_PRECISION_TF32 = 1,   /* tf32 operands on tcgen05 tensor cores, fp32 accumulators in TMEM  */
-  SCN_PRECISION_FP32_3XTF32 = 2 /* fp32 accuracy on the tensor cores: x = hi + lo, w = whi + wlo in tf32,
+  SCN_PRECISION_FP32_3XTF32 = 2, /* fp32 accuracy on the tensor cores: x = hi + lo, w = whi + wlo in tf32,
                                    hi*whi + lo*whi + hi*wlo accumulated in fp32 (error ~2^-20 relative);
                                    shapes the tensor path does not take use the exact FFMA tiles           */
+  SCN_PRECISION_BF16 = 3       /* forward / input-gradient contractions with bf16 operands (features rounded to
+                                   nearest, kind::f16 MMAs, A operand from tensor memory), fp32 accumulation;
+                                   the weight gradient runs in single-pass tf32                              */
 };
 
 /* ---- library ---------------------------------------------------------------------- */

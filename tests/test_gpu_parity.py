@@ -29,10 +29,13 @@ def rel(a, b):
 # tiles, same bound.  tf32: single-pass tcgen05 - operands carry a 10-bit mantissa (unit round-off
 # 2^-11 ~ 4.9e-4, features truncated / weights rounded), fp32 accumulation; stated tolerance per layer
 # 2e-3 of max|ref|, 1e-2 through the whole backbone.
-PREC_TOL = {"fp32": 1e-4, "fp32_ffma": 1e-4, "tf32": 2e-3}
+# bf16: forward / dX operands rounded to nearest bf16 (8-bit mantissa, unit round-off 2^-9 ~ 2e-3), fp32
+# accumulation, weight gradient in tf32; stated tolerance per layer 1e-2 of max|ref|, 5e-2 through the backbone.
+PREC_TOL = {"fp32": 1e-4, "fp32_ffma": 1e-4, "tf32": 2e-3, "bf16": 1e-2}
+REDUCED = ("tf32", "bf16")
 
 
-@pytest.fixture(scope="module", params=["fp32", "fp32_ffma", "tf32"])
+@pytest.fixture(scope="module", params=["fp32", "fp32_ffma", "tf32", "bf16"])
 def scn(request):
     import sparseconvnet
     sparseconvnet.set_conv_precision(request.param)
@@ -516,8 +519,8 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
     loss.backward()
     # tf32 truncates the gathered features (cp.async feeds them unconverted): a systematic -5e-4 per
     # product, ~2e-3 on this loss
-    assert abs(loss.item() - float(g["loss"])) <= (1e-2 if scn.PREC == "tf32" else 1e-4) * float(g["loss"])
-    feat_tol = scn.TOL * (5 if scn.PREC == "tf32" else 1)
+    assert abs(loss.item() - float(g["loss"])) <= (5 * scn.TOL if scn.PREC in REDUCED else 1e-4) * float(g["loss"])
+    feat_tol = scn.TOL * (5 if scn.PREC in REDUCED else 1)
     for i, m in enumerate(list(rpn) + list(roi)):
         loc = m.get_spatial_locations().numpy()
         assert (np.diff(loc[:, 3]) >= 0).all()
@@ -533,7 +536,7 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
             # ill-conditioned sums (BN shifts: sum of a masked gradient that mostly cancels) lose digits
             # in ANY finite precision - the reference's fp32 is itself 1.5e-2 off on the worst one
             tf32_bound = max(5e-1, 15 * ref_err)
-            assert rel(p.grad, truth64[k]) <= (tf32_bound if scn.PREC == "tf32" else 1e-4), (k, ref_err)
+            assert rel(p.grad, truth64[k]) <= (tf32_bound if scn.PREC in REDUCED else 1e-4), (k, ref_err)
             num += float((p.grad.detach().cpu().double() - truth64[k]).pow(2).sum())
             den += float(truth64[k].pow(2).sum())
             n += 1
@@ -542,7 +545,7 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
     assert n > 40
     # whole gradient vector: relative L2 error (tf32: individual ill-conditioned tensors vary with the
     # summation order between kernel versions, the vector as a whole does not)
-    assert (num / den) ** 0.5 <= (6e-2 if scn.PREC == "tf32" else 1e-4)
+    assert (num / den) ** 0.5 <= ({"tf32": 6e-2, "bf16": 3e-1}.get(scn.PREC, 1e-4))
     for k, v in net.state_dict().items():
         if "running_" in k and "after/" + k in g.files:
             assert rel(v, g["after/" + k]) <= feat_tol, k
