@@ -35,7 +35,7 @@ class Metadata_3(object):
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:          # `lib` is None while the interpreter shuts down
             lib.scn_metadata_destroy(h)
 
     # ---- reference methods used on the path -------------------------------------------

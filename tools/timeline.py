@@ -66,3 +66,18 @@ print("sum of kernel durations %.2f ms/step" % (S / N / 1e3))
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:26]:
     print("%-70s %5d %9.1f us/step %5.1f%%" % (k, v[0] // N, v[1] / N, 100 * v[1] / S))
 pf.close()
+
+# ---- idle gaps of the union timeline and busy time per stream -----------------------------------
+named = sorted((e.time_range.start, e.time_range.end, e.name.split("(")[0][:48],
+                getattr(e, "stream", None) if hasattr(e, "stream") else None) for e in ev)
+gaps, cur_e, last = [], None, None
+for s, e, nm, st in named:
+    if cur_e is not None and s > cur_e:
+        gaps.append((s - cur_e, last, nm, cur_e - named[0][0]))
+    if cur_e is None or e > cur_e:
+        cur_e, last = e, nm
+print("idle gaps: %d, total %.2f ms/step" % (len(gaps), sum(g[0] for g in gaps) / N / 1e3))
+for g in sorted(gaps, key=lambda g: -g[0])[:24]:
+    print("  %7.1f us at t=%8.1f us   after %-48s before %s" % (g[0], g[3], g[1], g[2]))
+hist = collections.Counter(min(int(g[0] // 5) * 5, 100) for g in gaps)
+print("gap histogram (us bucket: count/step):", {k: v // N for k, v in sorted(hist.items())})
