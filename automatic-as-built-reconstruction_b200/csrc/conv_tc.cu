@@ -180,7 +180,8 @@ __device__ int g_trace_n[5];
 #else
 #define SCN_TRACE_DW(role, tag) do { } while (0)
 #endif
-constexpr int MS = 3;                        // tile-metadata slots (producers may run ~2 tiles ahead of the epilogue)
+constexpr int MS = 3;                        // tile-metadata slots, at most (producers may run ~2 tiles ahead of the epilogue;
+                                             // heavy layers run with 2 when the third would cost a gathered-row stage)
 constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) / B (weight slices)
 // warp roles: 0-7 gather (one warp issues its cp.async chain at ~105 cycles per copy, so the ISSUE rate of
 // four warps bounded the step - tools/gemm_trace.py, dw_trace.py), 8 MMA, 9 weight loader, 10 metadata
@@ -205,14 +206,14 @@ struct Smem {
   int a, alo, b, stage, meta, meta_bytes, bars, tmem_slot, total;
   // mode 0: tf32, 1: 3xTF32 (a weight stage = hi slice + lo slice), 2: bf16 (a weight stage = N x 32 bf16)
   __host__ __device__ static int b_stage_bytes(int N, int mode) { return mode == 1 ? 2 * NCORE * N * 16 : (mode == 2 ? N * 64 : NCORE * N * 16); }
-  __host__ __device__ Smem(int N, int K, int nsa, int nsb, int mode) {
+  __host__ __device__ Smem(int N, int K, int nsa, int nsb, int mode, int ms) {
     a = 0;
     alo = a + nsa * A_STAGE;                // 3xTF32 with the low-order halves in shared memory: NLO stages
     b = alo + ((mode == 1 && !LO_TMEM) ? NLO * A_STAGE : 0);
     stage = b + nsb * b_stage_bytes(N, mode);
     meta = stage + 4 * 4096;                // 4 epilogue warps x 4 KB transpose tiles
     meta_bytes = K * TILE_M * 4 + TILE_M * 4 + 64;      // sIdx[K][128], sPerm[128], {nE, pad, sK[32]}
-    bars = meta + MS * meta_bytes;
+    bars = meta + ms * meta_bytes;
     tmem_slot = bars + (2 * NSA_MAX + 2 * NSB_MAX + 2 * MS + 4 + 4) * 8;
     total = tmem_slot + 16;
   }
@@ -270,16 +271,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // tensor memory (row r -> lane r, 32 values -> 16 columns) and the MMA warp issues two kind::f16 instructions
 // (K = 16) per step with that A operand from TMEM; the weight stage is the no-swizzle K-major bf16 image
 // (core matrices of 8 rows x 16 B, N x 64 bytes per step) - layouts confirmed by tools/tmem_a_bf16_probe.cu.
+// per-role stall accounting of CTA 0 (developer experiment, tools/gemm_stalls.py): cycles every warp's lane 0
+// spends inside each kind of mbarrier wait (0 metadata, 1 emptyA, 2 fullA, 3 fullB, 4 converted stage, 5 TMEM
+// accumulator) and, in slot 7, from kernel start to the end of its role
+#ifdef SCN_EXPERIMENT_STALLS
+__device__ long long g_stall[20][8];
+#define SCN_STALL_DECL long long stall_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long stall_t0_ = clock64()
+#define MBW(bar, parity, id) do { const long long t0_ = clock64(); mbar_wait(bar, parity); stall_[id] += clock64() - t0_; } while (0)
+#define SCN_STALL_T0 long long ts_ = clock64()
+#define SCN_STALL_ADD(id) do { const long long tn_ = clock64(); stall_[id] += tn_ - ts_; ts_ = tn_; } while (0)
+#define SCN_STALL_WRITE                                                                  \
+  do {                                                                                   \
+    stall_[7] = clock64() - stall_t0_;                                                   \
+    if (blockIdx.x == 0 && lane == 0)                                                    \
+      for (int i_ = 0; i_ < 8; ++i_) g_stall[warp][i_] = stall_[i_];                     \
+  } while (0)
+#else
+#define SCN_STALL_DECL do { } while (0)
+#define MBW(bar, parity, id) mbar_wait(bar, parity)
+#define SCN_STALL_T0 do { } while (0)
+#define SCN_STALL_ADD(id) do { } while (0)
+#define SCN_STALL_WRITE do { } while (0)
+#endif
 template <int DEPTH, int MODE>
 __global__ void __launch_bounds__(MODE ? NT_P3 : NT_P, 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int ldn, int K, long long n_rows, TileView tb, uint32_t acc_cols,
-              float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched) {
+              float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched, int ms) {
   // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool X3 = MODE == 1, BF = MODE == 2, CONV = MODE != 0;
-  const Smem L(N, K, NSA, NSB, MODE);
+  const Smem L(N, K, NSA, NSB, MODE, ms);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
   const uint32_t bar_fullA = smem_u32(smem + L.bars);
@@ -296,6 +319,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   const int B_STAGE = Smem::b_stage_bytes(N, MODE);
   const int item_stride = tb.n_tiles * splits;      // work items per column block
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SCN_STALL_DECL;
   const int n_tiles = tb.n_tiles;
   const int kchunks = Kd / KC;
 
@@ -317,7 +341,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       mbar_init(bar_fullB + i * 8, 1);
       mbar_init(bar_emptyB + i * 8, 1);
     }
-    for (int i = 0; i < MS; ++i) {
+    for (int i = 0; i < ms; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
       mbar_init(bar_mempty + i * 8, GP_W + 6 + (CONV ? 4 : 0));   // producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
     }
@@ -346,8 +370,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     // smsp__cycles_active vs sm__cycles_elapsed).  sched = {next item, CTAs done}; the last CTA to
     // finish resets both for the next launch on this stream.
     for (int it = 0;; ++it) {
-      const int slot = it % MS, use = it / MS;
-      if (use > 0) mbar_wait(bar_mempty + slot * 8, (use - 1) & 1);
+      const int slot = it % ms, use = it / ms;
+      if (use > 0) MBW(bar_mempty + slot * 8, (use - 1) & 1, 0);
       int q = 0;
       if (lane == 0) SCN_TRACE(0, 1);
       if (lane == 0) q = atomicAdd(sched, 1);
@@ -398,8 +422,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     constexpr int RSTEP = GP_W * 4;          // rows covered by one pass of the producer threads
     int g = 0;                               // global step counter of this CTA
     for (int it = 0;; ++it) {
-      const int slot = it % MS;
-      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      const int slot = it % ms;
+      MBW(bar_mfull + slot * 8, (it / ms) & 1, 0);
       const int item = meta_hdr(slot)[1];
       if (item < 0) break;
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
@@ -408,7 +432,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       if (tid == 0) SCN_TRACE(1, 1);
       for (int lst = 0; lst < steps; ++lst, ++g) {
         const int stage = g % NSA, use = g / NSA;
-        if (use > 0) mbar_wait(bar_emptyA + stage * 8, (use - 1) & 1);
+        if (use > 0) MBW(bar_emptyA + stage * 8, (use - 1) & 1, 1);
         const int st = split + lst * splits;
         const int e = st / kchunks, c = st - e * kchunks;
 #ifdef SCN_EXPERIMENT_NO_A          // timing experiment only (wrong results): what if the gathers were free?
@@ -440,64 +464,85 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
       // kind::f16, bf16 operands: D = f32 (bit 4), A = B = bf16 (1 at bits 7 and 10)
       const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-      int g = 0, accn = 0;
-      for (int it = 0;; ++it) {
-        const int slot = it % MS;
-        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      // This thread is the kernel's serial bottleneck (tools/gemm_stalls.py: tcgen05.mma issue blocks for the
+      // execution time of the previous instruction, so every cycle spent between two steps leaves the tensor
+      // pipe idle): ring positions and phases are running counters (NSB is a run-time value: no divisions),
+      // barriers are probed with test_wait before falling into the try_wait loop, descriptors are base + offset.
+      int accn = 0;
+      int stage = 0, stb = 0, stl = 0;
+      uint32_t phA = 0, phB = 0, phL = 0;
+      const uint64_t desc_hi = (uint64_t)(16u >> 4) << 16 | (uint64_t)(1024u >> 4) << 32 | (1ull << 46) | (2ull << 61);   // make_desc_sw128
+      const uint64_t desc_bf = make_desc(0, (uint32_t)N * 16, 128);      // bf16 weight stage: no swizzle, K-major
+      auto wait_fast = [&](uint32_t bar, uint32_t parity) { if (!mbar_test(bar, parity)) mbar_wait(bar, parity); };
+      for (int it = 0, slot = 0, mph = 0;; ++it) {
+        MBW(bar_mfull + slot * 8, mph, 0);
         const int item = meta_hdr(slot)[1];
         if (item < 0) break;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
         mbar_arrive(bar_mempty + slot * 8);
+        if (++slot == ms) { slot = 0; mph ^= 1; }
         SCN_TRACE(2, 1);
         SCN_TRACE(4, steps);
         if (steps == 0) continue;
         const int acc = accn & 1;
-        if (accn >= 2) mbar_wait(bar_tempty + acc * 8, ((accn >> 1) - 1) & 1);
+        if (accn >= 2) MBW(bar_tempty + acc * 8, ((accn >> 1) - 1) & 1, 5);
         tc_fence_after();
         SCN_TRACE(2, 2);
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
-        for (int lst = 0; lst < steps; ++lst, ++g) {
-          const int stage = g % NSA, use = g / NSA;
-          const int stb = g % NSB, useb = g / NSB;
-          mbar_wait(bar_fullB + stb * 8, useb & 1);
-          mbar_wait(bar_fullA + stage * 8, use & 1);
-          const int stl = g % NLT;
-          if (CONV) mbar_wait(bar_fullL + stl * 8, (g / NLT) & 1);
+        for (int lst = 0; lst < steps; ++lst) {
+          // converter modes: fullL implies fullA (the converters wait for the landed stage before they arrive)
+#ifdef SCN_EXPERIMENT_STALLS
+          MBW(bar_fullB + stb * 8, phB, 3);
+          if (CONV) MBW(bar_fullL + stl * 8, phL, 4);
+          else MBW(bar_fullA + stage * 8, phA, 2);
+#else
+          wait_fast(bar_fullB + stb * 8, phB);
+          if (CONV) wait_fast(bar_fullL + stl * 8, phL);
+          else wait_fast(bar_fullA + stage * 8, phA);
+#endif
+          SCN_STALL_T0;
           tc_fence_after();
+          SCN_STALL_ADD(0);            // (MMA role: slot 0 also counts the fences)
           if (lst == 0) SCN_TRACE(2, 3);
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
           const uint32_t sl = alo_base + stl * A_STAGE;
+          const uint64_t da = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4), db = desc_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+          const uint64_t dl = desc_hi | (uint64_t)((sl & 0x3FFFFu) >> 4);
+          const uint64_t db_lo = desc_hi | (uint64_t)(((sb + B_SLICE) & 0x3FFFFu) >> 4);
           if (BF) {
             // A (bf16 pairs) from TMEM: 16 columns per step, 8 per K = 16 instruction; B: no-swizzle K-major,
             // core matrices N*16 B apart along K (LBO), 8-row groups 128 B apart (SBO)
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk)
               mma_bf16_ts(tmem_d, tmem_base + 2 * acc_cols + (uint32_t)(stl * 16 + kk * 8),
-                          make_desc(sb + kk * 2 * N * 16, (uint32_t)N * 16, 128), idesc_bf, (lst > 0 || kk > 0) ? 1u : 0u);
+                          desc_bf + (uint64_t)(((sb + kk * 2 * N * 16) & 0x3FFFFu) >> 4), idesc_bf, (lst > 0 || kk > 0) ? 1u : 0u);
           }
 #pragma unroll
 #ifdef SCN_EXPERIMENT_NO_MMA     // timing experiment only (wrong results): one MMA per step instead of 4 / 12
           if (lst == 0) mma_tf32(tmem_d, make_desc_sw128(sa), make_desc_sw128(sb), idesc, 0u);
           for (int kk = 0; kk < 0; ++kk) {
 #else
-          for (int kk = 0; kk < (BF ? 0 : KC / 8); ++kk) { // K = 8 per instruction: 32 bytes further along the 128-byte rows
+          for (int kk = 0; kk < (BF ? 0 : KC / 8); ++kk) { // K = 8 per instruction: 32 bytes (2 descriptor units) further along the 128-byte rows
 #endif
-            mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + kk * 32), idesc,
-                     (lst > 0 || kk > 0) ? 1u : 0u);
+            mma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
               if (LO_TMEM)
-                mma_tf32_ts(tmem_d, tmem_base + 2 * acc_cols + (uint32_t)(stl * KC + kk * 8), make_desc_sw128(sb + kk * 32),
-                            idesc, 1u);
+                mma_tf32_ts(tmem_d, tmem_base + 2 * acc_cols + (uint32_t)(stl * KC + kk * 8), db + 2 * kk, idesc, 1u);
               else
-                mma_tf32(tmem_d, make_desc_sw128(sl + kk * 32), make_desc_sw128(sb + kk * 32), idesc, 1u);
-              mma_tf32(tmem_d, make_desc_sw128(sa + kk * 32), make_desc_sw128(sb + B_SLICE + kk * 32), idesc, 1u);
+                mma_tf32(tmem_d, dl + 2 * kk, db + 2 * kk, idesc, 1u);
+              mma_tf32(tmem_d, da + 2 * kk, db_lo + 2 * kk, idesc, 1u);
             }
           }
           // ONE commit per step: emptyA[g % NSA] completing means "the MMAs of step g are done"; the
           // weight loader and the converters wait on the same barrier for the step that last used the
           // stage they are about to refill (their rings are no deeper than NSA, so the barrier cannot
           // run two phases ahead of them)
+          SCN_STALL_ADD(6);            // descriptor arithmetic + tcgen05.mma issue
           tc_commit(bar_emptyA + stage * 8);
+          SCN_STALL_ADD(1);            // (MMA role: slot 1 = tcgen05.commit)
+          if (++stage == NSA) { stage = 0; phA ^= 1; }
+          if (++stb == NSB) { stb = 0; phB ^= 1; }
+          if (++stl == NLT) { stl = 0; phL ^= 1; }
         }
         tc_commit(bar_tfull + acc * 8);
         SCN_TRACE(2, 4);
@@ -509,8 +554,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     if (lane == 0) {
       int g = 0;
       for (int it = 0;; ++it) {
-        const int slot = it % MS;
-        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int slot = it % ms;
+        MBW(bar_mfull + slot * 8, (it / ms) & 1, 0);
         const int item = meta_hdr(slot)[1];
         if (item < 0) break;
         const int split = (item % item_stride) / n_tiles, col0 = (item / item_stride) * N;
@@ -518,7 +563,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         const int8_t *sK = reinterpret_cast<const int8_t *>(meta_hdr(slot) + 2);
         for (int lst = 0; lst < steps; ++lst, ++g) {
           const int stage = g % NSB;
-          if (g >= NSB) mbar_wait(bar_emptyA + ((g - NSB) % NSA) * 8, ((g - NSB) / NSA) & 1);
+          if (g >= NSB) MBW(bar_emptyA + ((g - NSB) % NSA) * 8, ((g - NSB) / NSA) & 1, 1);
           const int st = split + lst * splits;
           const int e = st / kchunks, c = st - e * kchunks;
           const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
@@ -552,8 +597,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       const int ct = tid - CONV_W * 32;
       int g = 0;
       for (int it = 0;; ++it) {
-        const int slot = it % MS;
-        mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+        const int slot = it % ms;
+        MBW(bar_mfull + slot * 8, (it / ms) & 1, 0);
         const int item = meta_hdr(slot)[1];
         if (item < 0) break;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
@@ -561,8 +606,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
         for (int lst = 0; lst < steps; ++lst, ++g) {
           const int stage = g % NSA, stl = g % NLT;
-          mbar_wait(bar_fullA + stage * 8, (g / NSA) & 1);
-          if (g >= NLT) mbar_wait(bar_emptyA + ((g - NLT) % NSA) * 8, ((g - NLT) / NSA) & 1);
+          MBW(bar_fullA + stage * 8, (g / NSA) & 1, 2);
+          if (g >= NLT) MBW(bar_emptyA + ((g - NLT) % NSA) * 8, ((g - NLT) / NSA) & 1, 1);
           if (BF) {
             // thread = row ct: its 8 chunks (un-swizzled by index) -> 16 bf16 pairs -> 16 columns of TMEM lane ct
             tc_fence_after();
@@ -620,8 +665,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     const int row = q * 32 + lane;
     int accn = 0;
     for (int it = 0;; ++it) {
-      const int slot = it % MS;
-      mbar_wait(bar_mfull + slot * 8, (it / MS) & 1);
+      const int slot = it % ms;
+      MBW(bar_mfull + slot * 8, (it / ms) & 1, 0);
       const int item = meta_hdr(slot)[1];
       if (item < 0) break;
       const int tile = item % n_tiles, split = (item % item_stride) / n_tiles, col0 = (item / item_stride) * N;
@@ -639,7 +684,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       }
       const int acc = accn & 1;
       if (steps > 0) {
-        mbar_wait(bar_tfull + acc * 8, (accn >> 1) & 1);
+        MBW(bar_tfull + acc * 8, (accn >> 1) & 1, 5);
         tc_fence_after();
       }
       if (warp == EPI_W && lane == 0) SCN_TRACE(3, 2);
@@ -714,6 +759,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       if (warp == EPI_W && lane == 0) SCN_TRACE(3, 3);
     }
   }
+  SCN_STALL_WRITE;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
@@ -909,27 +955,41 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   // ring depths: 2-3 weight-slice stages, then as many gathered-row stages as fit beside the metadata
   // slots (the gathers are latency-bound: depth = bytes in flight)
   const int b_stage = Smem::b_stage_bytes(NW, x3);
-  const int meta_total = MS * (K * TILE_M * 4 + TILE_M * 4 + 64);
+  const int meta_slot = K * TILE_M * 4 + TILE_M * 4 + 64;
   // 3xTF32 with the low-order halves in TMEM: three weight stages (the weight ring is latency-bound: a TMA
   // bulk copy takes ~1.2 us, so two 32 KB stages paced the step at 0.7 us)
   const int nsb = x3 == 2 ? 4 : ((x3 && LO_TMEM) ? 3 : (b_stage > 16384 ? 2 : 3));
-  const int budget = x3 ? 226 * 1024 : 218 * 1024;
-  const int nsa_fit = (budget - meta_total - 4 * 4096 - nsb * b_stage - ((x3 == 1 && !LO_TMEM) ? NLO * A_STAGE : 0)) / A_STAGE;
-  const int depth = nsa_fit >= 8 ? 6 : (nsa_fit >= 6 ? 4 : (nsa_fit >= 4 ? 2 : 1));
-  if (nsa_fit < 3) return 1;
-  const Smem L(NW, K, depth + 2, nsb, x3);
+  const int budget = 226 * 1024;
+  auto fit = [&](int ms) {
+    const int f = (budget - ms * meta_slot - 4 * 4096 - nsb * b_stage - ((x3 == 1 && !LO_TMEM) ? NLO * A_STAGE : 0)) / A_STAGE;
+    return f > NSA_MAX ? NSA_MAX : f;
+  };
+  // Both rings are latency-bound (profiles/experiments/README.md: period = (refill latency + MMA time) / depth),
+  // so every gathered-row stage counts: layers whose work items are long (>= 16 steps even with few active
+  // offsets) give up the third metadata slot when that buys another stage.
+  int ms = MS;
+  const int kchunks_ = Kd / KC;
+  if (fit(2) > fit(MS) && K * kchunks_ >= 32 && tv.n_tiles * ncb * 2 > num_sms()) ms = 2;   // (never with split work items)
+  int nsa_fit = fit(ms);
+  static const int env_nsa = getenv("SCN_B200_GEMM_NSA") ? atoi(getenv("SCN_B200_GEMM_NSA")) : 0;   // experiments
+  if (env_nsa >= 3 && nsa_fit > env_nsa) nsa_fit = env_nsa;
+  if (nsa_fit < 3 || nsb > nsa_fit) return 1;   // (the weight ring is never deeper than the gathered-row ring)
+  const int depth = nsa_fit - 2;
+  const Smem L(NW, K, depth + 2, nsb, x3, ms);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ae = cudaSuccess;
     auto setattr = [&](const void *f) {
       if (ae == cudaSuccess) ae = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     };
-    setattr((const void *)k_osgemm_tf32<1, 0>); setattr((const void *)k_osgemm_tf32<2, 0>);
-    setattr((const void *)k_osgemm_tf32<4, 0>); setattr((const void *)k_osgemm_tf32<6, 0>);
-    setattr((const void *)k_osgemm_tf32<1, 1>); setattr((const void *)k_osgemm_tf32<2, 1>);
-    setattr((const void *)k_osgemm_tf32<4, 1>); setattr((const void *)k_osgemm_tf32<6, 1>);
-    setattr((const void *)k_osgemm_tf32<1, 2>); setattr((const void *)k_osgemm_tf32<2, 2>);
-    setattr((const void *)k_osgemm_tf32<4, 2>); setattr((const void *)k_osgemm_tf32<6, 2>);
+#define SCN_SETATTR_MODE(M)                                                                                   \
+    setattr((const void *)k_osgemm_tf32<1, M>); setattr((const void *)k_osgemm_tf32<2, M>);                     \
+    setattr((const void *)k_osgemm_tf32<3, M>); setattr((const void *)k_osgemm_tf32<4, M>);                     \
+    setattr((const void *)k_osgemm_tf32<5, M>); setattr((const void *)k_osgemm_tf32<6, M>);
+    SCN_SETATTR_MODE(0)
+    SCN_SETATTR_MODE(1)
+    SCN_SETATTR_MODE(2)
+#undef SCN_SETATTR_MODE
     if (ae != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(ae));
       return -1;
@@ -962,23 +1022,18 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   prof_begin(PROF_GEMM, s);
 #define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
   k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, K, n_rows, tv, cols, ypart, \
-                                                                n_items, splits, nsb, sched)
-  if (x3 == 2) {
-    if (depth == 6) SCN_OSGEMM_LAUNCH(6, 2);
-    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, 2);
-    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, 2);
-    else SCN_OSGEMM_LAUNCH(1, 2);
-  } else if (x3 == 1) {
-    if (depth == 6) SCN_OSGEMM_LAUNCH(6, 1);
-    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, 1);
-    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, 1);
-    else SCN_OSGEMM_LAUNCH(1, 1);
-  } else {
-    if (depth == 6) SCN_OSGEMM_LAUNCH(6, 0);
-    else if (depth == 4) SCN_OSGEMM_LAUNCH(4, 0);
-    else if (depth == 2) SCN_OSGEMM_LAUNCH(2, 0);
-    else SCN_OSGEMM_LAUNCH(1, 0);
+                                                                n_items, splits, nsb, sched, ms)
+#define SCN_OSGEMM_DEPTH(T3)                                                                                  \
+  switch (depth) {                                                                                            \
+    case 6: SCN_OSGEMM_LAUNCH(6, T3); break;                                                                  \
+    case 5: SCN_OSGEMM_LAUNCH(5, T3); break;                                                                  \
+    case 4: SCN_OSGEMM_LAUNCH(4, T3); break;                                                                  \
+    case 3: SCN_OSGEMM_LAUNCH(3, T3); break;                                                                  \
+    case 2: SCN_OSGEMM_LAUNCH(2, T3); break;                                                                  \
+    default: SCN_OSGEMM_LAUNCH(1, T3); break;                                                                 \
   }
+  if (x3 == 2) { SCN_OSGEMM_DEPTH(2) } else if (x3 == 1) { SCN_OSGEMM_DEPTH(1) } else { SCN_OSGEMM_DEPTH(0) }
+#undef SCN_OSGEMM_DEPTH
 #undef SCN_OSGEMM_LAUNCH
   prof_end(PROF_GEMM, s, prof_bytes, prof_flops);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1181,11 +1236,16 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, Cout, 1, 1);
       for (int st = 0; st < steps; ++st) {
+        // (this thread paces the kernel like the gather-GEMM's issuer: probe with test_wait first; in 3xTF32
+        // mode the converters' barrier implies the landed stage)
         const int stage = st % NSTAGE, use = st / NSTAGE;
-        mbar_wait(bar_full + stage * 8, use & 1);
-        SCN_TRACE_DW(2, 1);
         const int stl = st % NLO;
-        if (X3) mbar_wait(bar_fullL + stl * 8, (st / NLO) & 1);
+        if (X3) {
+          if (!mbar_test(bar_fullL + stl * 8, (st / NLO) & 1)) mbar_wait(bar_fullL + stl * 8, (st / NLO) & 1);
+        } else {
+          if (!mbar_test(bar_full + stage * 8, use & 1)) mbar_wait(bar_full + stage * 8, use & 1);
+        }
+        SCN_TRACE_DW(2, 1);
         tc_fence_after();
         const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
         const uint32_t la = a_base + (NSTAGE + stl) * L.a_stage, lb = b_base + (NSTAGE + stl) * L.b_stage;
@@ -1285,6 +1345,13 @@ extern "C" int scn_debug_trace_read(unsigned long long *out, int *counts, int re
     int z[5] = {0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(scn::tc::g_trace_n, z, sizeof(z));
   }
+  return 0;
+}
+#endif
+#ifdef SCN_EXPERIMENT_STALLS
+extern "C" int scn_debug_stalls_read(long long *out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, scn::tc::g_stall, sizeof(long long) * 20 * 8);
   return 0;
 }
 #endif
