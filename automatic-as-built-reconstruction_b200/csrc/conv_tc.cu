@@ -200,6 +200,15 @@ constexpr bool LO_TMEM = true;
 constexpr bool LO_TMEM = false;
 #endif
 constexpr int LO_COLS = 128;                 // TMEM columns reserved for the low-order stages (4 x 32)
+// 3xTF32: the converters also copy the gathered rows THEMSELVES into tensor memory (another 4 x 32 columns), so all
+// three MMAs of a K = 8 slice take their A operand from TMEM.  The kernel is shared-memory-bandwidth bound in this
+// mode (per step: 80 KB of operand reads by the MMAs + 48 KB written by the copies + 16 KB read by the converters
+// = 1125 cycles at 128 B/clk against 768 cycles of MMAs); two of the three A reads (32 KB per step) go away.
+#ifndef SCN_X3_HI_SMEM
+constexpr bool HI_TMEM = LO_TMEM;
+#else
+constexpr bool HI_TMEM = false;
+#endif
 
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
@@ -219,6 +228,12 @@ struct Smem {
   }
 };
 
+// one lane of the (fully converged) warp: elect.sync
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
@@ -276,6 +291,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // accumulator) and, in slot 7, from kernel start to the end of its role
 #ifdef SCN_EXPERIMENT_STALLS
 __device__ long long g_stall[20][8];
+__device__ long long g_cta[160][4];      // per CTA (MMA thread): steps, items, globaltimer at start / end of its role
 #define SCN_STALL_DECL long long stall_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long stall_t0_ = clock64()
 #define MBW(bar, parity, id) do { const long long t0_ = clock64(); mbar_wait(bar, parity); stall_[id] += clock64() - t0_; } while (0)
 #define SCN_STALL_T0 long long ts_ = clock64()
@@ -459,8 +475,10 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
     }
   } else if (warp == MMA_W) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow: ring positions and descriptors
+    // stay in uniform registers), one elected lane issues the tcgen05 instructions.  Under `if (lane == 0)` the
+    // compiler wrapped every tcgen05.mma in an election loop and moved each operand through R2UR =====
+    {
       const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
       // kind::f16, bf16 operands: D = f32 (bit 4), A = B = bf16 (1 at bits 7 and 10)
       const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
@@ -474,20 +492,23 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       const uint64_t desc_hi = (uint64_t)(16u >> 4) << 16 | (uint64_t)(1024u >> 4) << 32 | (1ull << 46) | (2ull << 61);   // make_desc_sw128
       const uint64_t desc_bf = make_desc(0, (uint32_t)N * 16, 128);      // bf16 weight stage: no swizzle, K-major
       auto wait_fast = [&](uint32_t bar, uint32_t parity) { if (!mbar_test(bar, parity)) mbar_wait(bar, parity); };
+#ifdef SCN_EXPERIMENT_STALLS
+      long long cta_steps_ = 0, cta_items_ = 0, cta_t0_;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(cta_t0_));
+#endif
       for (int it = 0, slot = 0, mph = 0;; ++it) {
         MBW(bar_mfull + slot * 8, mph, 0);
         const int item = meta_hdr(slot)[1];
         if (item < 0) break;
         const int steps = item_steps(item, meta_hdr(slot)[0]);
-        mbar_arrive(bar_mempty + slot * 8);
+        if (lane == 0) mbar_arrive(bar_mempty + slot * 8);
         if (++slot == ms) { slot = 0; mph ^= 1; }
-        SCN_TRACE(2, 1);
-        SCN_TRACE(4, steps);
+        if (lane == 0) { SCN_TRACE(2, 1); SCN_TRACE(4, steps); }
         if (steps == 0) continue;
         const int acc = accn & 1;
         if (accn >= 2) MBW(bar_tempty + acc * 8, ((accn >> 1) - 1) & 1, 5);
         tc_fence_after();
-        SCN_TRACE(2, 2);
+        if (lane == 0) SCN_TRACE(2, 2);
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
         for (int lst = 0; lst < steps; ++lst) {
           // converter modes: fullL implies fullA (the converters wait for the landed stage before they arrive)
@@ -503,12 +524,13 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           SCN_STALL_T0;
           tc_fence_after();
           SCN_STALL_ADD(0);            // (MMA role: slot 0 also counts the fences)
-          if (lst == 0) SCN_TRACE(2, 3);
+          if (lst == 0 && lane == 0) SCN_TRACE(2, 3);
           const uint32_t sa = a_base + stage * A_STAGE, sb = b_base + stb * B_STAGE;
           const uint32_t sl = alo_base + stl * A_STAGE;
           const uint64_t da = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4), db = desc_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
           const uint64_t dl = desc_hi | (uint64_t)((sl & 0x3FFFFu) >> 4);
           const uint64_t db_lo = desc_hi | (uint64_t)(((sb + B_SLICE) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
           if (BF) {
             // A (bf16 pairs) from TMEM: 16 columns per step, 8 per K = 16 instruction; B: no-swizzle K-major,
             // core matrices N*16 B apart along K (LBO), 8-row groups 128 B apart (SBO)
@@ -524,6 +546,13 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 #else
           for (int kk = 0; kk < (BF ? 0 : KC / 8); ++kk) { // K = 8 per instruction: 32 bytes (2 descriptor units) further along the 128-byte rows
 #endif
+            if (X3 && HI_TMEM) {
+              const uint32_t ta = tmem_base + 2 * acc_cols + (uint32_t)(stl * KC + kk * 8);
+              mma_tf32_ts(tmem_d, ta + LO_COLS, db + 2 * kk, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
+              mma_tf32_ts(tmem_d, ta, db + 2 * kk, idesc, 1u);
+              mma_tf32_ts(tmem_d, ta + LO_COLS, db_lo + 2 * kk, idesc, 1u);
+              continue;
+            }
             mma_tf32(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
               if (LO_TMEM)
@@ -538,16 +567,32 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           // stage they are about to refill (their rings are no deeper than NSA, so the barrier cannot
           // run two phases ahead of them)
           SCN_STALL_ADD(6);            // descriptor arithmetic + tcgen05.mma issue
+#ifdef SCN_EXPERIMENT_XCOMMIT    // timing experiment: what does one more tcgen05.commit per step cost? (emptyB is unused)
+          tc_commit(bar_emptyB);
+#endif
           tc_commit(bar_emptyA + stage * 8);
+          if (lst + 1 == steps) tc_commit(bar_tfull + acc * 8);     // the tile's last step: accumulator complete
+          }
+          __syncwarp();
           SCN_STALL_ADD(1);            // (MMA role: slot 1 = tcgen05.commit)
           if (++stage == NSA) { stage = 0; phA ^= 1; }
           if (++stb == NSB) { stb = 0; phB ^= 1; }
           if (++stl == NLT) { stl = 0; phL ^= 1; }
         }
-        tc_commit(bar_tfull + acc * 8);
-        SCN_TRACE(2, 4);
+        if (lane == 0) SCN_TRACE(2, 4);
         ++accn;
+#ifdef SCN_EXPERIMENT_STALLS
+        cta_steps_ += steps; ++cta_items_;
+#endif
       }
+#ifdef SCN_EXPERIMENT_STALLS
+      if (blockIdx.x < 160) {
+        long long t1_;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1_));
+        g_cta[blockIdx.x][0] = cta_steps_; g_cta[blockIdx.x][1] = cta_items_;
+        g_cta[blockIdx.x][2] = cta_t0_; g_cta[blockIdx.x][3] = t1_;
+      }
+#endif
     }
   } else if (warp == WL_W) {
     // ===== weight-slice loader (TMA bulk copies of the packed B operand) =====
@@ -631,11 +676,15 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 #pragma unroll
             for (int jc = 0; jc < 8; ++jc) {
               const float4 v = row[jc ^ (ct & 7)];
-              w[4 * jc + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
-              w[4 * jc + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
-              w[4 * jc + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
-              w[4 * jc + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+              w[4 * jc + 0] = __float_as_uint(v.x); w[4 * jc + 1] = __float_as_uint(v.y);
+              w[4 * jc + 2] = __float_as_uint(v.z); w[4 * jc + 3] = __float_as_uint(v.w);
             }
+            // the row itself (kind::tf32 reads its upper 19 bits = hi), then lo = x - hi in place
+            if (HI_TMEM)
+              tmem_st32(tmem_base + 2 * acc_cols + LO_COLS + (uint32_t)(stl * KC) + ((uint32_t)((warp & 3) * 32) << 16), w);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              w[i] = __float_as_uint(__uint_as_float(w[i]) - __uint_as_float(w[i] & 0xffffe000u));
             tmem_st32(tmem_base + 2 * acc_cols + (uint32_t)(stl * KC) + ((uint32_t)((warp & 3) * 32) << 16), w);
             tmem_st_wait();
             tc_fence_before();
@@ -1352,6 +1401,11 @@ extern "C" int scn_debug_trace_read(unsigned long long *out, int *counts, int re
 extern "C" int scn_debug_stalls_read(long long *out) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, scn::tc::g_stall, sizeof(long long) * 20 * 8);
+  return 0;
+}
+extern "C" int scn_debug_cta_read(long long *out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, scn::tc::g_cta, sizeof(long long) * 160 * 4);
   return 0;
 }
 #endif

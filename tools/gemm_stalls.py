@@ -39,6 +39,16 @@ for prec in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "tf32", "
         torch.cuda.synchronize()
         conv(x)
         lib.scn_debug_stalls_read(buf.ctypes.data_as(ctypes.c_void_p))
+    cta = np.zeros((160, 4), dtype=np.int64)
+    lib.scn_debug_cta_read(cta.ctypes.data_as(ctypes.c_void_p))
+    cta = cta[cta[:, 3] > 0]
+    t0 = cta[:, 2].min()
+    end = (cta[:, 3] - t0) / 1e3
+    dur = (cta[:, 3] - cta[:, 2]) / 1e3
+    print("%s: %d CTAs, steps/CTA min %d mean %.0f max %d, items/CTA %d-%d; MMA role ends at %.1f .. %.1f us (mean %.1f), "
+          "us per step: min %.3f mean %.3f max %.3f" % (prec, len(cta), cta[:, 0].min(), cta[:, 0].mean(), cta[:, 0].max(),
+          cta[:, 1].min(), cta[:, 1].max(), end.min(), end.max(), end.mean(),
+          (dur / cta[:, 0]).min(), (dur / cta[:, 0]).mean(), (dur / cta[:, 0]).max()))
     print("%s  C=%d scale %d  (us at 1.965 GHz, CTA 0)" % (prec, C, s))
     for w, name in roles.items():
         if buf[w, 7] == 0:
