@@ -1281,44 +1281,49 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       if (lane == 0) mbar_arrive(bar_pempty + slot * 8);
     }
   } else if (warp == DW_MMA_W) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (see the gather-GEMM's MMA role) =====
+    {
       const uint32_t idesc = make_idesc(128, Cout, 1, 1);
+      int stage = 0, stl = 0;
+      uint32_t ph = 0, phl = 0;
       for (int st = 0; st < steps; ++st) {
-        // (this thread paces the kernel like the gather-GEMM's issuer: probe with test_wait first; in 3xTF32
-        // mode the converters' barrier implies the landed stage)
-        const int stage = st % NSTAGE, use = st / NSTAGE;
-        const int stl = st % NLO;
+        // this warp paces the kernel: probe with test_wait first; in 3xTF32 mode the converters' barrier
+        // implies the landed stage
         if (X3) {
-          if (!mbar_test(bar_fullL + stl * 8, (st / NLO) & 1)) mbar_wait(bar_fullL + stl * 8, (st / NLO) & 1);
+          if (!mbar_test(bar_fullL + stl * 8, phl)) mbar_wait(bar_fullL + stl * 8, phl);
         } else {
-          if (!mbar_test(bar_full + stage * 8, use & 1)) mbar_wait(bar_full + stage * 8, use & 1);
+          if (!mbar_test(bar_full + stage * 8, ph)) mbar_wait(bar_full + stage * 8, ph);
         }
-        SCN_TRACE_DW(2, 1);
+        if (lane == 0) SCN_TRACE_DW(2, 1);
         tc_fence_after();
-        const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
-        const uint32_t la = a_base + (NSTAGE + stl) * L.a_stage, lb = b_base + (NSTAGE + stl) * L.b_stage;
-        // descriptors differ only in the start address (bits 0-13, 16-byte units; the stages lie below
-        // 256 KB, so adding to the low word never carries into the next field)
-        uint64_t bd = make_desc_b32(sb, 512, sbo_b), bl = make_desc_b32(lb, 512, sbo_b);
-        uint64_t ad0 = make_desc_b32(sa, 512, sbo_a), al0 = make_desc_b32(la, 512, sbo_a);
-        const uint64_t da = (2 * sbo_a) >> 4, db = (2 * sbo_b) >> 4, dh = (4 * 512) >> 4;
+        if (elect_one()) {
+          const uint32_t sa = a_base + stage * L.a_stage, sb = b_base + stage * L.b_stage;
+          const uint32_t la = a_base + (NSTAGE + stl) * L.a_stage, lb = b_base + (NSTAGE + stl) * L.b_stage;
+          // descriptors differ only in the start address (bits 0-13, 16-byte units; the stages lie below
+          // 256 KB, so adding to the low word never carries into the next field)
+          uint64_t bd = make_desc_b32(sb, 512, sbo_b), bl = make_desc_b32(lb, 512, sbo_b);
+          uint64_t ad0 = make_desc_b32(sa, 512, sbo_a), al0 = make_desc_b32(la, 512, sbo_a);
+          const uint64_t da = (2 * sbo_a) >> 4, db = (2 * sbo_b) >> 4, dh = (4 * 512) >> 4;
 #pragma unroll 2
-        for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
-          for (int h = 0; h < halves; ++h) {
-            const uint64_t ad = ad0 + h * dh;
-            mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
-            if (X3) {   // + lo(x) * dy + x * lo(dy)
-              mma_tf32(tmem_d + (uint32_t)(h * Cout), al0 + h * dh, bd, idesc, 1u);
-              mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bl, idesc, 1u);
+          for (int kb = 0; kb < (KP >> 3); ++kb) {      // one MMA consumes 8 pairs = 2 k-atoms
+            for (int h = 0; h < halves; ++h) {
+              const uint64_t ad = ad0 + h * dh;
+              mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bd, idesc, (st > 0 || kb > 0) ? 1u : 0u);
+              if (X3) {   // + lo(x) * dy + x * lo(dy)
+                mma_tf32(tmem_d + (uint32_t)(h * Cout), al0 + h * dh, bd, idesc, 1u);
+                mma_tf32(tmem_d + (uint32_t)(h * Cout), ad, bl, idesc, 1u);
+              }
             }
+            ad0 += da; al0 += da; bd += db; bl += db;
           }
-          ad0 += da; al0 += da; bd += db; bl += db;
+          tc_commit(bar_empty + stage * 8);            // one commit per step (the converters wait on it too)
+          if (st + 1 == steps) tc_commit(bar_done);
         }
-        tc_commit(bar_empty + stage * 8);            // one commit per step (the converters wait on it too)
-        SCN_TRACE_DW(2, 2);
+        __syncwarp();
+        if (lane == 0) SCN_TRACE_DW(2, 2);
+        if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+        if (++stl == NLO) { stl = 0; phl ^= 1; }
       }
-      if (steps > 0) tc_commit(bar_done);
     }
   }
   if (X3 && warp >= DW_CONV_W) {
