@@ -1140,6 +1140,17 @@ struct DwSmem {
 // Warp-specialised like the gather-GEMM: warp 5 streams the work item's (in,out) pair list into a
 // ring of shared-memory slots, warps 0-3 gather both operands' rows with cp.async (arrivals lag
 // NSTAGE/2 steps behind the issue, so nobody waits for fresh data), warp 4 issues the MMAs.
+#ifdef SCN_EXPERIMENT_STALLS
+__device__ long long g_stall_dw[20][8];
+#define SCN_STALL_WRITE_DW                                                               \
+  do {                                                                                   \
+    stall_[7] = clock64() - stall_t0_;                                                   \
+    if (blockIdx.x == 0 && lane == 0)                                                    \
+      for (int i_ = 0; i_ < 8; ++i_) g_stall_dw[warp][i_] = stall_[i_];                  \
+  } while (0)
+#else
+#define SCN_STALL_WRITE_DW do { } while (0)
+#endif
 template <int NSTAGE, bool X3>
 __global__ void __launch_bounds__(X3 ? NT_DW3 : NT_DW)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
@@ -1161,6 +1172,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   int2 *sPairs = reinterpret_cast<int2 *>(smem + L.pairs);      // [DW_NPS][KP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SCN_STALL_DECL;
   const int KA = KP >> 2;                          // k-atoms (4 pairs) per step
   const uint32_t sbo_a = MA * 512, sbo_b = CB * 512;
 
@@ -1230,7 +1242,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
         const int st = st0 + u;
         if (st < steps) {
           const int slot = st % DW_NPS, use = st / DW_NPS;
-          if (use > 0) mbar_wait(bar_pempty + slot * 8, (use - 1) & 1);
+          if (use > 0) MBW(bar_pempty + slot * 8, (use - 1) & 1, 0);
           if (lane == 0) SCN_TRACE_DW(0, 1);
           if (lane < KP) sPairs[slot * KP + lane] = ra[u];
           if (KP > 32) sPairs[slot * KP + lane + 32] = rb[u];
@@ -1251,9 +1263,9 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     for (int st = 0; st < steps; ++st) {
       const int stage = st % NSTAGE, use = st / NSTAGE;
       const int slot = st % DW_NPS;
-      mbar_wait(bar_pfull + slot * 8, (st / DW_NPS) & 1);
+      MBW(bar_pfull + slot * 8, (st / DW_NPS) & 1, 0);
       if (tid == 0) SCN_TRACE_DW(1, 1);
-      if (use > 0) mbar_wait(bar_empty + stage * 8, (use - 1) & 1);
+      if (use > 0) MBW(bar_empty + stage * 8, (use - 1) & 1, 1);
       if (tid == 0) SCN_TRACE_DW(1, 2);
       const int2 *sp = sPairs + slot * KP;
       const uint32_t sa = a_base + stage * L.a_stage + piece, sb = b_base + stage * L.b_stage + piece;
@@ -1290,9 +1302,9 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
         // this warp paces the kernel: probe with test_wait first; in 3xTF32 mode the converters' barrier
         // implies the landed stage
         if (X3) {
-          if (!mbar_test(bar_fullL + stl * 8, phl)) mbar_wait(bar_fullL + stl * 8, phl);
+          if (!mbar_test(bar_fullL + stl * 8, phl)) MBW(bar_fullL + stl * 8, phl, 4);
         } else {
-          if (!mbar_test(bar_full + stage * 8, ph)) mbar_wait(bar_full + stage * 8, ph);
+          if (!mbar_test(bar_full + stage * 8, ph)) MBW(bar_full + stage * 8, ph, 2);
         }
         if (lane == 0) SCN_TRACE_DW(2, 1);
         tc_fence_after();
@@ -1332,8 +1344,8 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
     const int a16 = L.a_stage >> 4, b16 = L.b_stage >> 4;
     for (int st = 0; st < steps; ++st) {
       const int stage = st % NSTAGE, stl = st % NLO;
-      mbar_wait(bar_full + stage * 8, (st / NSTAGE) & 1);
-      if (st >= NLO) mbar_wait(bar_empty + ((st - NLO) % NSTAGE) * 8, ((st - NLO) / NSTAGE) & 1);
+      MBW(bar_full + stage * 8, (st / NSTAGE) & 1, 2);
+      if (st >= NLO) MBW(bar_empty + ((st - NLO) % NSTAGE) * 8, ((st - NLO) / NSTAGE) & 1, 1);
       auto lo4 = [](const float4 v) {
         float4 o;
         o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
@@ -1356,7 +1368,8 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   // ===== epilogue (warps 0-3): accumulator row = input channel, columns = output channels =====
   if (warp < 4) {
     if (steps > 0) {
-      mbar_wait(bar_done, 0);
+      SCN_STALL_WRITE_DW;
+      MBW(bar_done, 0, 5);
       tc_fence_after();
     }
     float *out = partial + (long long)out_slot * Cin * Cout;
@@ -1381,6 +1394,7 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       }
     }
   }
+  if (warp >= 4) SCN_STALL_WRITE_DW;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
@@ -1406,6 +1420,11 @@ extern "C" int scn_debug_trace_read(unsigned long long *out, int *counts, int re
 extern "C" int scn_debug_stalls_read(long long *out) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, scn::tc::g_stall, sizeof(long long) * 20 * 8);
+  return 0;
+}
+extern "C" int scn_debug_stalls_dw_read(long long *out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, scn::tc::g_stall_dw, sizeof(long long) * 20 * 8);
   return 0;
 }
 extern "C" int scn_debug_cta_read(long long *out) {

@@ -55,3 +55,24 @@ for prec in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "tf32", "
             continue
         print("  %-18s total %7.1f | " % (name, buf[w, 7] / 1965.0) +
               "  ".join("%s %6.1f" % (kinds[i], buf[w, i] / 1965.0) for i in range(7) if buf[w, i]))
+
+# ---- weight-gradient kernel (work item 0) ---------------------------------------------------------------------
+dw_roles = {0: "producer warp 0 (+epilogue)", 7: "producer warp 7", 8: "MMA issuer", 9: "pair-list loader", 10: "converter warp 0"}
+dw_kinds = ["pair list", "stage empty", "stage full", "-", "converted", "done", "-", "role total"]
+for prec in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "tf32"]):
+    scn.set_conv_precision(prec)
+    x = scn.InputLayer(3, ss, 4)([locs, feats])
+    x.features.requires_grad_(True)
+    y = conv(x)
+    g = torch.ones_like(y.features)
+    for _ in range(2):
+        y = conv(x)
+        y.features.backward(g)
+    buf = np.zeros((20, 8), dtype=np.int64)
+    lib.scn_debug_stalls_dw_read(buf.ctypes.data_as(ctypes.c_void_p))
+    print("dW %s  C=%d scale %d  (us at 1.965 GHz, work item 0)" % (prec, C, s))
+    for w, name in dw_roles.items():
+        if buf[w, 7] == 0:
+            continue
+        print("  %-28s total %7.1f | " % (name, buf[w, 7] / 1965.0) +
+              "  ".join("%s %6.1f" % (dw_kinds[i], buf[w, i] / 1965.0) for i in range(6) if buf[w, i]))
