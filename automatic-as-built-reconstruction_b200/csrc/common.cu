@@ -313,7 +313,7 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals
   }
 }
 
-int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s) {
+int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s, bool keys_out) {
   if (n <= 1 || bits <= 0) return 0;
   const int passes = (bits + RS_BITS - 1) / RS_BITS;
   const int n_chunks = cdiv(n, RS_CHUNK);
@@ -335,7 +335,7 @@ int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaS
     int32_t *tv = va; va = vb; vb = tv;
   }
   if (ka != keys) {
-    SCN_CUDA(cudaMemcpyAsync(keys, ka, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    if (keys_out) SCN_CUDA(cudaMemcpyAsync(keys, ka, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     SCN_CUDA(cudaMemcpyAsync(vals, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
   }
   dev_free(k2, s);

@@ -102,7 +102,8 @@ int num_sms();
 int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s);
 
 // ---- stable LSD radix sort of (key uint32, value int32), keys limited to `bits` ----------
-int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s);
+// keys_out = false: only the permuted values are needed, the key buffer is left in an unspecified order
+int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaStream_t s, bool keys_out = true);
 
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -34,6 +34,11 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
                   int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,
                   int precision, cudaStream_t s);
 
+// layer-graph forward: all weight operand images in one launch, fresh until prepack_weights_end()
+int prepack_weights_batch(int n, const int64_t *const *tags, const float *const *W, const int *K, const int *Cin,
+                          const int *Cout, int precision, cudaStream_t s);
+void prepack_weights_end();
+
 int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, cudaStream_t s);
 
 }  // namespace scn

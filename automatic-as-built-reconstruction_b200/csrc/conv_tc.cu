@@ -839,55 +839,129 @@ __global__ void k_splitk_reduce(const float *__restrict__ Ypart, const float *__
 // both operand images of a weight tensor in one launch: [0,total) forward layout, [total,2 total) dX layout.
 // x3 = 1 (3xTF32 mode): every (k, chunk) slice is stored twice, [k][c][hi|lo][n][32] with
 // hi = tf32(w), lo = tf32(w - hi); an image then holds 2 total floats.
+__device__ __forceinline__ void pack_element(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wb,
+                                             int K, int Cin, int Cout, int do_f, int do_b, int x3, long long i2) {
+  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
+  const int transpose = i2 >= total;
+  if (transpose ? !do_b : !do_f) return;
+  const long long i = transpose ? i2 - total : i2;
+  const int N = transpose ? Cin : Cout;
+  const int k = (int)(i / per_k);
+  long long r = i - (long long)k * per_k;
+  const int c = (int)(r / ((long long)KC * N));
+  r -= (long long)c * KC * N;
+  const int n = (int)(r >> 5), pos = (int)(r & 31);
+  const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
+  const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
+  const float hi = to_tf32(v);
+  float *dst = transpose ? Wb : Wf;
+  if (x3) {
+    const long long slice = (long long)KC * N;                 // floats of one (k, chunk) slice
+    const long long base = (i - r) * 2;                        // slices before this one, doubled
+    dst[base + r] = hi;
+    dst[base + slice + r] = to_tf32(v - hi);
+  } else {
+    dst[i] = hi;
+  }
+}
+
 __global__ void k_pack_weights_both(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wb,
                                     int K, int Cin, int Cout, int do_f, int do_b, int x3) {
-  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
+  const long long total = (long long)K * Cin * Cout;
   for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
-       i2 += (long long)gridDim.x * blockDim.x) {
-    const int transpose = i2 >= total;
-    if (transpose ? !do_b : !do_f) continue;
-    const long long i = transpose ? i2 - total : i2;
-    const int N = transpose ? Cin : Cout;
-    const int k = (int)(i / per_k);
-    long long r = i - (long long)k * per_k;
-    const int c = (int)(r / ((long long)KC * N));
-    r -= (long long)c * KC * N;
-    const int n = (int)(r >> 5), pos = (int)(r & 31);
-    const int kk = c * KC + ((((pos >> 2) ^ (n & 7)) << 2) | (pos & 3));
-    const float v = transpose ? W[((long long)k * Cin + n) * Cout + kk] : W[((long long)k * Cin + kk) * Cout + n];
-    const float hi = to_tf32(v);
-    float *dst = transpose ? Wb : Wf;
-    if (x3) {
-      const long long slice = (long long)KC * N;                 // floats of one (k, chunk) slice
-      const long long base = (i - r) * 2;                        // slices before this one, doubled
-      dst[base + r] = hi;
-      dst[base + slice + r] = to_tf32(v - hi);
-    } else {
-      dst[i] = hi;
-    }
-  }
+       i2 += (long long)gridDim.x * blockDim.x)
+    pack_element(W, Wf, Wb, K, Cin, Cout, do_f, do_b, x3, i2);
 }
 
 // bf16 operand images (mode 2): [k][chunk c][column block][core j = 4][NW rows][8 bf16] - the no-swizzle K-major
 // layout of tcgen05 (core matrix = 8 rows x 16 bytes), one contiguous NW x 32 slice per (k, c, column block);
 // NW = min(N, 128).  Forward image at Wf, dX image (W[k]^T) at Wb.
+__device__ __forceinline__ void pack_element_bf16(const float *__restrict__ W, __nv_bfloat16 *__restrict__ Wf,
+                                                  __nv_bfloat16 *__restrict__ Wb, int K, int Cin, int Cout, int do_f, int do_b,
+                                                  long long i2) {
+  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
+  const int transpose = i2 >= total;
+  if (transpose ? !do_b : !do_f) return;
+  const long long i = transpose ? i2 - total : i2;
+  const int k = (int)(i / per_k);
+  const long long r = i - (long long)k * per_k;
+  const int ci = (int)(r / Cout), co = (int)(r - (long long)ci * Cout);
+  const int kd = transpose ? co : ci, n = transpose ? ci : co;          // reduction index, operand row
+  const int Kd = transpose ? Cout : Cin, N = transpose ? Cin : Cout;
+  const int NW = N > 128 ? 128 : N, ncb = N / NW, kch = Kd / KC;
+  const int c = kd / KC, kin = kd % KC, j = kin >> 3, e = kin & 7, cb = n / NW, nb = n % NW;
+  const long long idx = (((((long long)k * kch + c) * ncb + cb) * 4 + j) * NW + nb) * 8 + e;
+  (transpose ? Wb : Wf)[idx] = __float2bfloat16(W[i]);
+}
+
 __global__ void k_pack_weights_bf16(const float *__restrict__ W, __nv_bfloat16 *__restrict__ Wf, __nv_bfloat16 *__restrict__ Wb,
                                     int K, int Cin, int Cout, int do_f, int do_b) {
-  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
+  const long long total = (long long)K * Cin * Cout;
   for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
-       i2 += (long long)gridDim.x * blockDim.x) {
-    const int transpose = i2 >= total;
-    if (transpose ? !do_b : !do_f) continue;
-    const long long i = transpose ? i2 - total : i2;
-    const int k = (int)(i / per_k);
-    const long long r = i - (long long)k * per_k;
-    const int ci = (int)(r / Cout), co = (int)(r - (long long)ci * Cout);
-    const int kd = transpose ? co : ci, n = transpose ? ci : co;          // reduction index, operand row
-    const int Kd = transpose ? Cout : Cin, N = transpose ? Cin : Cout;
-    const int NW = N > 128 ? 128 : N, ncb = N / NW, kch = Kd / KC;
-    const int c = kd / KC, kin = kd % KC, j = kin >> 3, e = kin & 7, cb = n / NW, nb = n % NW;
-    const long long idx = (((((long long)k * kch + c) * ncb + cb) * 4 + j) * NW + nb) * 8 + e;
-    (transpose ? Wb : Wf)[idx] = __float2bfloat16(W[i]);
+       i2 += (long long)gridDim.x * blockDim.x)
+    pack_element_bf16(W, Wf, Wb, K, Cin, Cout, do_f, do_b, i2);
+}
+
+// every convolution weight of a layer graph in ONE launch (blockIdx.y = tensor): the per-layer pack launches were
+// ~45 x 7 us of a backbone step
+struct PackJob { const float *W; float *wf, *wb; int K, Cin, Cout, flags; };     // flags: 1 forward image, 2 dX image
+constexpr int PACK_JOBS = 64;
+struct PackBatch { PackJob job[PACK_JOBS]; };
+// tf32 / 3xTF32 images: one warp per 32 x 32 tile (32 reduction indices x 32 operand rows) of one (k, chunk) slice,
+// global reads and writes both in 128-byte lines.  dX image (row n = input channel, reduction = output channels):
+// a weight row is contiguous along the reduction, lane l reads element l and writes it to its swizzled position
+// of the same 128-byte line.  Forward image (row n = output channel, reduction = input channels): the tile is
+// transposed through shared memory.  bf16 images keep the element-wise path.
+__global__ void __launch_bounds__(256) k_pack_weights_batch(const __grid_constant__ PackBatch b, int x3) {
+  const PackJob &j = b.job[blockIdx.y];
+  if (x3 == 2) {
+    const long long total = (long long)j.K * j.Cin * j.Cout;
+    for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
+         i2 += (long long)gridDim.x * blockDim.x)
+      pack_element_bf16(j.W, reinterpret_cast<__nv_bfloat16 *>(j.wf), reinterpret_cast<__nv_bfloat16 *>(j.wb), j.K, j.Cin, j.Cout,
+                        j.flags & 1, j.flags & 2, i2);
+    return;
+  }
+  __shared__ float tile[8][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int Cin = j.Cin, Cout = j.Cout;
+  // tiles of the dX image: K x (Cout/32 chunks) x (Cin/32 row groups); of the forward image: K x (Cin/32) x (Cout/32)
+  const int tiles_b = (j.flags & 2) ? j.K * (Cout >> 5) * (Cin >> 5) : 0;
+  const int tiles_f = (j.flags & 1) ? j.K * (Cin >> 5) * (Cout >> 5) : 0;
+  const int mul = x3 ? 2 : 1;
+  for (int t = blockIdx.x * 8 + w; t < tiles_b + tiles_f; t += gridDim.x * 8) {
+    if (t < tiles_b) {
+      const int ng = t % (Cin >> 5), c = (t / (Cin >> 5)) % (Cout >> 5), k = t / ((Cin >> 5) * (Cout >> 5));
+      // slice (k, c) of the dX image: Cin rows x 32 floats (x 2 in 3xTF32 mode: hi slice then lo slice)
+      float *slice = j.wb + ((long long)(k * (Cout >> 5) + c) * Cin * KC) * mul;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int n = ng * 32 + r;
+        const float v = j.W[((long long)k * Cin + n) * Cout + c * KC + lane];
+        const int pos = (((lane >> 2) ^ (n & 7)) << 2) | (lane & 3);
+        const float hi = to_tf32(v);
+        slice[n * KC + pos] = hi;
+        if (x3) slice[(long long)Cin * KC + n * KC + pos] = to_tf32(v - hi);
+      }
+    } else {
+      const int tf = t - tiles_b;
+      const int ng = tf % (Cout >> 5), c = (tf / (Cout >> 5)) % (Cin >> 5), k = tf / ((Cout >> 5) * (Cin >> 5));
+      float *slice = j.wf + ((long long)(k * (Cin >> 5) + c) * Cout * KC) * mul;
+      __syncwarp();
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r)           // row r of the tile = reduction index c*32 + r, lane = operand row
+        tile[w][r][lane] = j.W[((long long)k * Cin + c * KC + r) * Cout + ng * 32 + lane];
+      __syncwarp();
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {         // operand row n = ng*32 + r, lane = reduction index within the chunk
+        const int n = ng * 32 + r;
+        const float v = tile[w][lane][r];
+        const int pos = (((lane >> 2) ^ (n & 7)) << 2) | (lane & 3);
+        const float hi = to_tf32(v);
+        slice[n * KC + pos] = hi;
+        if (x3) slice[(long long)Cout * KC + n * KC + pos] = to_tf32(v - hi);
+      }
+    }
   }
 }
 
@@ -899,18 +973,20 @@ struct PackEntry {
   cudaStream_t stream = 0;
   float *wf = nullptr, *wb = nullptr;
   uint64_t last_use = 0;
+  uint64_t batch = 0;            // id of the prepack batch that last filled it (see prepack_weights_batch)
 };
 static std::mutex g_pack_mu;
 static std::vector<PackEntry *> g_pack;
 static uint64_t g_pack_clock = 0;
+static uint64_t g_batch_id = 0;      // current prepack batch (layer-graph forward), 0 = none active
+static uint64_t g_batch_seq = 0;
 
 static bool layout_ok(int Kd, int N) { return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256; }
 
 // returns the packed image for (transpose ? dX : forward), (re)building both when the version moved
 // mode: 0 tf32, 1 3xTF32 (hi + lo slices), 2 bf16
-static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int Cout, int transpose, int x3,
-                       cudaStream_t s, float **out) {
-  std::lock_guard<std::mutex> lk(g_pack_mu);
+// entry of the weight tensor `tag` sized for (K, Cin, Cout, mode); caller holds g_pack_mu
+static int pack_entry(const int64_t *tag, int K, int Cin, int Cout, int x3, PackEntry **out) {
   PackEntry *e = nullptr;
   for (PackEntry *p : g_pack)
     if (p->token == tag[0]) { e = p; break; }
@@ -937,10 +1013,23 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     e->K = K; e->Cin = Cin; e->Cout = Cout; e->x3 = x3;
     e->version = -1;
   }
+  *out = e;
+  return 0;
+}
+
+// returns the packed image for (transpose ? dX : forward), (re)building both when the version moved
+// mode: 0 tf32, 1 3xTF32 (hi + lo slices), 2 bf16
+static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int Cout, int transpose, int x3,
+                       cudaStream_t s, float **out) {
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  PackEntry *e = nullptr;
+  SCN_TRY(pack_entry(tag, K, Cin, Cout, x3, &e));
+  const size_t total = (size_t)K * Cin * Cout;
   // the forward pass (transpose == 0) always repacks: in-place edits through `.data` do not move the
-  // version counter, and the forward weights must never be stale; the dX pass of the same step reuses
-  // what its forward packed
-  if (!transpose || e->version != tag[1] || e->stream != s) {
+  // version counter, and the forward weights must never be stale - unless the layer-graph forward that is
+  // running has just packed this tensor in its batch; the dX pass of the same step reuses what its forward packed
+  const bool fresh = g_batch_id != 0 && e->batch == g_batch_id && e->version == tag[1] && e->stream == s;
+  if (!fresh && (!transpose || e->version != tag[1] || e->stream != s)) {
     e->has_f = layout_ok(Cin, Cout);
     e->has_b = layout_ok(Cout, Cin);
     int pb = cdiv(2 * (long long)total, 256);
@@ -960,6 +1049,54 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
   *out = transpose ? e->wb : e->wf;
   return 0;
 }
+
+}  // namespace tc
+
+// Pack the operand images of n weight tensors (forward + dX layouts) in one launch per 64 tensors and mark them
+// fresh for the per-op calls that follow until prepack_weights_end() (layer-graph forward).  Tensors without a tag
+// or without a tensor-core layout in either direction are skipped (their ops pack for themselves).
+int prepack_weights_batch(int n, const int64_t *const *tags, const float *const *W, const int *K, const int *Cin,
+                          const int *Cout, int precision, cudaStream_t s) {
+  using namespace tc;
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 0;
+  const int x3 = precision == SCN_PRECISION_FP32_3XTF32 ? 1 : (precision == SCN_PRECISION_BF16 ? 2 : 0);
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  g_batch_id = ++g_batch_seq;
+  PackBatch b;
+  int nj = 0;
+  auto flush = [&]() -> int {
+    if (nj == 0) return 0;
+    k_pack_weights_batch<<<dim3(num_sms(), nj), 256, 0, s>>>(b, x3);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    SCN_CUDA(cudaGetLastError());
+    nj = 0;
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    if (!tags[i] || !W[i]) continue;
+    const bool hf = layout_ok(Cin[i], Cout[i]), hb = layout_ok(Cout[i], Cin[i]);
+    if ((!hf && !hb) || ((uintptr_t)W[i] & 15)) continue;
+    if (x3 != 2 && ((Cin[i] | Cout[i]) & 31)) continue;     // the tiled pack kernel works on 32 x 32 tiles
+    PackEntry *e = nullptr;
+    SCN_TRY(pack_entry(tags[i], K[i], Cin[i], Cout[i], x3, &e));
+    if (e->batch == g_batch_id) continue;                   // the same tensor twice in one graph
+    e->has_f = hf; e->has_b = hb;
+    e->version = tags[i][1];
+    e->stream = s;
+    e->batch = g_batch_id;
+    e->last_use = ++g_pack_clock;
+    b.job[nj++] = PackJob{W[i], e->wf, e->wb, K[i], Cin[i], Cout[i], (hf ? 1 : 0) | (hb ? 2 : 0)};
+    if (nj == PACK_JOBS) SCN_TRY(flush());
+  }
+  return flush();
+}
+
+void prepack_weights_end() {
+  std::lock_guard<std::mutex> lk(tc::g_pack_mu);
+  tc::g_batch_id = 0;
+}
+
+namespace tc {
 
 int g_gemm_grid_limit = 0;   // test knob (scn_set_gemm_grid_limit): force many work items per CTA
 

@@ -4,6 +4,7 @@
 // between them, which at batch 1 bounds the step (reference dataflow: sparseconvnet/fpn_net.py:168-265,
 // sequential.py:15-17, tables.py:28-56).
 #include "common.cuh"
+#include "conv.cuh"
 #include "../../include/scn_b200.h"
 #include <vector>
 
@@ -49,6 +50,22 @@ int scn_graph_forward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_op
   SCN_CHECK(m && ops && values && rows && params, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   double total = 0;
+  struct BatchEnd { ~BatchEnd() { prepack_weights_end(); } } batch_end;     // (also on the error paths)
+  {   // operand images of every convolution weight in one launch (the per-op calls below then find them fresh)
+    std::vector<const int64_t *> tags;
+    std::vector<const float *> ws;
+    std::vector<int> Ks, cins, couts;
+    for (int i = 0; i < n_ops; ++i) {
+      const scn_graph_op_t &o = ops[i];
+      if (o.kind < 1 || o.kind > 3 || o.p0 < 0) continue;
+      tags.push_back(tag_of(param_tags, o.p0));
+      ws.push_back(params[o.p0]);
+      Ks.push_back((int)(o.filter[0] * o.filter[1] * o.filter[2]));
+      cins.push_back(o.n_in_planes);
+      couts.push_back(o.n_out_planes);
+    }
+    SCN_TRY(prepack_weights_batch((int)ws.size(), tags.data(), ws.data(), Ks.data(), cins.data(), couts.data(), precision, s));
+  }
   for (int i = 0; i < n_ops; ++i) {
     const scn_graph_op_t &o = ops[i];
     double mac = 0;
