@@ -54,6 +54,18 @@ def with_prefetch(n):
         fwd_bwd(p)
 
 
+def with_prefetch2(n):
+    pf.submit(ld)
+    if n > 1:
+        pf.submit(ld)
+    for i in range(n):
+        flush.fill_(1)
+        p = pf.get()
+        if i + 2 < n:
+            pf.submit(ld)
+        fwd_bwd(p)
+
+
 P = net.prepare(ld)
 
 
@@ -81,7 +93,7 @@ def build_only(n):
         net.prepare(ld)
 
 
-for name, fn in (("prefetch", with_prefetch), ("reuse prepared (no integer work)", reuse),
+for name, fn in (("prefetch", with_prefetch), ("prefetch, 2 batches ahead", with_prefetch2), ("reuse prepared (no integer work)", reuse),
                  ("reuse, forward only (no_grad)", reuse_fwd), ("inline build", inline), ("build only", build_only)):
     print("%-36s %7.2f ms/step" % (name, timed(fn)))
 pf.close()
