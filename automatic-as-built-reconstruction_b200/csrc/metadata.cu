@@ -458,7 +458,8 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   const int kbits = K < sort_bits ? K : sort_bits;
   k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx, K - kbits);
   SCN_LAUNCHED();
-  if (g_tile_grouping && K > 1) SCN_TRY(radix_sort_pairs(key, idx, n_rows, kbits, s, false));
+  // (books of at most 4 tiles keep the natural row order: nothing to group, and the sort is ~15 launches)
+  if (g_tile_grouping && K > 1 && n_rows > 4 * TILE_M) SCN_TRY(radix_sort_pairs(key, idx, n_rows, kbits, s, false));
   SCN_TRY(dev_alloc_t(&tb.perm, (size_t)tb.n_tiles * TILE_M, s));
   SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
   SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
