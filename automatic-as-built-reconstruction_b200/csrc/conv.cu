@@ -213,6 +213,7 @@ TileView make_view(const TileBook &tb, int k_flip) {
   v.perm = tb.perm;
   v.tile_mask = tb.tile_mask;
   v.tile_off = tb.tile_off;
+  v.order = tb.identity ? nullptr : tb.order;
   v.entries = tb.entries;
   return v;
 }

@@ -11,6 +11,7 @@ struct TileView {            // device view of a TileBook, passed by value to ke
   const int32_t *perm;
   const uint32_t *tile_mask;
   const int32_t *tile_off;
+  const int32_t *order;      // tiles heaviest first (null: identity books)
   const int32_t *entries;
 };
 

@@ -399,7 +399,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         if (lane == 0) { hdr[1] = -1; mbar_arrive(bar_mfull + slot * 8); }
         break;
       }
-      const int tile = n_tiles - 1 - q % n_tiles;
+      // heaviest tiles first: by the tile book's order (descending number of active offsets)
+      const int tile = tb.order ? tb.order[q % n_tiles] : n_tiles - 1 - q % n_tiles;
       if (lane == 0) hdr[1] = q - q % n_tiles + tile;
       if (tb.identity) {
 #pragma unroll

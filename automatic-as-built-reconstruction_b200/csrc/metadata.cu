@@ -78,6 +78,7 @@ static void tilebook_free(TileBook &tb, cudaStream_t s) {
   dev_free(tb.perm, s);
   dev_free(tb.tile_mask, s);
   dev_free(tb.tile_off, s);
+  dev_free(tb.order, s);
   dev_free(tb.entries, s);
   tb = TileBook();
 }
@@ -420,6 +421,23 @@ k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ 
   }
 }
 
+// tiles ordered by descending number of active offsets (counting sort, one block): the persistent gather-GEMM hands
+// its work items out in this order - longest first, so the last wave consists of the shortest items
+__global__ void __launch_bounds__(1024)
+k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restrict__ order) {
+  __shared__ int cnt[40], base[40];
+  if (threadIdx.x < 40) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&cnt[min(tile_pop[t], 39)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int p = 39; p >= 0; --p) { base[p] = run; run += cnt[p]; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) order[atomicAdd(&base[min(tile_pop[t], 39)], 1)] = t;
+}
+
 __global__ void __launch_bounds__(TILE_M)
 k_fill_entries(const int32_t *__restrict__ T, long long n, const int32_t *__restrict__ perm,
                const uint32_t *__restrict__ tile_mask, const int32_t *__restrict__ tile_off,
@@ -465,6 +483,9 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
   SCN_TRY(dev_alloc_t(&pop, (size_t)tb.n_tiles + 1, s));
   k_tile_masks<<<tb.n_tiles, TILE_M, 0, s>>>(mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
+  SCN_LAUNCHED();
+  SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles, s));
+  k_tile_order<<<1, 1024, 0, s>>>(pop, tb.n_tiles, tb.order);
   SCN_LAUNCHED();
   SCN_TRY(exclusive_scan_i32(pop, tb.tile_off, tb.n_tiles, s));
   SCN_CUDA(cudaMemcpyAsync(meta_slot, tb.tile_off + tb.n_tiles, 4, cudaMemcpyDeviceToDevice, s));
