@@ -92,7 +92,7 @@ def n_active0(locs):
 # ---- clocks ---------------------------------------------------------------------------------------
 class ClockSampler(object):
     """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process, every
-    25 ms) - the same counters as the profiling recipe's nvidia-smi clocks line."""
+    5 ms) - the same counters as the profiling recipe's nvidia-smi clocks line."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4))
 
@@ -121,7 +121,7 @@ class ClockSampler(object):
                 self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.025)
+            time.sleep(0.005)
 
     def stop(self):
         if self.h is None:
