@@ -424,15 +424,17 @@ k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ 
 // tiles ordered by descending number of active offsets (counting sort, one block): the persistent gather-GEMM hands
 // its work items out in this order - longest first, so the last wave consists of the shortest items
 __global__ void __launch_bounds__(1024)
-k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restrict__ order) {
+k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restrict__ order,
+             int32_t *__restrict__ n_entries) {
   __shared__ int cnt[40], base[40];
   if (threadIdx.x < 40) cnt[threadIdx.x] = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&cnt[min(tile_pop[t], 39)], 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    int run = 0;
-    for (int p = 39; p >= 0; --p) { base[p] = run; run += cnt[p]; }
+    int run = 0, entries = 0;                     // (a tile has at most MAX_K = 32 active offsets)
+    for (int p = 39; p >= 0; --p) { base[p] = run; run += cnt[p]; entries += p * cnt[p]; }
+    *n_entries = entries;                         // the entry total the host reads back (= tile_off[n_tiles])
   }
   __syncthreads();
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) order[atomicAdd(&base[min(tile_pop[t], 39)], 1)] = t;
@@ -485,10 +487,9 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   k_tile_masks<<<tb.n_tiles, TILE_M, 0, s>>>(mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
   SCN_LAUNCHED();
   SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles, s));
-  k_tile_order<<<1, 1024, 0, s>>>(pop, tb.n_tiles, tb.order);
+  k_tile_order<<<1, 1024, 0, s>>>(pop, tb.n_tiles, tb.order, meta_slot);
   SCN_LAUNCHED();
   SCN_TRY(exclusive_scan_i32(pop, tb.tile_off, tb.n_tiles, s));
-  SCN_CUDA(cudaMemcpyAsync(meta_slot, tb.tile_off + tb.n_tiles, 4, cudaMemcpyDeviceToDevice, s));
   dev_free(mask, s);
   dev_free(key, s);
   dev_free(idx, s);
