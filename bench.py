@@ -223,8 +223,11 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, points=None):
-    return {"workload": "FPN_Net sparse3d backbone fwd+bwd, %d x %dk-point synthetic building per GPU "
-                        "(BASELINE configs[1])" % (args.batch, (points or args.points) // 1000),
+    pts = points or args.points
+    which = ("BASELINE configs[1]" if (args.batch, pts, args.floors) == (1, 300000, 1) else
+             "BASELINE configs[1] geometry, non-default size")
+    return {"workload": "FPN_Net sparse3d backbone fwd+bwd, %d x %dk-point synthetic building per GPU (%s)"
+                        % (args.batch, pts // 1000, which),
             "per_gpu_batch": args.batch, "points_per_building": points or args.points, "floors": args.floors,
             "full_scale": FULL_SCALE, "planes": PLANES, "precision": args.precision,
             "parallelism": "dp%d" % args.gpus,
