@@ -1,4 +1,4 @@
-"""Developer tool (GPU box, needs tools/_exp/libscn_STALLS.so = csrc built with -DSCN_EXPERIMENT_STALLS): for one
+"""Developer tool (GPU box, needs tools/_exp/libscn_STALLS.so: `tools/build_exp.sh STALLS`): for one
 gather-GEMM launch, the cycles CTA 0's roles spend inside each kind of mbarrier wait - which ring paces the step?"""
 import ctypes
 import os
