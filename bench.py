@@ -164,36 +164,20 @@ def reference_state_dict():
     return sd
 
 
-def cpu_reference_step(sd, locs, feats, keep_outputs=False):
-    """one fwd+bwd of the compiled reference CPU path (fresh Metadata); returns seconds (and, for the
-    parity report, the 8 output maps as (locations, features))"""
+REF_CFG = dict(full_scale=FULL_SCALE, n_planes=PLANES, rpn_map_sizes=RPN_SIZES)
+# stated feature tolerances of the reduced-precision modes (tests/test_full_parity.py)
+REDUCED_FEATURE_TOL = {"tf32": 1e-2, "bf16": 5e-2}
+
+
+def _parity():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ref_backbone as RB
-    net = RB.RefBackbone(sd, full_scale=FULL_SCALE, n_planes=PLANES, rpn_map_sizes=RPN_SIZES)
-    t0 = time.perf_counter()
-    rpn, roi = net.forward(locs, feats)
-    RB.backbone_loss(rpn, roi).backward()
-    dt = time.perf_counter() - t0
-    if keep_outputs:
-        return dt, [(m.locations(), m.features.detach(), m.ss.tolist()) for m in list(rpn) + list(roi)]
-    return dt
+    import parity
+    return parity
 
 
-def parity_report(gpu_maps, ref_maps):
-    """max relative feature error of the backbone's 8 output maps against the reference CPU run of the
-    same batch and weights, rows matched by coordinate (canonical order)"""
-    import scn_oracle as O
-    worst, sites_equal = 0.0, True
-    for g, (rloc, rfeat, ss) in zip(gpu_maps, ref_maps):
-        gloc = g.get_spatial_locations().numpy()
-        og, orf = np.argsort(O.canonical_rank(gloc, ss)), np.argsort(O.canonical_rank(rloc.numpy(), ss))
-        if gloc.shape != tuple(rloc.shape) or not np.array_equal(gloc[og], rloc.numpy()[orf]):
-            sites_equal = False
-            continue
-        a, b = g.features.detach().cpu().numpy()[og], rfeat.numpy()[orf]
-        worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)))
-    return {"active_site_sets_equal": sites_equal, "max_rel_feature_err_vs_reference_cpu": worst,
-            "maps_compared": len(ref_maps)}
+def cpu_reference_step(sd, locs, feats):
+    """one fwd+bwd of the compiled reference CPU path (fresh Metadata); returns seconds"""
+    return _parity().reference_step(sd, locs, feats, REF_CFG)[0]
 
 
 def run_reference(args, rank, world):
@@ -369,20 +353,43 @@ def run_b200(args, rank, local_rank, world):
             "kernel_classes": classes,
             "grad_allreduce_bytes": bucket.nbytes() if world > 1 else 0,
         }
+        failed = None
         if world == 1 and not args.no_cpu_baseline:
+            # Parity at the benchmark's own size (oracle/parity.py): the 8 output maps and every live parameter
+            # gradient of this very batch, library vs the compiled reference CPU run (which is also the
+            # cpu_baseline sample) vs a float64 evaluation of the same graph.
+            P = _parity()
             cores = os.cpu_count()
             torch.set_num_threads(cores)
             sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-            with torch.no_grad():
-                rpn_g, roi_g = net([locs_dev, feats_dev])
-            t, ref_maps = cpu_reference_step(sd, locs, feats, keep_outputs=True)
-            out["parity"] = parity_report(list(rpn_g) + list(roi_g), ref_maps)
+            net.zero_grad(set_to_none=True)
+            rpn_g, roi_g = net([locs_dev, feats_dev])
+            sum((m.features ** 2).sum() for m in list(rpn_g) + list(roi_g)).backward()
+            gpu_maps = [(m.get_spatial_locations().numpy(), m.features.detach().cpu(), m.spatial_size.tolist())
+                        for m in list(rpn_g) + list(roi_g)]
+            gpu_grads = {k: p.grad.detach().cpu() for k, p in net.named_parameters() if p.grad is not None}
+            t, ref_maps, ref_grads = P.reference_step(sd, locs, feats, REF_CFG)
             out["cpu_baseline"] = {"value": na_local / t, "unit": "active voxels/s", "cores": cores,
                                    "kind": "reference", "seconds_per_step": t,
                                    "sample": "1 step (same %d-point batch, nActive %d) fwd+bwd on the compiled "
                                              "reference CPU SparseConvNet, fresh Metadata, no warm-up"
                                              % (len(locs), na_local)}
+            if args.batch * args.points <= 700000:
+                truth_maps, truth_grads = P.truth_step(sd, locs, feats, REF_CFG, device=dev)
+                rep = P.summary(P.three_way(gpu_maps, gpu_grads, ref_maps, ref_grads, truth_maps, truth_grads))
+                rep["max_rel_feature_err_vs_reference_cpu"] = rep["features"]["gpu_vs_ref"]
+                rep["truth"] = "float64 evaluation of the same graph (oracle/scn_oracle.py OracleBackbone)"
+                if args.precision in REDUCED_FEATURE_TOL:
+                    tol = REDUCED_FEATURE_TOL[args.precision]
+                    rep["stated_feature_tolerance"] = tol
+                    rep["ok"] = bool(rep["active_site_sets_equal"] and rep["features"]["gpu_vs_ref"] <= tol)
+                out["parity"] = rep
+                if not rep["ok"]:
+                    failed = "parity outside the stated bound: %s" % json.dumps(rep)
         print(json.dumps(out))
+        if failed:
+            sys.stdout.flush()
+            sys.exit("bench.py: " + failed)
     if world > 1:
         dist.destroy_process_group()
 

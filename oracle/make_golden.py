@@ -35,6 +35,13 @@ def small_net_cfg():
                 rpn_map_sizes=[[32, 32, 32], [16, 16, 16], [8, 8, 8], [4, 4, 4]])
 
 
+def wide_net_cfg():
+    """tensor-core-width FPN_Net (every convolution but the 9-channel stem has Cin, Cout in {32, 64}: the
+    widths the tcgen05 gather-GEMM / weight-gradient kernels take), same index space and cloud as small_net"""
+    return dict(full_scale=[512, 512, 512], n_planes=[32, 64, 32, 32, 32, 32, 32, 32, 32], n_plane_m=32,
+                rpn_map_sizes=[[32, 32, 32], [16, 16, 16], [8, 8, 8], [4, 4, 4]])
+
+
 def reference_package():
     """import the reference's own sparseconvnet python on top of SCN_ref.so"""
     dst = os.path.join(PKG, "sparseconvnet")
@@ -186,12 +193,59 @@ def small_net_golden(ref_scn):
     return out
 
 
+def wide_net_golden(ref_scn):
+    """the reference's own fpn_net.py at tensor-core widths.  Parameters come from scn_oracle.seeded_state_dict
+    (the fixture stores the seed, not 4 MB of random weights); parameter gradients above 4096 elements are
+    stored subsampled (scn_oracle.subsample)."""
+    cfg = wide_net_cfg()
+    net = ref_scn.FPN_Net(cfg["full_scale"], 3, ["xyz", "color", "normal"], 1, cfg["n_planes"],
+                          nPlaneM=cfg["n_plane_m"], residual_blocks=True, fpn_scales_from_top=[4, 3, 2, 1],
+                          roi_scales_from_top=(4, 3), downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8],
+                          rpn_map_sizes=cfg["rpn_map_sizes"], voxel_scale=50,
+                          rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95,
+                          track_running_stats=False)
+    seed = 7
+    net.load_state_dict(scn_oracle.seeded_state_dict({k: v.shape for k, v in net.state_dict().items()}, seed))
+    net.train()
+    xyz = [scn_oracle.building(6000, L=(9.0, 8.0, 3.0), floors=1, seed=10 + s) for s in range(2)]
+    locs, feats = scn_oracle.to_input(xyz, scale=50, full=cfg["full_scale"], seed=1)
+    rpn, roi = net([locs, feats])
+    loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
+    loss.backward()
+    out = {"locs": locs.numpy().astype(np.int16), "feats": feats.numpy(), "loss": np.array(loss.item()),
+           "seed": np.array(seed)}
+    for k, v in net.state_dict().items():
+        out["shape/" + k] = np.array(v.shape)
+    for i, m in enumerate(list(rpn) + list(roi)):
+        loc = m.get_spatial_locations().numpy()
+        order = np.argsort(scn_oracle.canonical_rank(loc, m.spatial_size.tolist()))
+        out["out%d_loc" % i] = loc[order].astype(np.int16)
+        out["out%d_feat" % i] = m.features.detach().numpy()[order]
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            out["grad/" + k] = scn_oracle.subsample(p.grad.numpy())
+    net.eval()
+    with torch.no_grad():
+        rpn, roi = net([locs, feats])
+    for i, m in enumerate(list(rpn) + list(roi)):
+        loc = m.get_spatial_locations().numpy()
+        order = np.argsort(scn_oracle.canonical_rank(loc, m.spatial_size.tolist()))
+        out["eval%d_feat" % i] = scn_oracle.subsample(m.features.numpy()[order], stride=3)
+    np.savez_compressed(os.path.join(GOLD, "wide_net.npz"), **out)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":      # only the fixture added in round 2
+        wide_net_golden(reference_package())
+        print("wide_net.npz", os.path.getsize(os.path.join(GOLD, "wide_net.npz")))
+        return
     appendix_c()
     dump_rulebooks(random_cloud(1500, [40, 36, 24], 2, seed=1), [48, 48, 32], "cloud_rulebooks")
     ref_scn = reference_package()
     small_net_golden(ref_scn)
+    wide_net_golden(ref_scn)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -1,0 +1,120 @@
+"""parity.py - three-way parity report of a backbone step: library (GPU) vs the compiled reference (CPU fp32,
+oracle/_ref through ref_backbone.py) vs a float64 evaluation of the same graph (scn_oracle.OracleBackbone).
+
+TEST INFRASTRUCTURE ONLY (used by tests/, bench.py's parity / cpu_baseline leg and smoke()); never imported by
+the product package.
+
+Why three ways: the north-star bound is `max|gpu - ref| <= 1e-4 max|ref|` in fp32 mode.  The reference CPU path
+itself rounds (sequential fp32 BN sums over up to 3e5 rows, CPU/BatchNormalization.cpp:19-33,86-95; fp32
+index_add of 27 partial products, CPU/Convolution.cpp:46-80), so at full size `ref` carries its own error.
+The float64 evaluation separates the two: a quantity passes when it is within 1e-4 of the reference, or when
+the library is at least as close to the float64 truth as the reference is (the reference is then the noisier
+side and the bound against it cannot be met by ANY more exact implementation).
+
+Error measure everywhere: max|a - b| / max|b| over a tensor (rows matched by coordinate)."""
+import time
+
+import numpy as np
+import torch
+
+import ref_backbone as RB
+import scn_oracle as O
+
+BOUND = 1e-4
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def reference_step(sd, locs, feats, cfg, train=True):
+    """one forward (+ backward) of the compiled reference on the CPU.  Returns (seconds, maps, grads) with
+    maps = [(loc [n,4] ndarray, features tensor, spatial size list)] for the 6 rpn + 2 roi outputs."""
+    net = RB.RefBackbone(sd, **cfg)
+    net.training = train
+    t0 = time.perf_counter()
+    if train:
+        rpn, roi = net.forward(locs, feats)
+        RB.backbone_loss(rpn, roi).backward()
+    else:
+        with torch.no_grad():
+            rpn, roi = net.forward(locs, feats)
+    dt = time.perf_counter() - t0
+    maps = [(m.locations().numpy(), m.features.detach(), m.ss.tolist()) for m in list(rpn) + list(roi)]
+    return dt, maps, (net.grads() if train else {})
+
+
+def truth_step(sd, locs, feats, cfg, device="cpu"):
+    """float64 forward + backward of the same graph and loss (scn_oracle.OracleBackbone)"""
+    net = O.OracleBackbone(sd, cfg["full_scale"], cfg["n_planes"], cfg["rpn_map_sizes"], dtype=torch.float64,
+                           device=device)
+    rpn, roi = net.forward(np.asarray(locs), feats)
+    sum((m[0] ** 2).sum() for m in rpn + roi).backward()
+    maps = [(loc, f.detach().cpu(), list(ss)) for f, loc, ss in rpn + roi]
+    return maps, {k: v.cpu() for k, v in net.grads().items()}
+
+
+def _canon(loc, feat, ss):
+    order = np.argsort(O.canonical_rank(loc, ss))
+    return loc[order], torch.as_tensor(feat)[torch.from_numpy(order)]
+
+
+def three_way(gpu_maps, gpu_grads, ref_maps, ref_grads, truth_maps, truth_grads, bound=BOUND):
+    """gpu_maps / ref_maps / truth_maps: lists of (loc, features, spatial size); *_grads: name -> tensor (gpu_grads
+    may hold None / all-zero entries for parameters no gradient reaches).  Returns the report dict."""
+    rep = {"bound": bound, "maps": [], "grads": {}, "active_site_sets_equal": True}
+    for g, r, t in zip(gpu_maps, ref_maps, truth_maps):
+        gl, gf = _canon(*g)
+        rl, rf = _canon(*r)
+        tl, tf = _canon(*t)
+        if gl.shape != rl.shape or not np.array_equal(gl, rl) or not np.array_equal(gl, tl):
+            rep["active_site_sets_equal"] = False
+            continue
+        rep["maps"].append({"rows": int(len(gl)), "gpu_vs_ref": _rel(gf, rf), "gpu_vs_fp64": _rel(gf, tf),
+                            "ref_vs_fp64": _rel(rf, tf)})
+    live = 0
+    for k, tg in truth_grads.items():
+        rg, gg = ref_grads.get(k), gpu_grads.get(k)
+        if float(tg.abs().max()) == 0.0:
+            continue
+        if gg is None or rg is None:
+            rep["grads"][k] = {"missing": "gpu" if gg is None else "ref"}
+            continue
+        live += 1
+        rep["grads"][k] = {"gpu_vs_ref": _rel(gg, rg), "gpu_vs_fp64": _rel(gg, tg), "ref_vs_fp64": _rel(rg, tg)}
+    rep["live_parameter_gradients"] = live
+
+    def ok(e):
+        return "missing" not in e and (e["gpu_vs_ref"] <= bound or e["gpu_vs_fp64"] <= e["ref_vs_fp64"])
+
+    def worst(items, key):
+        vals = [e[key] for e in items if key in e]
+        return max(vals) if vals else None
+
+    gl = list(rep["grads"].values())
+    rep["features"] = {k: worst(rep["maps"], k) for k in ("gpu_vs_ref", "gpu_vs_fp64", "ref_vs_fp64")}
+    rep["gradients"] = {k: worst(gl, k) for k in ("gpu_vs_ref", "gpu_vs_fp64", "ref_vs_fp64")}
+    rep["features_ok"] = rep["active_site_sets_equal"] and len(rep["maps"]) == len(gpu_maps) and \
+        all(ok(e) for e in rep["maps"])
+    failing = sorted(k for k, e in rep["grads"].items() if not ok(e))
+    rep["gradients_ok"] = not failing and live > 0
+    rep["failing_gradients"] = failing
+    rep["rule"] = "pass = gpu_vs_ref <= bound, or gpu_vs_fp64 <= ref_vs_fp64 (the reference is the noisier side)"
+    rep["ok"] = bool(rep["features_ok"] and rep["gradients_ok"])
+    return rep
+
+
+def summary(rep):
+    """the compact block bench.py prints (per-tensor detail stays in the test output)"""
+    out = {k: rep[k] for k in ("bound", "rule", "active_site_sets_equal", "features", "gradients", "features_ok",
+                               "gradients_ok", "live_parameter_gradients", "failing_gradients", "ok")}
+    out["maps_compared"] = len(rep["maps"])
+    out["gradients_within_bound_of_ref"] = sum(1 for e in rep["grads"].values()
+                                               if "missing" not in e and e["gpu_vs_ref"] <= rep["bound"])
+    out["gradients_closer_to_fp64_than_ref"] = sum(1 for e in rep["grads"].values()
+                                                   if "missing" not in e and e["gpu_vs_fp64"] <= e["ref_vs_fp64"])
+    return out

@@ -375,6 +375,34 @@ def to_input(xyz_list, scale=50, full=(4096, 4096, 512), seed=0):
     return torch.cat(locs), torch.cat(feats)
 
 
+def seeded_state_dict(shapes, seed=0):
+    """deterministic FPN_Net parameters from (key -> shape), independent of any module's init order: fixtures
+    that would mostly consist of random weights store the seed instead (tests/golden/wide_net.npz).  Keys
+    are visited in sorted order, one CPU generator per key; convolution weights N(0, 2/(K Cin)), BN scales
+    1 + 0.1 N(0,1), BN shifts 0.1 N(0,1), running statistics 0 / 1."""
+    sd = {}
+    for i, k in enumerate(sorted(shapes)):
+        shp = tuple(int(v) for v in shapes[k])
+        g = torch.Generator().manual_seed(1000003 * (seed + 1) + i)
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros(shp)
+        elif k.endswith("running_var"):
+            sd[k] = torch.ones(shp)
+        elif len(shp) == 4:
+            sd[k] = torch.randn(shp, generator=g) * (2.0 / (shp[0] * shp[2])) ** 0.5
+        elif k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            sd[k] = 0.1 * torch.randn(shp, generator=g)
+    return sd
+
+
+def subsample(a, limit=4096, stride=5):
+    """fixture view of a large tensor: flat, every `stride`-th element when it has more than `limit`"""
+    a = np.asarray(a).reshape(-1)
+    return a[::stride] if a.size > limit else a
+
+
 # --------------------------------------------------------------------------------------------
 # the whole backbone on the restated ops, any dtype (float64 = ground truth for tolerance studies)
 # --------------------------------------------------------------------------------------------
@@ -385,9 +413,11 @@ class OracleBackbone(object):
 
     def __init__(self, state_dict, full_scale, n_planes, rpn_map_sizes, dtype=torch.float64, leakiness=0.0,
                  eps=1e-4, fpn_scales_from_top=(4, 3, 2, 1), roi_scales_from_top=(4, 3),
-                 rpn_3d_2d_selector=(1, 2, 3, 4, 5, 6)):
-        self.dt = dtype
-        self.p = {k: v.detach().clone().to(dtype) for k, v in state_dict.items()}
+                 rpn_3d_2d_selector=(1, 2, 3, 4, 5, 6), device="cpu"):
+        # device: where the float arithmetic of this CHECKER runs (the integer rules stay numpy on the host);
+        # "cuda" makes the float64 truth of a full-size building a matter of seconds
+        self.dt, self.dev = dtype, torch.device(device)
+        self.p = {k: v.detach().clone().to(device=self.dev, dtype=dtype) for k, v in state_dict.items()}
         for k, v in self.p.items():
             if "running_" not in k:
                 v.requires_grad_(True)
@@ -399,10 +429,10 @@ class OracleBackbone(object):
         self.rules = {}
 
     def _conv(self, x, w, rules, n_out, swap=False):
-        y = torch.zeros(n_out, w.shape[3], dtype=self.dt)
+        y = torch.zeros(n_out, w.shape[3], dtype=self.dt, device=self.dev)
         for k, r in enumerate(rules):
             if len(r):
-                r = torch.as_tensor(np.asarray(r), dtype=torch.int64)
+                r = torch.as_tensor(np.asarray(r), dtype=torch.int64).to(self.dev)
                 i, o = (r[:, 1], r[:, 0]) if swap else (r[:, 0], r[:, 1])
                 y = y.index_add(0, o, x[i] @ w[k, 0])
         return y
@@ -436,9 +466,9 @@ class OracleBackbone(object):
 
     def forward(self, coords, feats):
         loc, prow, header, table = input_layer_rules(np.asarray(coords), 4)
-        t = torch.as_tensor(np.asarray(table), dtype=torch.int64)
-        f = torch.as_tensor(feats).to(self.dt)
-        x = torch.zeros(header[3], f.shape[1], dtype=self.dt)
+        t = torch.as_tensor(np.asarray(table), dtype=torch.int64).to(self.dev)
+        f = torch.as_tensor(feats).to(device=self.dev, dtype=self.dt)
+        x = torch.zeros(header[3], f.shape[1], dtype=self.dt, device=self.dev)
         for j in range(header[1]):
             sel = t[:, 0] > j
             x[sel] += (1.0 / t[sel, 0].to(self.dt))[:, None] * f[t[sel, 1 + j]]

@@ -129,3 +129,45 @@ def test_ref_backbone_driver_matches_real_fpn_net(gold):
     for i, m in enumerate(list(rpn) + list(roi)):
         order = np.argsort(O.canonical_rank(m.locations().numpy(), m.ss.tolist()))
         np.testing.assert_allclose(m.features.numpy()[order], ge["out%d_feat" % i], rtol=1e-5, atol=1e-6)
+
+
+def _wide_cfg():
+    return dict(full_scale=[512, 512, 512], n_planes=[32, 64, 32, 32, 32, 32, 32, 32, 32],
+                rpn_map_sizes=[[32, 32, 32], [16, 16, 16], [8, 8, 8], [4, 4, 4]])
+
+
+def wide_state_dict(g):
+    return O.seeded_state_dict({k[6:]: g[k] for k in g.files if k.startswith("shape/")}, int(g["seed"]))
+
+
+def test_ref_backbone_driver_matches_real_fpn_net_wide(gold):
+    """the tensor-core-width fixture (tests/golden/wide_net.npz, generated by the reference's own fpn_net.py
+    on seeded parameters): the compiled-reference driver reproduces it, and the float64 OracleBackbone is
+    within the fp32 bound of it (pins the restatement that serves as ground truth at full size)"""
+    g = gold("wide_net")
+    sd = wide_state_dict(g)
+    locs, feats = torch.from_numpy(g["locs"].astype(np.int64)), torch.from_numpy(g["feats"])
+    net = RB.RefBackbone(sd, **_wide_cfg())
+    rpn, roi = net.forward(locs, feats)
+    loss = RB.backbone_loss(rpn, roi)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for i, m in enumerate(list(rpn) + list(roi)):
+        loc = m.locations().numpy()
+        order = np.argsort(O.canonical_rank(loc, m.ss.tolist()))
+        assert np.array_equal(loc[order], g["out%d_loc" % i])
+        np.testing.assert_allclose(m.features.detach().numpy()[order], g["out%d_feat" % i], rtol=1e-5, atol=1e-6)
+    grads = net.grads()
+    n = 0
+    for k in g.files:
+        if k.startswith("grad/"):
+            np.testing.assert_allclose(O.subsample(grads[k[5:]].numpy()), g[k], rtol=1e-4, atol=1e-5)
+            n += 1
+    assert n > 40
+    truth = O.OracleBackbone(sd, **_wide_cfg())
+    trpn, troi = truth.forward(locs.numpy(), feats)
+    for i, (tf, tloc, tss) in enumerate(trpn + troi):
+        order = np.argsort(O.canonical_rank(tloc, tss))
+        assert np.array_equal(tloc[order], g["out%d_loc" % i])
+        ref = g["out%d_feat" % i]
+        assert np.abs(tf.detach().numpy()[order] - ref).max() <= 1e-4 * np.abs(ref).max()
