@@ -118,8 +118,11 @@ __device__ __forceinline__ void bn_fwd_coef(const double *__restrict__ acc, long
     const double dmean = sum / (double)n;
     const double s = sq - dmean * dmean * (double)n;  // sum of squared deviations
     mean = (float)dmean;
-    invstd = powf((float)(s / (double)n) + eps, -0.5f);
-    if (publish) {
+    // train == 2: evaluation with the statistics of the CURRENT batch and the unbiased variance - what the
+    // reference's Python layer does in eval mode with track_running_stats=False (batchNormalization.py:51-56:
+    // features.mean(0) / features.var(0) handed to the C++ eval path); the running buffers are left alone
+    invstd = powf((float)(s / (double)(train == 2 ? n - 1 : n)) + eps, -0.5f);
+    if (publish && train == 1) {
       running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mean;
       running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(s / (double)(n - 1));
     }
@@ -318,6 +321,7 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)C64;
   SCN_CHECK(C > 0 && C <= 4096 && save_mean && save_invstd && running_mean && running_var, "bad BN arguments");
+  SCN_CHECK(train >= 0 && train <= 2, "BN mode %d not in {0 eval, 1 train, 2 eval with batch statistics}", train);
   if (n == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, out, in, out);
@@ -333,7 +337,7 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
                                                                                      0.f, n, C, acc);
     SCN_LAUNCHED();
   }
-  BnFwdArgs a{other, other_used, acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train ? 1 : 0};
+  BnFwdArgs a{other, other_used, acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train};
   const long long total = (long long)n * C;
   const size_t sm = (size_t)2 * C * sizeof(float);
   if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, a, leakiness, n, C);

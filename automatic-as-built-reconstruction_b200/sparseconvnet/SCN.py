@@ -359,7 +359,7 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
             raise RuntimeError("BatchNormalization: %s must be a contiguous CUDA tensor" % nm)
     check(lib.scn_batchnorm_forward(ptr(x), ptr(output_features), ptr(saveMean), ptr(saveInvStd),
                                     ptr(runningMean), ptr(runningVar), ptr(weight), ptr(bias),
-                                    float(eps), float(momentum), 1 if train else 0,
+                                    float(eps), float(momentum), 2 if train == 2 else (1 if train else 0),
                                     float(leakiness), x.size(0), x.size(1), stream()))
 
 

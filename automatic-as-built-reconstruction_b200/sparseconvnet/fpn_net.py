@@ -105,8 +105,9 @@ class FPN_Net(torch.nn.Module):
         if not getattr(net, "rulebooks_built", False):
             self._prebuild_rulebooks(net)
         g = self._layer_graph() if self.use_layer_graph else None
-        if g is not None and g.bn_modules_use_running_buffers(self.training, self):
-            return self.forward_fpn_graph(net, g)
+        mode = g.bn_mode(self.training, self) if g is not None else None
+        if mode is not None:
+            return self.forward_fpn_graph(net, g, mode)
         return self.forward_fpn(self.layers_in[1](net))
 
     # ---- one-call execution of the whole graph (sparseconvnet/graph.py) ----------------------
@@ -150,8 +151,8 @@ class FPN_Net(torch.nn.Module):
             self._graph_cache = g
         return g or None
 
-    def forward_fpn_graph(self, net, g):
-        feats = _graph.GraphFunction.apply(g, net.metadata, self.training, net.features, *g.grad_params)
+    def forward_fpn_graph(self, net, g, bn_mode):
+        feats = _graph.GraphFunction.apply(g, net.metadata, bn_mode, net.features, *g.grad_params)
         by_value = dict(zip(g.outputs, feats))
 
         def wrap(v):

@@ -146,8 +146,16 @@ class LayerGraph(object):
                 self.is_weight[o.p0] = True
         return self
 
-    def bn_modules_use_running_buffers(self, training, root):
-        return training or all(m.track_running_stats for m in root.modules() if isinstance(m, M.BatchNormalization))
+    def bn_mode(self, training, root):
+        """BN mode of one graph execution (scn_batchnorm_forward `train`): 1 training, 0 evaluation with the
+        running buffers, 2 evaluation with batch statistics (track_running_stats=False,
+        batchNormalization.py:51-56); None when the BN layers of `root` disagree (per-layer path then)"""
+        if training:
+            return 1
+        track = set(bool(m.track_running_stats) for m in root.modules() if isinstance(m, M.BatchNormalization))
+        if len(track) > 1:
+            return None
+        return 0 if (not track or track.pop()) else 2
 
     # ---- execution --------------------------------------------------------------------------
     def _param_arrays(self, plist):
@@ -199,7 +207,7 @@ class GraphFunction(Function):
         ptrs, tags = graph._param_arrays(plist)
         macs = c_double()
         _lib.check(_lib.lib.scn_graph_forward(metadata._h, graph._c_ops, len(graph.ops), vals, rows, ptrs, tags,
-                                              _lib.ptr(bn_save), 1 if train else 0, _lib.precision(), _lib.stream(),
+                                              _lib.ptr(bn_save), int(train), _lib.precision(), _lib.stream(),
                                               ctypes.byref(macs)))
         sparseconvnet.forward_pass_multiplyAdd_count += macs.value
         ctx.graph, ctx.metadata_, ctx.keep = graph, metadata, (x0, arena, bn_save, outs)

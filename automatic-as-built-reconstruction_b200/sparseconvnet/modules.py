@@ -440,7 +440,7 @@ class BatchNormalizationFunction(Function):
     @staticmethod
     def forward(ctx, input_features, weight, bias, running_mean, running_var, eps, momentum, train,
                 leakiness):
-        ctx.train = train
+        ctx.train = train is True or train == 1
         ctx.leakiness = leakiness
         n_planes = running_mean.shape[0]
         out = input_features.new_empty(0)
@@ -491,13 +491,14 @@ class BatchNormalization(Module):
     def forward(self, input):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes, \
             (self.nPlanes, input.features.shape)
-        if self.training or self.track_running_stats:
-            mean, var = self.running_mean, self.running_var
-        else:
-            mean, var = input.features.mean(0), input.features.var(0)
+        # eval with track_running_stats=False (every shipped config): the reference computes features.mean(0) /
+        # features.var(0) eagerly and hands them to the eval path (batchNormalization.py:51-56); here the
+        # statistics kernel does it in the same launch pair as training (mode 2: batch statistics, unbiased
+        # variance, running buffers untouched)
+        mode = self.training if (self.training or self.track_running_stats) else 2
         return _like(input, BatchNormalizationFunction.apply(
-            input.features, optionalTensor(self, "weight"), optionalTensor(self, "bias"), mean, var,
-            self.eps, self.momentum, self.training, self.leakiness))
+            input.features, optionalTensor(self, "weight"), optionalTensor(self, "bias"), self.running_mean,
+            self.running_var, self.eps, self.momentum, mode, self.leakiness))
 
     def input_spatial_size(self, out_size):
         return out_size

@@ -197,9 +197,13 @@ int scn_nin_backward(const float *in, float *d_in, const float *d_out, const flo
 
 /* ---- BatchNormalization fused with (Leaky)ReLU (replaces BatchNormalization_updateOutput /
  *      _backward, sparseconvnet.h:21-32, CPU/BatchNormalization.cpp:13-107) ------------
- * train != 0: batch statistics (biased var for normalisation, unbiased for running_var),
+ * train == 1: batch statistics (biased var for normalisation, unbiased for running_var),
  * running stats updated in place with `momentum` weighting the OLD value.
  * train == 0: normalise with running_mean / running_var as passed.
+ * train == 2: evaluation with the statistics of the current batch and the UNBIASED variance, running
+ * buffers untouched - the reference's eval mode with track_running_stats=False
+ * (sparseconvnet/batchNormalization.py:51-56 computes features.mean(0) / features.var(0) eagerly and
+ * passes them to the train == 0 path; here the statistics kernel of the train path does it).
  * weight / bias may be NULL.  Unlike the reference, d_out is NOT modified in place. */
 int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *save_invstd,
                           float *running_mean, float *running_var, const float *weight,

@@ -531,12 +531,11 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
     for k, p in net.named_parameters():
         if "grad/" + k in g.files:
             assert p.grad is not None, k
-            ref_err = rel(g["grad/" + k], truth64[k])              # the reference's own rounding error
-            # tf32: 50+ layers of 10-bit-mantissa products behind the stem gradient: stated bound 1e-1 (BN scale gradients cancel heavily)
-            # ill-conditioned sums (BN shifts: sum of a masked gradient that mostly cancels) lose digits
-            # in ANY finite precision - the reference's fp32 is itself 1.5e-2 off on the worst one
-            tf32_bound = max(5e-1, 15 * ref_err)
-            assert rel(p.grad, truth64[k]) <= (tf32_bound if scn.PREC in REDUCED else 1e-4), (k, ref_err)
+            # fp32 modes: 1e-4 of the float64 truth on every tensor of this narrow net (FFMA tiles).  tf32 / bf16:
+            # individual tensors are not bounded (ill-conditioned BN-shift gradients sit at 0.4 / 0.8 of their
+            # maximum, a bound covering them cannot fail): the gate is the vector L2 below
+            if scn.PREC not in REDUCED:
+                assert rel(p.grad, truth64[k]) <= 1e-4, k
             num += float((p.grad.detach().cpu().double() - truth64[k]).pow(2).sum())
             den += float(truth64[k].pow(2).sum())
             n += 1
@@ -545,7 +544,8 @@ def test_backbone_matches_reference_golden(scn, gold, truth64):
     assert n > 40
     # whole gradient vector: relative L2 error (tf32: individual ill-conditioned tensors vary with the
     # summation order between kernel versions, the vector as a whole does not)
-    assert (num / den) ** 0.5 <= ({"tf32": 6e-2, "bf16": 3e-1}.get(scn.PREC, 1e-4))
+    # stated tolerances of the reduced modes = measured x3 (tests/test_full_parity.py REDUCED_TOL)
+    assert (num / den) ** 0.5 <= ({"tf32": 1.3e-1, "bf16": 3e-1}.get(scn.PREC, 1e-4))
     for k, v in net.state_dict().items():
         if "running_" in k and "after/" + k in g.files:
             assert rel(v, g["after/" + k]) <= feat_tol, k
