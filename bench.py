@@ -1,7 +1,11 @@
 """bench.py - the sparse3d backbone (FPN_Net) forward+backward on synthetic SUNCG-shaped buildings.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode train|infer]
+                    [--batch B] [--precision fp32|fp32_ffma|tf32|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+--mode infer times the evaluation forward (no_grad, batch statistics as every shipped config has
+track_running_stats=False) of one 2M-point 3-storey building per GPU with no collective (BASELINE configs[4]).
 
 A step = one pass of the hot path over one batch: fresh Metadata (voxel hashing + every rulebook
 rebuilt, as in real training), FPN_Net forward, loss = sum(features^2) over the 6 rpn + 2 roi maps,
@@ -10,6 +14,8 @@ BASELINE.json configs[1]: one 300k-point building, batch 1 (SURVEY.md section 8d
 Metric: active voxels/s (sum over samples of nActive at scale 0 / time), whole job over all GPUs.
 
   value     inputs resident in HBM when the timed region starts
+  value_inline  the same step through the reference's own call net([coords, feats]) - no prefetcher, voxel
+            hashing and all rulebooks built inside the step
   e2e       same step through the public API from pinned HOST buffers (coords + features H2D and a
             D2H read of the loss inside the timed region)
   roofline  conv gather-GEMM class: algorithmic bytes (SURVEY.md 8d formula) / CUDA-event time of
@@ -175,9 +181,9 @@ def _parity():
     return parity
 
 
-def cpu_reference_step(sd, locs, feats):
-    """one fwd+bwd of the compiled reference CPU path (fresh Metadata); returns seconds"""
-    return _parity().reference_step(sd, locs, feats, REF_CFG)[0]
+def cpu_reference_step(sd, locs, feats, train=True):
+    """one fwd+bwd (train) / eval forward of the compiled reference CPU path (fresh Metadata); returns seconds"""
+    return _parity().reference_step(sd, locs, feats, REF_CFG, train=train)[0]
 
 
 def run_reference(args, rank, world):
@@ -187,14 +193,18 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     # one reference step of the full 300k-point workload takes ~4.2 s on the box's host cores: up to 30 steps
     # (~2 minutes) run the workload itself, longer runs a bounded 60k-point sample of it
+    train = args.mode == "train"
     points = args.points if (args.steps + args.warmup) <= 30 else min(args.points, 60000)
+    if not train and (args.steps + args.warmup) * args.points > 12_000_000:      # 2M-point forward: ~10 s each
+        points = min(args.points, 300000)
     locs, feats = make_batch(points, args.floors, args.batch, 0)
     na = n_active0(locs)
     sd = reference_state_dict()
-    sample = "%d building(s) x %d points (nActive %d), fwd+bwd, fresh Metadata each step" % (args.batch, points, na)
+    sample = "%d building(s) x %d points (nActive %d), %s, fresh Metadata each step" % (
+        args.batch, points, na, "fwd+bwd" if train else "eval forward")
     for _ in range(args.warmup):
-        cpu_reference_step(sd, locs, feats)
-    ts = [cpu_reference_step(sd, locs, feats) for _ in range(args.steps)]
+        cpu_reference_step(sd, locs, feats, train)
+    ts = [cpu_reference_step(sd, locs, feats, train) for _ in range(args.steps)]
     sec = float(np.mean(ts))
     val = na / sec
     print(json.dumps({
@@ -210,14 +220,22 @@ def run_reference(args, rank, world):
 
 def workload_config(args, points=None):
     pts = points or args.points
-    which = ("BASELINE configs[1]" if (args.batch, pts, args.floors) == (1, 300000, 1) else
-             "BASELINE configs[1] geometry, non-default size")
-    return {"workload": "FPN_Net sparse3d backbone fwd+bwd, %d x %dk-point synthetic building per GPU (%s)"
-                        % (args.batch, pts // 1000, which),
+    train = args.mode == "train"
+    if train:
+        which = {(1, 300000, 1): "BASELINE configs[1]", (2, 300000, 1): "BASELINE configs[2] backbone, batch 2 per GPU",
+                 (4, 300000, 1): "BASELINE configs[3] backbone, 4 buildings per GPU"}.get(
+                     (args.batch, pts, args.floors), "BASELINE configs[1] geometry, non-default size")
+    else:
+        which = ("BASELINE configs[4]: large-scene inference, one building per GPU, no collective"
+                 if (args.batch, pts, args.floors) == (1, 2000000, 3) else "inference, non-default size")
+    return {"workload": "FPN_Net sparse3d backbone %s, %d x %dk-point synthetic building per GPU (%s)"
+                        % ("fwd+bwd" if train else "eval forward (no_grad)", args.batch, pts // 1000, which),
+            "mode": args.mode,
             "per_gpu_batch": args.batch, "points_per_building": points or args.points, "floors": args.floors,
             "full_scale": FULL_SCALE, "planes": PLANES, "precision": args.precision,
             "parallelism": "dp%d" % args.gpus,
-            "prefetch": "Metadata (hash grids + rulebooks) of batch i+1 built on a side stream during batch i",
+            "prefetch": "Metadata (hash grids + rulebooks) of batch i+1 built on a side stream during batch i"
+                        " (value, e2e); value_inline = plain net([coords, feats]), builds inside the step",
             "l2": "256 MiB flush buffer written between steps; per-step activations (GBs) exceed the 126 MB L2"}
 
 
@@ -235,22 +253,32 @@ def run_b200(args, rank, local_rank, world):
                       fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
                       downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8], rpn_map_sizes=RPN_SIZES, voxel_scale=50,
                       rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95, track_running_stats=False)
-    net = net.to(dev).train()
+    train = args.mode == "train"
+    net = net.to(dev).train() if train else net.to(dev).eval()
     scn.broadcast_parameters(net)
-    bucket = scn.GradBucket(net.parameters())
+    bucket = scn.GradBucket(net.parameters()) if train else None
     locs, feats = make_batch(args.points, args.floors, args.batch, rank * args.batch)   # weak scaling
     na_local = n_active0(locs)
     locs_pin, feats_pin = locs.pin_memory(), feats.pin_memory()
     locs_dev, feats_dev = locs.to(dev), feats.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(coords, f):
+    def train_step(coords, f):
         bucket.zero()
         rpn, roi = net([coords, f])
         loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
         loss.backward()
         bucket.allreduce_mean()
         return loss
+
+    def infer_step(coords, f):
+        # inference (engine/inference_3d.py:17-30): eval mode, no_grad, whole buildings per rank, no collective;
+        # the step's result is a checksum of the 8 output maps (what the detector heads would consume)
+        with torch.no_grad():
+            rpn, roi = net([coords, f])
+            return torch.stack([m.features.sum() for m in list(rpn) + list(roi)]).sum()
+
+    step = train_step if train else infer_step
 
     # The integer work of a batch (voxel hashing, 13 grids, 25 rulebooks) depends on its coordinates
     # only: like the reference's DataLoader workers it runs one batch ahead - here on a side stream
@@ -295,6 +323,25 @@ def run_b200(args, rank, local_rank, world):
     clk = clocks.stop() if rank == 0 else None
     step(locs_pin, feats_pin.to(dev, non_blocking=True))
     ms_e2e, _ = timed(args.steps, True)
+
+    def timed_inline(n_steps):
+        """the reference's own call, net([coords, feats]) with nothing prepared: voxel hashing and every
+        rulebook are built inside the step, on the step's stream (what tools/train_net_sparse3d.py does)"""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n_steps):
+            flush.fill_(1)
+            step(locs_dev, feats_dev)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_inline = timed_inline(args.steps)
 
     na_t = torch.tensor([na_local], device=dev, dtype=torch.float64)
     if world > 1:
@@ -344,6 +391,9 @@ def run_b200(args, rank, local_rank, world):
             "config": workload_config(args),
             "e2e": {"value": na_total / sec_e2e, "unit": "active voxels/s", "ms_per_step": sec_e2e * 1e3,
                     "h2d_bytes_per_step": int(locs.numel() * 8 + feats.numel() * 4), "d2h_bytes_per_step": 4},
+            "value_inline": {"value": na_total / (ms_inline * 1e-3 / args.steps), "unit": "active voxels/s",
+                             "ms_per_step": ms_inline / args.steps,
+                             "what": "plain net([coords, feats]) - no prefetcher, rulebook builds inside the step"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "conv gather-GEMM (fwd + dX), all launches of a step",
@@ -351,10 +401,41 @@ def run_b200(args, rank, local_rank, world):
                          "unit": "GB/s", "frac": ach / hbm_peak if hbm_peak else None, "traffic": traffic,
                          "launches_per_step": g["regions"] // 2, "ms_per_step": g["ms"] / 2},
             "kernel_classes": classes,
-            "grad_allreduce_bytes": bucket.nbytes() if world > 1 else 0,
+            "grad_allreduce_bytes": bucket.nbytes() if (world > 1 and train) else 0,
         }
         failed = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not train:
+            P = _parity()
+            cores = os.cpu_count()
+            torch.set_num_threads(cores)
+            sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+            with torch.no_grad():
+                rpn_g, roi_g = net([locs_dev, feats_dev])
+            gpu_maps = [(m.get_spatial_locations().numpy(), m.features.detach().cpu(), m.spatial_size.tolist())
+                        for m in list(rpn_g) + list(roi_g)]
+            t, ref_maps, _ = P.reference_step(sd, locs, feats, REF_CFG, train=False)
+            out["cpu_baseline"] = {"value": na_local / t, "unit": "active voxels/s", "cores": cores,
+                                   "kind": "reference", "seconds_per_step": t,
+                                   "sample": "1 eval forward (same %d-point batch, nActive %d) on the compiled "
+                                             "reference CPU SparseConvNet, fresh Metadata, no warm-up"
+                                             % (len(locs), na_local)}
+            worst, same = 0.0, True
+            for g_, r_ in zip(gpu_maps, ref_maps):
+                gl, gf = P._canon(*g_)
+                rl, rf = P._canon(*r_)
+                same = same and gl.shape == rl.shape and bool(np.array_equal(gl, rl))
+                if same:
+                    worst = max(worst, P._rel(gf, rf))
+            tol = REDUCED_FEATURE_TOL.get(args.precision, 1e-4)
+            out["parity"] = {"mode": "eval forward (batch statistics: track_running_stats=False)",
+                             "active_site_sets_equal": same, "max_rel_feature_err_vs_reference_cpu": worst,
+                             "maps_compared": len(ref_maps), "bound": tol,
+                             "note": "the reference's own fp32 rounding at this size is ~1e-4 (train-mode "
+                                     "three-way report); a float64 evaluation is not run at 2M points",
+                             "ok": bool(same and worst <= 2 * tol)}
+            if not out["parity"]["ok"]:
+                failed = "parity outside the stated bound: %s" % json.dumps(out["parity"])
+        if world == 1 and not args.no_cpu_baseline and train:
             # Parity at the benchmark's own size (oracle/parity.py): the 8 output maps and every live parameter
             # gradient of this very batch, library vs the compiled reference CPU run (which is also the
             # cpu_baseline sample) vs a float64 evaluation of the same graph.
@@ -400,14 +481,21 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: fwd+bwd (+ gradient all-reduce for N > 1); infer: eval forward, no_grad, one "
+                         "2M-point 3-storey building per GPU by default (BASELINE configs[4]), no collective")
     ap.add_argument("--batch", type=int, default=1, help="buildings per GPU")
-    ap.add_argument("--points", type=int, default=300000)
-    ap.add_argument("--floors", type=int, default=1)
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--floors", type=int, default=None)
     ap.add_argument("--precision", default=os.environ.get("SCN_B200_PRECISION", "fp32"),
                     choices=["fp32", "fp32_ffma", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.points is None:
+        args.points = 300000 if args.mode == "train" else 2000000
+    if args.floors is None:
+        args.floors = 1 if args.mode == "train" else 3
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
