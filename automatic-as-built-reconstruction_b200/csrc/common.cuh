@@ -60,7 +60,7 @@ inline int dev_alloc_t(T **p, size_t n, cudaStream_t s) {
 // Per-op scratch (packed weights, split-K partials, BN sums, dW partials): one grow-only buffer per
 // (stream, slot).  Ops on a stream are serialised, so the next op may overwrite the previous op's
 // scratch; this replaces a cudaMallocAsync/cudaFreeAsync pair per op (~3 us of host time each).
-enum WsSlot { WS_PACKED_W = 0, WS_SPLITK = 1, WS_BN = 2, WS_DW_PARTIAL = 3, WS_WT = 4, WS_PAD_X = 5, WS_PAD_W = 6, WS_SLOTS = 7 };
+enum WsSlot { WS_PACKED_W = 0, WS_SPLITK = 1, WS_BN = 2, WS_DW_PARTIAL = 3, WS_WT = 4, WS_PAD_X = 5, WS_PAD_W = 6, WS_CHAIN = 7, WS_SLOTS = 8 };
 int workspace(void **p, int slot, size_t bytes, cudaStream_t s);
 template <typename T>
 inline int workspace_t(T **p, int slot, size_t n, cudaStream_t s) {

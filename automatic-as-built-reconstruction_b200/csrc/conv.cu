@@ -97,7 +97,7 @@ k_osgemm_ffma(const float *__restrict__ X, const float *__restrict__ W,
         ras[j] = (idx >= 0 && kc + kk < Cin) ? __ldg(X + (long long)idx * Cin + kc + kk) : 0.f;
       }
     }
-    const float *Wk = W + (long long)(tb.k_flip >= 0 ? tb.k_flip - k : k) * Cin * Cout;
+    const float *Wk = W + (long long)(tb.k_flip >= 0 ? tb.k_flip - (tb.k_base + k) : tb.k_base + k) * Cin * Cout;
     if (VB) {
       if (tid < BK * BN / 4) {
         const int kk = tid / (BN / 4), n4 = tid % (BN / 4);
@@ -210,6 +210,7 @@ TileView make_view(const TileBook &tb, int k_flip) {
   v.identity = tb.identity ? 1 : 0;
   v.n_tiles = tb.n_tiles;
   v.k_flip = k_flip;
+  v.k_base = tb.k_base;
   v.perm = tb.perm;
   v.tile_mask = tb.tile_mask;
   v.tile_off = tb.tile_off;
@@ -249,33 +250,33 @@ static int pad_rows(const float *X, long long rows, int Cin, float **out, cudaSt
   return 0;
 }
 
-// Y[stationary rows] = bias + sum_k X[partner_k] @ W[k]   (W: [K,Cin,Cout] row-major)
-int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
-           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip,
-           const int64_t *weight_tag) {
-  if (tb.n_tiles == 0) return 0;
+__global__ void k_accumulate(float *__restrict__ y, const float *__restrict__ t, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] += t[i];
+}
+
+// one tile book: Y[stationary rows] = bias + sum over the book's offsets of X[partner_k] @ W[k]; K = offsets of
+// the whole filter (W: [K,Cin,Cout] row-major)
+static int osgemm_book(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
+                       const TileBook &tb, int K, double bytes, double flops, int precision, int transpose_w,
+                       cudaStream_t s, int k_flip, const int64_t *weight_tag) {
   const TileView tv = make_view(tb, k_flip);
-  // algorithmic bytes (SURVEY 8d): every feature row once, the weights once, 8 B per pair.  The timed
-  // region is the gather-GEMM kernel itself (weight packing / split-K reduce are outside it).
-  const double bytes = 4.0 * ((double)tb.n_partner * Cin + (double)tb.n_rows * Cout) +
-                       4.0 * tb.K * Cin * Cout + (tb.identity ? 0.0 : 8.0 * tb.n_pairs);
-  const double flops = 2.0 * tb.n_pairs * Cin * Cout;
   int r = 1;
   if (!transpose_w && !tb.identity && pad_ok(Cin, Cout, precision)) {
     float *xp = nullptr, *wp = nullptr;
     SCN_TRY(pad_rows(X, tb.n_partner, Cin, &xp, s));
-    SCN_TRY(workspace_t(&wp, WS_PAD_W, (size_t)tb.K * PAD_C * Cout, s));
-    k_pad_w_rows<<<cdiv((long long)tb.K * PAD_C * Cout, 256), 256, 0, s>>>(W, wp, tb.K, Cin, PAD_C, Cout);
+    SCN_TRY(workspace_t(&wp, WS_PAD_W, (size_t)K * PAD_C * Cout, s));
+    k_pad_w_rows<<<cdiv((long long)K * PAD_C * Cout, 256), 256, 0, s>>>(W, wp, K, Cin, PAD_C, Cout);
     SCN_LAUNCHED();
-    r = osgemm_tc(xp, wp, bias, Y, PAD_C, Cout, tb.n_rows, tv, tb.K, precision, 0, s, bytes, flops, nullptr);
+    r = osgemm_tc(xp, wp, bias, Y, PAD_C, Cout, tb.n_rows, tv, K, tb.K, precision, 0, s, bytes, flops, nullptr);
   } else if (precision != SCN_PRECISION_FP32)
-    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, tb.K, precision, transpose_w, s, bytes, flops, weight_tag);
+    r = osgemm_tc(X, W, bias, Y, Cin, Cout, tb.n_rows, tv, K, tb.K, precision, transpose_w, s, bytes, flops, weight_tag);
   if (r > 0) {  // 0 = done, negative = -(error); positive = shape outside the tensor path (e.g. Cin = 9)
     float *wt = nullptr;
     r = 0;
     if (transpose_w) {
-      r = workspace_t(&wt, WS_WT, (size_t)tb.K * Cin * Cout, s);
-      if (!r) r = transpose_weights(W, wt, tb.K, Cout, Cin, s);   // W is [K][Cout=N][Cin=Kd] -> [K][Kd][N]
+      r = workspace_t(&wt, WS_WT, (size_t)K * Cin * Cout, s);
+      if (!r) r = transpose_weights(W, wt, K, Cout, Cin, s);   // W is [K][Cout=N][Cin=Kd] -> [K][Kd][N]
     }
     const float *w = transpose_w ? wt : W;
     prof_begin(PROF_GEMM, s);
@@ -287,6 +288,34 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
     r = -r;
   }
   return r;
+}
+
+// Y[stationary rows] = bias + sum_k X[partner_k] @ W[k]   (W: [K,Cin,Cout] row-major).  Filters of more than
+// MAX_K offsets come as a chain of tile books (metadata.cuh): the first book writes Y, every further one its
+// own partial into a scratch buffer that is then added (rare: FPN_Net's [1,1,64] z-collapse, 4^3 / 5^3 filters).
+int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin, int Cout,
+           const TileBook &tb, int precision, int transpose_w, cudaStream_t s, int k_flip,
+           const int64_t *weight_tag) {
+  if (tb.n_tiles == 0) return 0;
+  int K = 0;
+  for (const TileBook *b = &tb; b; b = b->next) K = b->k_base + b->K;
+  // algorithmic bytes (SURVEY 8d): every feature row once, the weights once, 8 B per pair.  The timed
+  // region is the gather-GEMM kernel itself (weight packing / split-K reduce are outside it).
+  const double bytes = 4.0 * ((double)tb.n_partner * Cin + (double)tb.n_rows * Cout) +
+                       4.0 * K * Cin * Cout + (tb.identity ? 0.0 : 8.0 * tb.n_pairs);
+  const double flops = 2.0 * tb.n_pairs * Cin * Cout;
+  SCN_TRY(osgemm_book(X, W, bias, Y, Cin, Cout, tb, K, bytes, flops, precision, transpose_w, s, k_flip, weight_tag));
+  for (const TileBook *b = tb.next; b; b = b->next) {
+    float *part = nullptr;
+    const long long n = (long long)tb.n_rows * Cout;
+    SCN_TRY(workspace_t(&part, WS_CHAIN, (size_t)n, s));
+    SCN_TRY(osgemm_book(X, W, nullptr, part, Cin, Cout, *b, K, 0.0, 0.0, precision, transpose_w, s, k_flip, weight_tag));
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    k_accumulate<<<(int)blocks, 256, 0, s>>>(Y, part, n);
+    SCN_LAUNCHED();
+  }
+  return 0;
 }
 
 // Wt[k][co][ci] = W[k][ci][co]
@@ -404,7 +433,7 @@ k_dw_partial(const float *__restrict__ X, const float *__restrict__ dY,
   }
 }
 
-struct KFirst { int v[MAX_K + 1]; };
+struct KFirst { int v[MAX_KT + 1]; };
 
 // cc = Cin*Cout elements of dW[k]; ccp = elements of one partial (Cin padded up for narrow inputs: the
 // first Cin rows of a partial are the real ones)

@@ -8,6 +8,7 @@ struct TileView {            // device view of a TileBook, passed by value to ke
   int identity;
   int n_tiles;
   int k_flip;                // >= 0: table offset k uses weight slice k_flip - k (submanifold dX), else k
+  int k_base;                // first filter offset of this book: its table offset j is filter offset k = k_base + j
   const int32_t *perm;
   const uint32_t *tile_mask;
   const int32_t *tile_off;
@@ -28,8 +29,9 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Kd, 
 
 // tensor-core variants. Return 0 = done, >0 = shape/precision not handled (caller uses the FFMA
 // kernels), <0 = -(error) with scn_last_error set.
+// K = offsets of the whole filter (what the weight tensor / its packed images hold), Kb = offsets of the tile book
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N,
-              long long n_rows, const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s,
+              long long n_rows, const TileView &tv, int K, int Kb, int precision, int transpose_w, cudaStream_t s,
               double prof_bytes, double prof_flops, const int64_t *weight_tag);
 int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const DwWork *work, float *partial,
                   int Cin, int Cout, int xcol, int ycol, int n_work, long long ident_n, int ident_chunk,

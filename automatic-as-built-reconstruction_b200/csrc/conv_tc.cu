@@ -615,7 +615,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (g >= NSB) MBW(bar_emptyA + ((g - NSB) % NSA) * 8, ((g - NSB) / NSA) & 1, 1);
           const int st = split + lst * splits;
           const int e = st / kchunks, c = st - e * kchunks;
-          const int kw = tb.k_flip >= 0 ? tb.k_flip - sK[e] : sK[e];   // weight slice of this table offset
+          const int kw = tb.k_flip >= 0 ? tb.k_flip - (tb.k_base + sK[e]) : tb.k_base + sK[e];   // weight slice of this table offset
           const uint32_t bytes = (uint32_t)B_STAGE;
 #ifdef SCN_EXPERIMENT_NO_B          // timing experiment only (wrong results): what if weight slices were free?
           if (g >= NSB) { mbar_arrive(bar_fullB + stage * 8); continue; }
@@ -1114,7 +1114,7 @@ static bool tf32_shape_ok(const float *X, const float *W, const float *bias, flo
 // Y[stationary] = bias + sum_k X[partner_k] @ Wg[k], where Wg[k] is W[k] (transpose_w = 0, W is
 // [K][Kd][N]) or W[k]^T (transpose_w = 1, W is [K][N][Kd]).
 int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int Kd, int N, long long n_rows,
-              const TileView &tv, int K, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
+              const TileView &tv, int K, int Kb, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
               double prof_flops, const int64_t *weight_tag) {
   using namespace tc;
   if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 1;
@@ -1145,7 +1145,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   // ring depths: 2-3 weight-slice stages, then as many gathered-row stages as fit beside the metadata
   // slots (the gathers are latency-bound: depth = bytes in flight)
   const int b_stage = Smem::b_stage_bytes(NW, x3);
-  const int meta_slot = K * TILE_M * 4 + TILE_M * 4 + 64;
+  const int meta_slot = Kb * TILE_M * 4 + TILE_M * 4 + 64;
   // 3xTF32 with the low-order halves in TMEM: three weight stages (the weight ring is latency-bound: a TMA
   // bulk copy takes ~1.2 us, so two 32 KB stages paced the step at 0.7 us)
   const int nsb = x3 == 2 ? 4 : ((x3 && LO_TMEM) ? 3 : (b_stage > 16384 ? 2 : 3));
@@ -1159,13 +1159,13 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   // offsets) give up the third metadata slot when that buys another stage.
   int ms = MS;
   const int kchunks_ = Kd / KC;
-  if (fit(2) > fit(MS) && K * kchunks_ >= 32 && tv.n_tiles * ncb * 2 > num_sms()) ms = 2;   // (never with split work items)
+  if (fit(2) > fit(MS) && Kb * kchunks_ >= 32 && tv.n_tiles * ncb * 2 > num_sms()) ms = 2;   // (never with split work items)
   int nsa_fit = fit(ms);
   static const int env_nsa = getenv("SCN_B200_GEMM_NSA") ? atoi(getenv("SCN_B200_GEMM_NSA")) : 0;   // experiments
   if (env_nsa >= 3 && nsa_fit > env_nsa) nsa_fit = env_nsa;
   if (nsa_fit < 3 || nsb > nsa_fit) return 1;   // (the weight ring is never deeper than the gathered-row ring)
   const int depth = nsa_fit - 2;
-  const Smem L(NW, K, depth + 2, nsb, x3, ms);
+  const Smem L(NW, Kb, depth + 2, nsb, x3, ms);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ae = cudaSuccess;
@@ -1194,7 +1194,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   const int kchunks = (Kd + KC - 1) / KC;
   if (tv.n_tiles * ncb * 2 <= num_sms() && !tv.identity) {
     splits = num_sms() / (tv.n_tiles * ncb);
-    const int max_split = (K * kchunks + 3) / 4;
+    const int max_split = (Kb * kchunks + 3) / 4;
     if (splits > max_split) splits = max_split;
     if (splits > 32) splits = 32;
     if (splits < 1) splits = 1;
@@ -1211,7 +1211,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   if (sched_counters(&sched, s)) return -1;
   prof_begin(PROF_GEMM, s);
 #define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
-  k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, K, n_rows, tv, cols, ypart, \
+  k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, Kb, n_rows, tv, cols, ypart, \
                                                                 n_items, splits, nsb, sched, ms)
 #define SCN_OSGEMM_DEPTH(T3)                                                                                  \
   switch (depth) {                                                                                            \

@@ -75,6 +75,10 @@ static void grid_free(Grid *g, cudaStream_t s) {
 }
 
 static void tilebook_free(TileBook &tb, cudaStream_t s) {
+  if (tb.next) {
+    tilebook_free(*tb.next, s);
+    delete tb.next;
+  }
   dev_free(tb.perm, s);
   dev_free(tb.tile_mask, s);
   dev_free(tb.tile_off, s);
@@ -509,30 +513,56 @@ static int tilebook_phase2(TileBook &tb, const int32_t *T, int64_t n_entries, cu
   return 0;
 }
 
+// the chain of tile books over a table T [K, n_rows]: one book per group of <= MAX_K offsets (phase 1 of each;
+// meta_slot + g receives the entry total of book g)
+static int tilebook_chain_phase1(TileBook &head, const int32_t *T, int K, int64_t n_rows, int64_t n_partner,
+                                 int32_t *meta_slot, cudaStream_t s) {
+  TileBook *tb = &head;
+  for (int k0 = 0, g = 0; k0 < K; k0 += MAX_K, ++g) {
+    if (g > 0) {
+      tb->next = new TileBook();
+      tb = tb->next;
+    }
+    tb->k_base = k0;
+    SCN_TRY(tilebook_phase1(*tb, T + (long long)k0 * n_rows, std::min(MAX_K, K - k0), n_rows, n_partner, meta_slot + g, s));
+  }
+  return 0;
+}
+static int tilebook_chain_phase2(TileBook &head, const int32_t *T, const int32_t *entry_totals, int64_t n_pairs,
+                                 cudaStream_t s) {
+  int g = 0;
+  for (TileBook *tb = &head; tb; tb = tb->next, ++g) {
+    SCN_TRY(tilebook_phase2(*tb, T + (long long)tb->k_base * tb->n_rows, entry_totals[g], s));
+    tb->n_pairs = n_pairs;       // (algorithmic-bytes accounting: the whole rulebook, counted on the first book only)
+  }
+  return 0;
+}
+static int n_books(int K) { return (K + MAX_K - 1) / MAX_K; }
+
 // pairs + tb_out from t_out with a single read-back
 static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
-  const int K = rb->K;
+  const int K = rb->K, G = n_books(K);
   const int64_t n = rb->n_out;
   const long long total = (long long)K * n;
   SCN_CHECK(total < (1LL << 31), "rulebook table too large (%lld entries)", total);
   int32_t *pos = nullptr, *meta = nullptr;
   SCN_TRY(dev_alloc_t(&pos, (size_t)total + 1, s));
-  SCN_TRY(dev_alloc_t(&meta, (size_t)K + 8, s));
+  SCN_TRY(dev_alloc_t(&meta, (size_t)K + 8 + 2 * G, s));
   if (total > 0) {
     k_flag_table<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, total);
     SCN_LAUNCHED();
   }
   SCN_TRY(exclusive_scan_i32(pos, pos, total, s));
-  k_pair_offsets<<<1, 64, 0, s>>>(pos, n, K, meta);
+  k_pair_offsets<<<1, MAX_KT + 32, 0, s>>>(pos, n, K, meta);
   SCN_LAUNCHED();
-  SCN_TRY(tilebook_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s));
+  SCN_TRY(tilebook_chain_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s));
   // strided rulebooks also carry the in-stationary lists (conv dX, deconv forward); building them
   // here shares this read-back, so the backward pass never synchronises
   const bool both = rb->kind == 1 && rb->t_in != nullptr;
-  if (both) SCN_TRY(tilebook_phase1(rb->tb_in, rb->t_in, K, rb->n_in, rb->n_out, meta + K + 2, s));
-  int64_t *hs = host_scratch(64);
+  if (both) SCN_TRY(tilebook_chain_phase1(rb->tb_in, rb->t_in, K, rb->n_in, rb->n_out, meta + K + 1 + G, s));
+  int64_t *hs = host_scratch((size_t)(K + 8 + 2 * G) / 2 + 8);
   int32_t *h32 = (int32_t *)hs;
-  SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)(K + 3) * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)(K + 1 + 2 * G) * 4, cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back: pair counts + entry totals
   for (int k = 0; k <= K; ++k) rb->pair_off[k] = h32[k];
   for (int k = 0; k < K; ++k) rb->counts[k] = h32[k + 1] - h32[k];
@@ -542,12 +572,8 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
     k_emit_pairs<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, n, total, rb->pairs);
     SCN_LAUNCHED();
   }
-  SCN_TRY(tilebook_phase2(rb->tb_out, rb->t_out, h32[K + 1], s));
-  rb->tb_out.n_pairs = rb->total_pairs;
-  if (both) {
-    SCN_TRY(tilebook_phase2(rb->tb_in, rb->t_in, h32[K + 2], s));
-    rb->tb_in.n_pairs = rb->total_pairs;
-  }
+  SCN_TRY(tilebook_chain_phase2(rb->tb_out, rb->t_out, h32 + K + 1, rb->total_pairs, s));
+  if (both) SCN_TRY(tilebook_chain_phase2(rb->tb_in, rb->t_in, h32 + K + 1 + G, rb->total_pairs, s));
   SCN_TRY(ensure_dw_work(rb, s));
   dev_free(pos, s);
   dev_free(meta, s);
@@ -562,7 +588,7 @@ static int build_t_in(RuleBook *rb, cudaStream_t s) {
   if (rb->total_pairs > 0) {
     int32_t *poff = nullptr;
     SCN_TRY(dev_alloc_t(&poff, (size_t)rb->K + 1, s));
-    int32_t h[MAX_K + 1];
+    int32_t h[MAX_KT + 1];
     for (int k = 0; k <= rb->K; ++k) h[k] = (int32_t)rb->pair_off[k];
     // pageable source: the copy is staged before return, so the stack array may die
     SCN_CUDA(cudaMemcpyAsync(poff, h, (size_t)(rb->K + 1) * 4, cudaMemcpyHostToDevice, s));
@@ -589,14 +615,14 @@ int ensure_tilebook(RuleBook *rb, bool stationary_out, cudaStream_t s) {
   }
   SCN_CHECK(!stationary_out, "internal: tb_out must be built with the rulebook");
   SCN_TRY(build_t_in(rb, s));
+  const int G = n_books(rb->K);
   int32_t *meta = nullptr;
-  SCN_TRY(dev_alloc_t(&meta, 4, s));
-  SCN_TRY(tilebook_phase1(tb, rb->t_in, rb->K, rb->n_in, rb->n_out, meta, s));
-  int32_t *h32 = (int32_t *)host_scratch(16);
-  SCN_CUDA(cudaMemcpyAsync(h32, meta, 4, cudaMemcpyDeviceToHost, s));
+  SCN_TRY(dev_alloc_t(&meta, (size_t)G + 4, s));
+  SCN_TRY(tilebook_chain_phase1(tb, rb->t_in, rb->K, rb->n_in, rb->n_out, meta, s));
+  int32_t *h32 = (int32_t *)host_scratch((size_t)G / 2 + 8);
+  SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)G * 4, cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));  // documented read-back (first backward use only)
-  SCN_TRY(tilebook_phase2(tb, rb->t_in, h32[0], s));
-  tb.n_pairs = rb->total_pairs;
+  SCN_TRY(tilebook_chain_phase2(tb, rb->t_in, h32, rb->total_pairs, s));
   dev_free(meta, s);
   return 0;
 }
@@ -674,8 +700,8 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
   SCN_CHECK(g, "no active sites at spatial size [%lld,%lld,%lld]", (long long)ss[0],
             (long long)ss[1], (long long)ss[2]);
   const int64_t K64 = filter[0] * filter[1] * filter[2];
-  SCN_CHECK(filter[0] > 0 && filter[1] > 0 && filter[2] > 0 && K64 <= MAX_K,
-            "filter volume %lld not in 1..%d", (long long)K64, MAX_K);
+  SCN_CHECK(filter[0] > 0 && filter[1] > 0 && filter[2] > 0 && K64 <= MAX_KT,
+            "filter volume %lld not in 1..%d", (long long)K64, MAX_KT);
   RuleBook *rb = new RuleBook();
   rb->kind = 0;
   memcpy(rb->in_ss, ss, 24); memcpy(rb->out_ss, ss, 24); memcpy(rb->filter, filter, 24);
@@ -839,7 +865,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   SCN_CHECK(gi, "no active sites at spatial size [%lld,%lld,%lld]", (long long)in_ss[0],
             (long long)in_ss[1], (long long)in_ss[2]);
   const int64_t K64 = filter[0] * filter[1] * filter[2];
-  SCN_CHECK(K64 >= 1 && K64 <= MAX_K, "filter volume %lld not in 1..%d", (long long)K64, MAX_K);
+  SCN_CHECK(K64 >= 1 && K64 <= MAX_KT, "filter volume %lld not in 1..%d", (long long)K64, MAX_KT);
   Filter3 f;
   R3s R3;
   int R = 1;
@@ -1154,7 +1180,9 @@ int scn_rulebook_stats(scn_metadata_t *m, int kind, const int64_t *in_ss, const 
   TileBook &tb = out_side ? rb->tb_out : rb->tb_in;
   SCN_CHECK(tb.built, "tile book not built yet");
   stats[0] = rb->total_pairs;
-  stats[1] = tb.identity ? (int64_t)tb.n_tiles * TILE_M : tb.n_entries * TILE_M;
+  stats[1] = 0;
+  for (const TileBook *b = &tb; b; b = b->next)
+    stats[1] += b->identity ? (int64_t)b->n_tiles * TILE_M : b->n_entries * TILE_M;
   stats[2] = tb.n_tiles;
   return 0;
 }

@@ -8,7 +8,8 @@
 namespace scn {
 
 constexpr int TILE_M = 128;       // output rows per gather-GEMM tile
-constexpr int MAX_K = 32;         // filter volume limit (tile masks are 32-bit)
+constexpr int MAX_K = 32;         // offsets per tile book (tile masks are 32-bit); larger filters chain tile books
+constexpr int MAX_KT = 512;       // filter volume limit of a rulebook (8^3; the reference has none)
 constexpr uint64_t EMPTY_KEY = ~0ULL;
 
 struct Grid {                     // one spatial scale (Metadata.h:28-34 SparseGrids)
@@ -26,7 +27,10 @@ struct Grid {                     // one spatial scale (Metadata.h:28-34 SparseG
 struct TileBook {
   bool built = false;
   bool identity = false;          // 1x1x1 filter: partner(row) = row, no lists kept
-  int K = 0;
+  int K = 0;                      // offsets covered by THIS book (<= MAX_K)
+  int k_base = 0;                 // first filter offset of this book
+  TileBook *next = nullptr;       // filters of more than MAX_K offsets: one book per group of <= MAX_K offsets (the
+                                  // gather-GEMM runs once per book and sums; FPN_Net's [1,1,64] z-collapse, 4^3, 5^3)
   int64_t n_rows = 0;             // stationary rows
   int64_t n_partner = 0;          // rows of the gathered side
   int n_tiles = 0;
@@ -47,8 +51,8 @@ struct RuleBook {                 // Metadata.h:35 RuleBook + its derived gather
   int K = 0;
   int64_t n_in = 0, n_out = 0;
   bool identity = false;
-  int64_t counts[MAX_K];          // pairs per offset
-  int64_t pair_off[MAX_K + 1];    // host copy of the prefix
+  int64_t counts[MAX_KT];         // pairs per offset
+  int64_t pair_off[MAX_KT + 1];   // host copy of the prefix
   int64_t total_pairs = 0;
   int32_t *pairs = nullptr;       // [total_pairs,2] (in,out), offsets contiguous, sorted by out
   int32_t *t_out = nullptr;       // [K,n_out] in-row feeding out-row at offset k (-1 none)

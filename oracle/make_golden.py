@@ -142,6 +142,29 @@ def dump_rulebooks(coords, ss, name):
     return out
 
 
+def zcollapse64():
+    """[1,1,64] z-collapse (FPN_Net with RPN_SCALES_FROM_TOP [5,4,3] on a z = 512 index space,
+    configs/Stanford_walls/*.yaml): a filter volume of 64 through the reference Metadata"""
+    D = ref_backbone.scn_refdump()
+    L = ref_backbone.L
+    ss, zs = [24, 20, 64], [24, 20, 1]
+    rng = np.random.RandomState(4)
+    c = np.concatenate([np.concatenate([(rng.rand(1200, 3) * np.array(ss)).astype(np.int64),
+                                        np.full((1200, 1), b, np.int64)], 1) for b in range(2)])
+    m = D.RefMetadata3()
+    m.inputLayer(L(ss), torch.from_numpy(c), 0, 4)
+    loc0 = m.getSpatialLocations(L(ss)).numpy()
+    r0 = scn_oracle.canonical_rank(loc0, ss)
+    rules = m.getRuleBook(L(ss), L(zs), L([1, 1, 64]), L([1, 1, 1]))
+    locz = m.getSpatialLocations(L(zs)).numpy()
+    rz = scn_oracle.canonical_rank(locz, zs)
+    out = {"coords": c, "ss": np.array(ss), "locz_sorted": locz[np.argsort(rz)].astype(np.int16)}
+    for k, r in enumerate(rules):
+        out["zc_%d" % k] = scn_oracle.canonical_pairs(r.numpy(), r0, rz).astype(np.int32)
+    np.savez_compressed(os.path.join(GOLD, "zcollapse64.npz"), **out)
+    return out
+
+
 def appendix_c():
     coords = np.array([[0, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 0], [3, 3, 3, 0], [2, 2, 2, 0], [1, 0, 0, 1],
                        [0, 0, 0, 1]], np.int64)
@@ -237,15 +260,20 @@ def wide_net_golden(ref_scn):
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == "wide":      # only the fixture added in round 2
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":      # only the fixtures added in round 2
         wide_net_golden(reference_package())
         print("wide_net.npz", os.path.getsize(os.path.join(GOLD, "wide_net.npz")))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "zc64":
+        zcollapse64()
+        print("zcollapse64.npz", os.path.getsize(os.path.join(GOLD, "zcollapse64.npz")))
         return
     appendix_c()
     dump_rulebooks(random_cloud(1500, [40, 36, 24], 2, seed=1), [48, 48, 32], "cloud_rulebooks")
     ref_scn = reference_package()
     small_net_golden(ref_scn)
     wide_net_golden(ref_scn)
+    zcollapse64()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

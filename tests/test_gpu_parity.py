@@ -305,7 +305,46 @@ def test_strided_convolution_and_deconvolution(scn, cin, cout):
     assert rel(t.leaf.grad, _input_grad(t, c, odx)) <= scn.TOL
 
 
-@pytest.mark.parametrize("Z", [4, 8, 16, 32])
+def test_zcollapse64_rulebook_matches_reference_golden(scn, gold):
+    """filter volume 64 (two chained tile books): rulebook against the reference Metadata's"""
+    g = gold("zcollapse64")
+    ss, zs = g["ss"].tolist(), [int(g["ss"][0]), int(g["ss"][1]), 1]
+    t, _ = make_input(scn, g["coords"], ss, C=1)
+    m = t.metadata
+    rules = m.getRuleBook(ss, zs, [1, 1, 64], [1, 1, 1])
+    loc0, locz = m.getSpatialLocations(ss).numpy(), m.getSpatialLocations(zs).numpy()
+    r0, rz = O.canonical_rank(loc0, ss), O.canonical_rank(locz, zs)
+    assert np.array_equal(locz[np.argsort(rz)], g["locz_sorted"])
+    assert len(rules) == 64
+    for k, r in enumerate(rules):
+        assert np.array_equal(canon(r, r0, rz), g["zc_%d" % k]), k
+
+
+@pytest.mark.parametrize("cin,cout,fs", [(32, 32, 5), (64, 32, 4), (9, 16, 5)])
+def test_submanifold_convolution_large_filters(scn, cin, cout, fs):
+    """filter volumes 125 / 64 (> 32 offsets: chained tile books, the odd filter through the mirrored dX lists)"""
+    ss = [64, 64, 16]
+    c = _cloud()
+    t, _ = make_input(scn, c, ss, C=cin)
+    conv = scn.SubmanifoldConvolution(3, cin, cout, fs, False).cuda()
+    y = conv(t)
+    loc = t.get_spatial_locations().numpy()
+    rules = O.submanifold_rules(loc, ss, [fs] * 3)
+    r0 = O.canonical_rank(loc, ss)
+    got = t.metadata.getSubmanifoldRuleBook(ss, [fs] * 3)
+    assert len(got) == fs ** 3
+    for k in range(fs ** 3):
+        assert np.array_equal(canon(got[k], r0, r0), canon(rules[k], r0, r0)), k
+    x, w = t.features.detach().cpu(), conv.weight.detach().cpu()
+    assert rel(y.features, O.conv_forward(x, w, rules, len(loc), None)) <= scn.TOL
+    dy = torch.randn_like(y.features)
+    y.features.backward(dy)
+    dx, dw, _ = O.conv_backward(x, dy.cpu(), w, rules)
+    assert rel(conv.weight.grad, dw) <= scn.TOL
+    assert rel(t.leaf.grad, _input_grad(t, c, dx)) <= scn.TOL
+
+
+@pytest.mark.parametrize("Z", [4, 8, 16, 32, 48, 64])
 def test_z_collapse_convolution(scn, Z):
     ss = [32, 32, Z]
     c = _cloud(2500, (30, 30, Z), seed=Z)
@@ -325,6 +364,7 @@ def test_z_collapse_convolution(scn, Z):
     ody[po] = dy.cpu()[pg]
     odx, odw, _ = O.conv_backward(x, ody, w, rules)
     assert rel(conv.weight.grad, odw) <= scn.TOL
+    assert rel(t.leaf.grad, _input_grad(t, c, odx)) <= scn.TOL
 
 
 @pytest.mark.parametrize("limit", [1, 3])

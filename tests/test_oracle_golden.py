@@ -110,3 +110,16 @@ def test_empty_inputs():
     assert all(len(r) == 0 for r in O.submanifold_rules(loc, [8, 8, 8], [3, 3, 3]))
     l1, rules = O.conv_rules(loc, [8, 8, 8], [2, 2, 2], [2, 2, 2], [4, 4, 4])
     assert len(l1) == 0 and len(rules) == 8
+
+
+def test_zcollapse64_rules_match_reference_golden(gold):
+    """filter volume 64 ([1,1,64] z-collapse): the restated rule generator against the reference Metadata"""
+    g = gold("zcollapse64")
+    ss, zs = g["ss"].tolist(), [int(g["ss"][0]), int(g["ss"][1]), 1]
+    loc0, _, _, _ = O.input_layer_rules(g["coords"], 4)
+    locz, rules = O.conv_rules(loc0, ss, [1, 1, 64], [1, 1, 1], zs)
+    r0, rz = O.canonical_rank(loc0, ss), O.canonical_rank(locz, zs)
+    assert np.array_equal(locz[np.argsort(rz)], g["locz_sorted"])
+    assert len(rules) == 64
+    for k, r in enumerate(rules):
+        assert np.array_equal(O.canonical_pairs(r, r0, rz), g["zc_%d" % k]), k
