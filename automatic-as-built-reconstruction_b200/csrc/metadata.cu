@@ -23,35 +23,6 @@ static bool g_tile_grouping = true;
 // ---------------------------------------------------------------------------------------
 // hash grid
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t pack_key(int x, int y, int z, int b) {
-  return ((uint64_t)(uint32_t)b << 48) | ((uint64_t)(uint32_t)x << 32) |
-         ((uint64_t)(uint32_t)y << 16) | (uint64_t)(uint32_t)z;
-}
-__device__ __forceinline__ bool coord_ok(int x, int y, int z) {
-  return ((unsigned)x | (unsigned)y | (unsigned)z) < 65536u;
-}
-__device__ __forceinline__ uint32_t hash_insert(uint64_t *hk, uint32_t mask, uint64_t key) {
-  uint32_t slot = (uint32_t)mix64(key) & mask;
-  while (true) {
-    unsigned long long prev =
-        atomicCAS((unsigned long long *)&hk[slot], (unsigned long long)EMPTY_KEY,
-                  (unsigned long long)key);
-    if (prev == EMPTY_KEY || prev == key) return slot;
-    slot = (slot + 1) & mask;
-  }
-}
-__device__ __forceinline__ int hash_find(const uint64_t *__restrict__ hk,
-                                         const int32_t *__restrict__ hv, uint32_t mask,
-                                         uint64_t key) {
-  uint32_t slot = (uint32_t)mix64(key) & mask;
-  while (true) {
-    const uint64_t k = hk[slot];
-    if (k == key) return hv[slot];
-    if (k == EMPTY_KEY) return -1;
-    slot = (slot + 1) & mask;
-  }
-}
-
 static uint32_t table_capacity(int64_t n) {
   uint64_t c = 64;
   while (c < (uint64_t)(2 * n + 2)) c <<= 1;

@@ -12,6 +12,38 @@ constexpr int MAX_K = 32;         // offsets per tile book (tile masks are 32-bi
 constexpr int MAX_KT = 512;       // filter volume limit of a rulebook (8^3; the reference has none)
 constexpr uint64_t EMPTY_KEY = ~0ULL;
 
+#ifdef __CUDACC__
+// ---- hash grid: open addressing, linear probing, key = batch<<48 | x<<32 | y<<16 | z ------------------------
+__device__ __forceinline__ uint64_t pack_key(int x, int y, int z, int b) {
+  return ((uint64_t)(uint32_t)b << 48) | ((uint64_t)(uint32_t)x << 32) |
+         ((uint64_t)(uint32_t)y << 16) | (uint64_t)(uint32_t)z;
+}
+__device__ __forceinline__ bool coord_ok(int x, int y, int z) {
+  return ((unsigned)x | (unsigned)y | (unsigned)z) < 65536u;
+}
+__device__ __forceinline__ uint32_t hash_insert(uint64_t *hk, uint32_t mask, uint64_t key) {
+  uint32_t slot = (uint32_t)mix64(key) & mask;
+  while (true) {
+    unsigned long long prev =
+        atomicCAS((unsigned long long *)&hk[slot], (unsigned long long)EMPTY_KEY,
+                  (unsigned long long)key);
+    if (prev == EMPTY_KEY || prev == key) return slot;
+    slot = (slot + 1) & mask;
+  }
+}
+__device__ __forceinline__ int hash_find(const uint64_t *__restrict__ hk,
+                                         const int32_t *__restrict__ hv, uint32_t mask,
+                                         uint64_t key) {
+  uint32_t slot = (uint32_t)mix64(key) & mask;
+  while (true) {
+    const uint64_t k = hk[slot];
+    if (k == key) return hv[slot];
+    if (k == EMPTY_KEY) return -1;
+    slot = (slot + 1) & mask;
+  }
+}
+#endif
+
 struct Grid {                     // one spatial scale (Metadata.h:28-34 SparseGrids)
   int64_t ss[3] = {0, 0, 0};
   int64_t n_active = 0;

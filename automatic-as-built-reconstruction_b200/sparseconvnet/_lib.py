@@ -101,6 +101,10 @@ _sig = {
     "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                              c_void_p]),
     "scn_scale_inplace": (c_int, [c_void_p, c_float, c_int64, c_void_p]),
+    "scn_roi_align_rotated_3d_forward": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_void_p, c_int64, c_float,
+                                                 I64P, c_int, c_void_p, c_void_p]),
+    "scn_roi_align_rotated_3d_backward": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_void_p, c_int64, c_float,
+                                                  I64P, c_int, c_void_p, c_void_p]),
     "scn_launch_count": (c_int64, []),
     "scn_rulebook_stats": (c_int, [c_void_p, c_int, I64P, I64P, I64P, I64P]),
     "scn_set_tile_grouping": (c_int, [c_int]),

@@ -293,6 +293,25 @@ int scn_set_gemm_grid_limit(int max_ctas);
 /* 0: tiles in natural row order, 1 (default): rows grouped by neighbour mask */
 int scn_set_tile_grouping(int enabled);
 
+/* ---- ROIAlignRotated3D sampled from the sparse map -----------------------
+ * Replaces the pair  sparse_3d_to_dense_2d(input_s3d)  (SparseConvNet/sparseconvnet/tools_3d_2d.py:7-26: a dense
+ * [B,C,X,Y,Z] tensor cropped to max active coordinate + 1)  +  _C.roi_align_rotated_3d_forward / _backward
+ * (maskrcnn_benchmark/layers/roi_align_rotated_3d.py:14-57 ->
+ * maskrcnn_benchmark/csrc/ROIAlignRotated3D.h, csrc/cuda/ROIAlignRotated3D_cuda.cu:357-454): the trilinear
+ * corners are looked up in the scale's hash grid, inactive corners contribute 0 (= the zero-filled dense tensor).
+ * feats [nActive(ss), n_planes] device; rois [n_rois, 8] device float (batch, center_w, center_h, center_z,
+ * width, height, zsize, theta in degrees - same meaning and axis convention as the reference: the dense H axis is
+ * the sparse x axis, W the sparse y axis); pooled = {pooled_height, pooled_width, pooled_zsize};
+ * out [n_rois, n_planes, pooled_height, pooled_width, pooled_zsize] device.
+ * backward: d_feats [nActive, n_planes] is zero-filled, then receives the gradient of the ACTIVE sites (what
+ * SparseToDense's backward keeps of the reference's dense gradient). */
+int scn_roi_align_rotated_3d_forward(scn_metadata_t *m, const int64_t *spatial_size, const float *feats,
+                                     int64_t n_planes, const float *rois, int64_t n_rois, float spatial_scale,
+                                     const int64_t *pooled, int sampling_ratio, float *out, void *stream);
+int scn_roi_align_rotated_3d_backward(scn_metadata_t *m, const int64_t *spatial_size, const float *d_out,
+                                      int64_t n_planes, const float *rois, int64_t n_rois, float spatial_scale,
+                                      const int64_t *pooled, int sampling_ratio, float *d_feats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
