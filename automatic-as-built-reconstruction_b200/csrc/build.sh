@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 ${SCN_NVCC_EXTRA}"
 OUT=../libscn_b200.so
-SRCS="common.cu metadata.cu conv.cu conv_tc.cu bn.cu io.cu graph.cu roi.cu"
+SRCS="common.cu metadata.cu conv.cu conv_tc.cu bn.cu io.cu graph.cu roi.cu rpn.cu"
 mkdir -p build
 pids=()
 for f in $SRCS; do

@@ -44,4 +44,9 @@ void prepack_weights_end();
 
 int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, cudaStream_t s);
 
+// dW[k] = X[in_k]^T @ dY[out_k] for every offset (xcol / ycol: which pair column indexes X / dY); d_bias = column sums
+int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, RuleBook *rb, int xcol, int ycol,
+                int precision, cudaStream_t s);
+int bias_grad(const float *d_out, float *d_bias, long long n, int C, cudaStream_t s);
+
 }  // namespace scn

@@ -148,7 +148,110 @@ __global__ void k_quant_emit(const double *__restrict__ xyz, long long n, double
   o[3] = batch_idx;
 }
 
+// ---- batched voxelisation front end ------------------------------------------
+// points [N, C] float32 (columns 0-2 = xyz in metres) of B buildings back to back, first[b] = first point of
+// building b.  a = xyz @ M in float64 (data3d/suncg_utils/suncg_dataset.py:126-137: M = eye(3) * scale times the
+// augmentations), a -= a.min(0) per building (:140-147), keep 0 <= a < full_scale (:171-183), truncate.
+struct Vox { double m[9]; long long full[3]; double scale; };
+
+__global__ void k_fill_double(double *p, double v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__device__ __forceinline__ int vox_building(const int64_t *__restrict__ first, int B, long long i) {
+  int lo = 0, hi = B;                       // last b with first[b] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (first[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// a[d] = (x m[0][d] + y m[1][d]) + z m[2][d], every operation rounded separately (no FMA): exact - and therefore
+// equal to numpy's matmul in any summation order - whenever M is diagonal (the shipped configs: zoom / rotation off)
+__device__ __forceinline__ void vox_transform(const float *__restrict__ p, const Vox &v, double a[3]) {
+  const double x = p[0], y = p[1], z = p[2];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    a[d] = __dadd_rn(__dadd_rn(__dmul_rn(x, v.m[d]), __dmul_rn(y, v.m[3 + d])), __dmul_rn(z, v.m[6 + d]));
+}
+
+// per-building minimum of the transformed coordinates: a block owns VOX_PER_BLOCK consecutive points; when they
+// all belong to one building (all but <= B - 1 blocks) it reduces in shared memory and issues 3 atomics
+constexpr int VOX_PER_BLOCK = 256 * 8;
+__global__ void __launch_bounds__(256)
+k_vox_min(const float *__restrict__ pts, int C, long long n, const int64_t *__restrict__ first, int B,
+          Vox v, double *__restrict__ mn /* [B,3] */) {
+  __shared__ double sm[3][256];
+  const long long p0 = (long long)blockIdx.x * VOX_PER_BLOCK;
+  const long long p1 = min(p0 + VOX_PER_BLOCK, n);
+  const int b0 = vox_building(first, B, p0), b1 = vox_building(first, B, p1 - 1);
+  double m[3] = {1e300, 1e300, 1e300};
+  for (long long i = p0 + threadIdx.x; i < p1; i += 256) {
+    double a[3];
+    vox_transform(pts + i * C, v, a);
+    if (b0 == b1) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) m[d] = fmin(m[d], a[d]);
+    } else {
+      const int b = vox_building(first, B, i);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) atomic_min_double(&mn[b * 3 + d], a[d]);
+    }
+  }
+  if (b0 != b1) return;                      // (block-uniform)
+#pragma unroll
+  for (int d = 0; d < 3; ++d) sm[d][threadIdx.x] = m[d];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sm[d][threadIdx.x] = fmin(sm[d][threadIdx.x], sm[d][threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) atomic_min_double(&mn[b0 * 3 + threadIdx.x], sm[threadIdx.x][0]);
+}
+
+__global__ void k_vox_flag(const float *__restrict__ pts, int C, long long n, const int64_t *__restrict__ first, int B,
+                           Vox v, const double *__restrict__ mn, int32_t *__restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[3];
+  vox_transform(pts + i * C, v, a);
+  const int b = vox_building(first, B, i);
+  bool k = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double q = __dsub_rn(a[d], mn[b * 3 + d]);
+    k = k && (q >= 0.0) && (q < (double)v.full[d]);
+  }
+  flag[i] = k ? 1 : 0;
+}
+
+__global__ void k_vox_emit(const float *__restrict__ pts, int C, long long n, const int64_t *__restrict__ first, int B,
+                           Vox v, const double *__restrict__ mn, const int32_t *__restrict__ pos,
+                           int64_t *__restrict__ coords, float *__restrict__ feats, int xyz_feature) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = pos[i];
+  if (pos[i + 1] == p) return;
+  double a[3];
+  vox_transform(pts + i * C, v, a);
+  const int b = vox_building(first, B, i);
+  int64_t *o = coords + (long long)p * 4;
+  float *f = feats + (long long)p * C;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double q = __dsub_rn(a[d], mn[b * 3 + d]);
+    o[d] = (int64_t)q;                                               // trunc, q >= 0 (a.long())
+    f[d] = xyz_feature ? (float)__ddiv_rn(q, v.scale) : pts[i * C + d];   // b[:,0:3] = a / scale (:160-162)
+  }
+  o[3] = b;
+  for (int c = 3; c < C; ++c) f[c] = pts[i * C + c];
+}
+
 }  // namespace scn
+
 
 using namespace scn;
 
@@ -269,6 +372,45 @@ int scn_quantize_points(const double *xyz, int64_t n, double scale, const int64_
   SCN_CUDA(cudaMemcpyAsync(h32, pos + n, 4, cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));
   *n_kept = h32[0];
+  dev_free(mn, s);
+  dev_free(pos, s);
+  return 0;
+}
+
+int scn_voxelize_batch(const float *points, int64_t n, int64_t n_cols, const int64_t *first_dev, int64_t n_buildings,
+                       const double *matrix, double scale, const int64_t *full_scale, int xyz_feature,
+                       int64_t *coords_out, float *feats_out, int64_t *n_kept, void *stream) {
+  SCN_CHECK(full_scale && n_kept && matrix, "null argument");
+  SCN_CHECK(n_cols >= 3, "voxelize: points need at least the 3 xyz columns, got %lld", (long long)n_cols);
+  SCN_CHECK(n < (1LL << 31), "voxelize: %lld points do not fit the int32 row space", (long long)n);
+  cudaStream_t s = (cudaStream_t)stream;
+  *n_kept = 0;
+  if (n == 0 || n_buildings == 0) return 0;
+  SCN_CHECK(points && first_dev && coords_out && feats_out, "null pointer");
+  prof_begin(PROF_IO, s);
+  Vox v;
+  for (int i = 0; i < 9; ++i) v.m[i] = matrix[i];
+  for (int d = 0; d < 3; ++d) v.full[d] = full_scale[d];
+  v.scale = scale;
+  double *mn = nullptr;
+  int32_t *pos = nullptr;
+  SCN_TRY(dev_alloc_t(&mn, (size_t)n_buildings * 3, s));
+  SCN_TRY(dev_alloc_t(&pos, (size_t)n + 1, s));
+  k_fill_double<<<cdiv(n_buildings * 3, 256), 256, 0, s>>>(mn, 1e300, n_buildings * 3);
+  SCN_LAUNCHED();
+  const int C = (int)n_cols, B = (int)n_buildings;
+  k_vox_min<<<cdiv(n, VOX_PER_BLOCK), 256, 0, s>>>(points, C, n, first_dev, B, v, mn);
+  SCN_LAUNCHED();
+  k_vox_flag<<<cdiv(n, 256), 256, 0, s>>>(points, C, n, first_dev, B, v, mn, pos);
+  SCN_LAUNCHED();
+  SCN_TRY(exclusive_scan_i32(pos, pos, n, s));
+  k_vox_emit<<<cdiv(n, 256), 256, 0, s>>>(points, C, n, first_dev, B, v, mn, pos, coords_out, feats_out, xyz_feature);
+  SCN_LAUNCHED();
+  int32_t *h32 = (int32_t *)host_scratch(16);
+  SCN_CUDA(cudaMemcpyAsync(h32, pos + n, 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));    // documented read-back: the batch's row count (tensor shapes)
+  *n_kept = h32[0];
+  prof_end(PROF_IO, s, (double)n * n_cols * 4.0 + (double)*n_kept * (32.0 + n_cols * 4.0), 0);
   dev_free(mn, s);
   dev_free(pos, s);
   return 0;

@@ -57,6 +57,8 @@ _sig = {
     "scn_get_spatial_locations_device": (c_int, [c_void_p, I64P, c_void_p, c_void_p]),
     "scn_quantize_points": (c_int, [c_void_p, c_int64, c_double, I64P, c_int64, c_void_p, c_void_p,
                                     I64P, c_void_p]),
+    "scn_voxelize_batch": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, POINTER(c_double), c_double, I64P,
+                                   c_int, c_void_p, c_void_p, I64P, c_void_p]),
     "scn_input_layer_prepare": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_int, c_int, c_int64,
                                         c_int, c_void_p, I64P]),
     "scn_build_plan": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_int,
@@ -101,6 +103,12 @@ _sig = {
     "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                              c_void_p]),
     "scn_scale_inplace": (c_int, [c_void_p, c_float, c_int64, c_void_p]),
+    "scn_grid_anchors": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_float, POINTER(c_float), c_void_p, c_void_p,
+                                 c_int64, c_void_p]),
+    "scn_rpn_head_forward": (c_int, [c_void_p, c_int64, c_int64] + [c_void_p] * 4 + [c_int64, c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "scn_rpn_head_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_int64] + [c_void_p] * 10 + [c_int, c_void_p]),
     "scn_roi_align_rotated_3d_forward": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_void_p, c_int64, c_float,
                                                  I64P, c_int, c_void_p, c_void_p]),
     "scn_roi_align_rotated_3d_backward": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_void_p, c_int64, c_float,

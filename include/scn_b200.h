@@ -79,6 +79,21 @@ int scn_quantize_points(const double *xyz, int64_t n, double scale, const int64_
                         int64_t batch_idx, int64_t *coords_out, uint8_t *keep_out,
                         int64_t *n_kept, void *stream);
 
+/* Whole-batch front end: the dataset's per-building quantisation AND the collate, on the device, fed by ONE float32
+ * buffer (replaces SUNCGDataset.__getitem__, data3d/suncg_utils/suncg_dataset.py:126-188, and trainMerge,
+ * data3d/data.py:25-37).  points: DEVICE float32 [n, n_cols], columns 0-2 = xyz in metres, the rest features
+ * (rgb, normal), the buildings of the batch back to back; first_dev: DEVICE int64 [n_buildings] first point of
+ * each building; matrix: HOST double[9], row-major, the dataset's `m` (eye(3) * scale times its zoom / flip /
+ * rotation augmentations): a = xyz @ matrix in float64, a -= a.min(0) per building, rows with 0 <= a < full_scale
+ * kept, coordinates truncated.  coords_out: DEVICE int64 [n,4] (x,y,z,building) and feats_out: DEVICE float32
+ * [n, n_cols], both compacted in input order; xyz_feature != 0 writes a / scale into feature columns 0-2 (:160-162).
+ * n_kept is read back to the host (one sync).  Results equal the numpy pipeline bit for bit when `matrix` is
+ * diagonal; with rotation / zoom the float64 products are summed as (x m0 + y m1) + z m2, which numpy's BLAS
+ * matmul does not pin. */
+int scn_voxelize_batch(const float *points, int64_t n, int64_t n_cols, const int64_t *first_dev,
+                       int64_t n_buildings, const double *matrix, double scale, const int64_t *full_scale,
+                       int xyz_feature, int64_t *coords_out, float *feats_out, int64_t *n_kept, void *stream);
+
 /* ---- InputLayer / OutputLayer (replaces InputLayer_updateOutput / _updateGradInput,
  *      OutputLayer_updateOutput / _updateGradInput: pybind.cpp:154-170,
  *      CPU/IOLayers.cpp:45-140, Metadata::inputLayer Metadata.cpp:406-417,
@@ -311,6 +326,31 @@ int scn_roi_align_rotated_3d_forward(scn_metadata_t *m, const int64_t *spatial_s
 int scn_roi_align_rotated_3d_backward(scn_metadata_t *m, const int64_t *spatial_size, const float *d_out,
                                       int64_t n_planes, const float *rois, int64_t n_rois, float spatial_scale,
                                       const int64_t *pooled, int sampling_ratio, float *d_feats, void *stream);
+
+/* ---- RPN: anchors and head on the device ----------------------------------
+ * scn_grid_anchors replaces AnchorGenerator.grid_anchors + examples_bidx_2_sizes
+ * (maskrcnn_benchmark/modeling/rpn/anchor_generator_sparse3d.py:88-104, 137-146, 174-185), which copy every
+ * level's get_spatial_locations() to the host each step: anchors_out DEVICE float [nActive(ss) * n_anchors, 7] =
+ * ((x,y,z) / voxel_scale * stride, 0,0,0,0) + base_anchors[a] in the reference's flatten order [site, anchor, 7];
+ * scope_out (optional) DEVICE int64 [batch_size, 2] = row range of every sample times n_anchors.
+ * base_anchors DEVICE float [n_anchors, 7]; stride HOST float[3]. */
+int scn_grid_anchors(scn_metadata_t *m, const int64_t *spatial_size, const float *base_anchors, int64_t n_anchors,
+                     float voxel_scale, const float *stride, float *anchors_out, int64_t *scope_out,
+                     int64_t batch_size, void *stream);
+/* RPNHead.forward (maskrcnn_benchmark/modeling/rpn/rpn_sparse3d.py:97-131) on the row-major [n, C] features of one
+ * level: hidden = relu(x Wc^T + bc), logits [n, n_cls] = hidden Wl^T + bl, reg [n, n_box] = hidden Wr^T + br
+ * (n_cls = A * S, n_box = 7 * A * S; row-major [n, A*S] IS the reference's [1, n, A, S] after its permute + reshape).
+ * Weights in nn.Conv2d layout [Cout, Cin(,1,1)], consumed in place.  `hidden` [n, C] is an output the caller keeps
+ * for the backward pass; d_hidden [n, C] is caller-provided scratch; d_x may be NULL. */
+int scn_rpn_head_forward(const float *x, int64_t n, int64_t n_planes, const float *w_conv, const float *b_conv,
+                         const float *w_cls, const float *b_cls, int64_t n_cls, const float *w_box,
+                         const float *b_box, int64_t n_box, float *hidden, float *logits, float *reg, int precision,
+                         void *stream);
+int scn_rpn_head_backward(const float *x, const float *hidden, int64_t n, int64_t n_planes, const float *w_conv,
+                          const float *w_cls, int64_t n_cls, const float *w_box, int64_t n_box,
+                          const float *d_logits, const float *d_reg, float *d_hidden, float *d_x, float *dw_conv,
+                          float *db_conv, float *dw_cls, float *db_cls, float *dw_box, float *db_box, int precision,
+                          void *stream);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,29 @@ def quantize_points(xyz, scale, full_scale, batch_idx=0):
     return np.concatenate([c, np.full((len(c), 1), batch_idx, np.int64)], 1), keep
 
 
+def voxelize_batch(buildings, scale, full_scale, matrix=None, xyz_feature=True):
+    """dataset + collate for a batch of raw buildings (float32 [n_i, C], columns 0-2 = xyz in metres):
+    suncg_dataset.py:126-137 a = np.matmul(a, m) in float64 with m = eye(3) * scale (times the augmentations);
+    :140-147 a += -a.min(0); :160-162 b[:, 0:3] = a / scale; :171-188 keep 0 <= a < full_scale, a.long();
+    data3d/data.py:25-37 concatenate, append the sample index.  Returns (locs int64 [N,4], feats float32 [N,C])."""
+    m = np.eye(3) * float(scale) if matrix is None else np.asarray(matrix, dtype=np.float64).reshape(3, 3)
+    locs, feats = [], []
+    for i, pts in enumerate(buildings):
+        pts = np.asarray(pts)
+        assert pts.dtype == np.float32
+        a = np.matmul(pts[:, 0:3], m)                      # float32 @ float64 -> float64, as in the reference
+        if len(a):
+            a = a + (-a.min(0))
+        b = pts.copy()
+        if xyz_feature:
+            b[:, 0:3] = a / scale
+        keep = (a.min(1) >= 0) * np.all(a < np.asarray(full_scale)[np.newaxis, :], 1) if len(a) else np.zeros(0, bool)
+        a, b = a[keep], b[keep]
+        locs.append(np.concatenate([a.astype(np.int64), np.full((len(a), 1), i, np.int64)], 1))
+        feats.append(b)
+    return np.concatenate(locs), np.concatenate(feats)
+
+
 # --------------------------------------------------------------------------------------------
 # input layer (Metadata/IOLayersRules.h:19-125, CPU/IOLayers.cpp:12-46)
 # --------------------------------------------------------------------------------------------

@@ -646,3 +646,56 @@ def test_layer_graph_equals_per_layer_path(scn):
     assert n_live > 60
     for k in rb:
         assert rel(ra[k], rb[k]) <= 1e-6, k
+
+
+# ---------------------------------------------------------------------------------------------
+# voxelisation front end for whole batches
+# ---------------------------------------------------------------------------------------------
+def _raw_buildings(sizes, seed=0, L=(19.0, 16.3, 3.0)):
+    out = []
+    for i, n in enumerate(sizes):
+        xyz = (O.building(n, L=L, seed=seed + i) if n >= 60 else np.random.RandomState(seed + i).rand(n, 3) * L)
+        xyz = xyz.astype(np.float32)
+        rest = np.random.RandomState(100 + i).randn(n, 6).astype(np.float32)
+        out.append(np.concatenate([xyz, rest], 1))
+    return out
+
+
+@pytest.mark.parametrize("sizes", [[5000], [3000, 0, 4100, 1], [20000, 30000]])
+def test_voxelize_batch_matches_dataset_and_collate(scn, sizes):
+    """bit-exact coordinates and features against the numpy dataset + collate restatement, ragged / empty buildings
+    included; the building with a huge extent loses the points beyond full_scale exactly as numpy does"""
+    raw = _raw_buildings(sizes)
+    if len(sizes) > 1 and sizes[0]:
+        raw[0][: sizes[0] // 4, 2] += 15.0                  # z beyond 512 / 50 m: dropped by the range filter
+    want_l, want_f = O.voxelize_batch(raw, 50, [4096, 4096, 512])
+    got_l, got_f = scn.voxelize_batch([torch.from_numpy(b).pin_memory() for b in raw], 50, [4096, 4096, 512])
+    assert got_l.is_cuda and got_l.dtype == torch.int64 and got_f.dtype == torch.float32
+    assert np.array_equal(got_l.cpu().numpy(), want_l)
+    assert np.array_equal(got_f.cpu().numpy(), want_f)
+    # without the xyz feature the columns pass through; a diagonal augmentation matrix (flip / anisotropic zoom) stays exact
+    m = np.diag([-50.0, 49.5, 50.0])
+    want_l, want_f = O.voxelize_batch(raw, 50, [4096, 4096, 512], matrix=m, xyz_feature=False)
+    got_l, got_f = scn.voxelize_batch([torch.from_numpy(b).cuda() for b in raw], 50, [4096, 4096, 512], matrix=m,
+                                      xyz_feature=False)
+    assert np.array_equal(got_l.cpu().numpy(), want_l) and np.array_equal(got_f.cpu().numpy(), want_f)
+
+
+def test_voxel_loader_feeds_the_backbone(scn, gold):
+    """raw buildings -> VoxelLoader (upload, voxelise, prepare on a side stream) -> FPN_Net: same outputs as the
+    host-side numpy pipeline feeding the plain call"""
+    g = gold("small_net")
+    net = _small_net(scn, g).train()
+    batches = [_raw_buildings([6000, 6000], seed=s, L=(9.0, 8.0, 3.0)) for s in (0, 7)]
+    pinned = [[torch.from_numpy(b).pin_memory() for b in raw] for raw in batches]
+    loader = scn.VoxelLoader(pinned, net.prepare, 50, [512] * 3)
+    n = 0
+    for (prepared, feats), raw in zip(loader, batches):
+        rpn, roi = net([prepared, feats])
+        locs, f = O.voxelize_batch(raw, 50, [512] * 3)
+        rpn2, roi2 = net([torch.from_numpy(locs), torch.from_numpy(f).cuda()])
+        for a, b in zip(list(rpn) + list(roi), list(rpn2) + list(roi2)):
+            assert torch.equal(a.get_spatial_locations(), b.get_spatial_locations())
+            assert rel(a.features, b.features) <= 1e-6
+        n += 1
+    assert n == 2

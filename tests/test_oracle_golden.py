@@ -123,3 +123,16 @@ def test_zcollapse64_rules_match_reference_golden(gold):
     assert len(rules) == 64
     for k, r in enumerate(rules):
         assert np.array_equal(O.canonical_pairs(r, r0, rz), g["zc_%d" % k]), k
+
+
+def test_voxelize_batch_is_the_per_building_quantiser_plus_collate():
+    raw = []
+    for i, n in enumerate((4000, 0, 2500)):
+        xyz = O.building(n, seed=i).astype(np.float32) if n else np.zeros((0, 3), np.float32)
+        raw.append(np.concatenate([xyz, np.random.RandomState(i).randn(n, 6).astype(np.float32)], 1))
+    locs, feats = O.voxelize_batch(raw, 50, [4096, 4096, 512])
+    want = [O.quantize_points(b[:, :3].astype(np.float64), 50, [4096, 4096, 512], i)[0] for i, b in enumerate(raw)]
+    assert np.array_equal(locs, np.concatenate(want))
+    assert feats.dtype == np.float32 and feats.shape == (len(locs), 9)
+    assert np.array_equal(feats[:, 3:], np.concatenate([b[:, 3:] for b in raw]))
+    assert np.abs(feats[:, :3] * 50 - locs[:, :3]).max() < 1.0 + 1e-3     # feature xyz = voxel-space position / scale
