@@ -22,6 +22,7 @@ from .fpn_net import FPN_Net  # noqa: E402
 from . import tools_3d_2d  # noqa: E402
 from .roi_align_rotated_3d import ROIAlignRotated3D, roi_align_rotated_3d  # noqa: E402
 from .rpn import RPNHead, grid_anchors  # noqa: E402
+from .nms import boxes_iou_3d, rotate_iou_gpu_eval, rotate_nms, rotate_nms_3d  # noqa: E402
 from .voxelize import VoxelLoader, quantize_points, voxelize_batch  # noqa: E402
 from .data_parallel import GradBucket, broadcast_parameters, shard_indices  # noqa: E402
 

@@ -103,6 +103,8 @@ _sig = {
     "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                              c_void_p]),
     "scn_scale_inplace": (c_int, [c_void_p, c_float, c_int64, c_void_p]),
+    "scn_rotate_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "scn_rotate_nms": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int64, c_int64, c_void_p, I64P, c_void_p]),
     "scn_grid_anchors": (c_int, [c_void_p, I64P, c_void_p, c_int64, c_float, POINTER(c_float), c_void_p, c_void_p,
                                  c_int64, c_void_p]),
     "scn_rpn_head_forward": (c_int, [c_void_p, c_int64, c_int64] + [c_void_p] * 4 + [c_int64, c_void_p, c_void_p,

@@ -352,6 +352,23 @@ int scn_rpn_head_backward(const float *x, const float *hidden, int64_t n, int64_
                           float *db_conv, float *dw_cls, float *db_cls, float *dw_box, float *db_box, int precision,
                           void *stream);
 
+/* ---- rotated box IoU / rotated NMS on the device -------------------------
+ * scn_rotate_iou replaces second/core/non_max_suppression/nms_gpu.py:667-703 rotate_iou_gpu_eval (numba-CUDA,
+ * host arrays in / out): boxes DEVICE float [n_boxes,5], query DEVICE float [n_query,5], rows (x, y, size_x,
+ * size_y, yaw); iou_out DEVICE float [n_boxes, n_query]; criterion as in devRotateIoUEval (:552-623: -1 IoU,
+ * 0 inter / query area, 1 inter / box area, 2 thin-box variant, 3-6 its experimental distance scores, else the
+ * intersection area).
+ * scn_rotate_nms replaces the body of rotate_nms_3d (second/pytorch/core/box_torch_ops.py:557-582 ->
+ * second/core/non_max_suppression/nms_cpu.py:32-44 -> spconv.utils.rotate_non_max_suppression_cpu): top
+ * pre_max_size boxes by score (<= 0: all), greedy suppression in score order where IoU >= iou_threshold, at most
+ * post_max_size kept (<= 0: no limit).  boxes DEVICE float [n,5] BEV rows as above (the caller passes
+ * bbox3d[:, [0,1,3,4,6]] as the reference does), scores DEVICE float [n]; keep_out DEVICE int64 [min(n, post)]
+ * indices into the input in descending score order; *n_keep read back to the host (one sync). */
+int scn_rotate_iou(const float *boxes, int64_t n_boxes, const float *query, int64_t n_query, int criterion,
+                   float *iou_out, void *stream);
+int scn_rotate_nms(const float *boxes, const float *scores, int64_t n, float iou_threshold, int64_t pre_max_size,
+                   int64_t post_max_size, int64_t *keep_out, int64_t *n_keep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
