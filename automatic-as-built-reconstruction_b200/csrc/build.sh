@@ -12,7 +12,7 @@ for f in $SRCS; do
   o=build/${f%.cu}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer "$o")" ] || [ ../../include/scn_b200.h -nt "$o" ]; then
     extra=""
-    # nms.cu: no FMA contraction, so the float32 box geometry rounds like the reference golden (oracle/nms_oracle.py)
+    # nms.cu: no FMA contraction, so the float32 box geometry rounds like the golden values of the reference kernels
     [ "$f" = nms.cu ] && extra="-fmad=false"
     $NVCC $FLAGS $extra -c "$f" -o "$o" &
     pids+=($!)

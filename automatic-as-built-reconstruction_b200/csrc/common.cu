@@ -177,21 +177,35 @@ int64_t *host_scratch(size_t n) {
 }
 
 // ---------------------------------------------------------------------------------------
-// exclusive scan: 512 threads x 8 items per block, recursive over block sums
+// exclusive scan in ONE pass: 512 threads x 8 items per tile, tiles chained by decoupled look-back
+// (Merrill & Garland).  A tile takes its index from a per-stream ticket counter (so every predecessor has
+// started), publishes its aggregate, then walks back over its predecessors' descriptors until it meets an
+// inclusive prefix.  Descriptor = epoch << 34 | state << 32 | value in one 64-bit word: a word of another epoch
+// reads as "not ready", so neither the descriptors nor the ticket counter are cleared between scans (the host
+// keeps the per-stream epoch and the running ticket base).  FLAGS: the scanned value is (in[i] >= 0), which
+// fuses the rulebook's "partner present" flag pass into the scan.
 // ---------------------------------------------------------------------------------------
 constexpr int SCAN_T = 512, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
 
+template <bool FLAGS>
 __global__ void __launch_bounds__(SCAN_T)
-k_scan_block(const int32_t *in, int32_t *out,
-             int32_t *__restrict__ block_sums, long long n_in, long long n_out) {
+k_scan_lookback(const int32_t *in, int32_t *out, long long n_in, long long n_out,
+                volatile unsigned long long *desc, unsigned int *ticket, unsigned int ticket_base,
+                unsigned long long epoch) {
   __shared__ int32_t warp_tot[SCAN_T / 32];
-  const long long base = (long long)blockIdx.x * SCAN_B + (long long)threadIdx.x * SCAN_I;
+  __shared__ unsigned int s_tile;
+  __shared__ int32_t s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const long long base = (long long)tile * SCAN_B + (long long)threadIdx.x * SCAN_I;
   int32_t v[SCAN_I];
   int32_t tsum = 0;
 #pragma unroll
   for (int i = 0; i < SCAN_I; ++i) {
     long long g = base + i;
-    v[i] = (g < n_in) ? in[g] : 0;
+    int32_t x = (g < n_in) ? in[g] : (FLAGS ? -1 : 0);
+    v[i] = FLAGS ? (x >= 0 ? 1 : 0) : x;
     tsum += v[i];
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -212,10 +226,43 @@ k_scan_block(const int32_t *in, int32_t *out,
       if (lane >= o) wi += t;
     }
     if (lane < SCAN_T / 32) warp_tot[lane] = wi - w;  // exclusive warp offsets
-    if (lane == SCAN_T / 32 - 1 && block_sums) block_sums[blockIdx.x] = wi;
+    const int32_t agg = __shfl_sync(0xffffffffu, wi, SCAN_T / 32 - 1);
+    const unsigned long long tag = epoch << 34;
+    int32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) desc[0] = tag | (2ull << 32) | (unsigned int)agg;
+    } else {
+      if (lane == 0) desc[tile] = tag | (1ull << 32) | (unsigned int)agg;
+      // look back 32 predecessors at a time: lane l reads tile - 1 - l (of the current window)
+      long long first = (long long)tile - 1;
+      for (;;) {
+        const long long t = first - lane;
+        unsigned long long d = 0;
+        bool ready = t < 0;                         // before tile 0: nothing to add, counts as "prefix"
+        unsigned int st = 2;
+        int32_t val = 0;
+        if (t >= 0) {
+          d = desc[t];
+          ready = (d >> 34) == epoch && ((d >> 32) & 3ull) != 0;
+          st = (unsigned int)((d >> 32) & 3ull);
+          val = (int32_t)(unsigned int)d;
+        }
+        if (!__all_sync(0xffffffffu, ready)) continue;          // spin until the whole window is published
+        const unsigned int pref = __ballot_sync(0xffffffffu, st == 2);
+        const int stop = pref ? __ffs(pref) - 1 : 32;           // nearest predecessor holding a prefix
+        int32_t part = lane <= stop ? val : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        excl += part;
+        if (pref) break;
+        first -= 32;
+      }
+      if (lane == 0) desc[tile] = tag | (2ull << 32) | (unsigned int)(excl + agg);
+    }
+    if (lane == 0) s_prefix = excl;
   }
   __syncthreads();
-  int32_t run = warp_tot[wid] + inc - tsum;
+  int32_t run = s_prefix + warp_tot[wid] + inc - tsum;
 #pragma unroll
   for (int i = 0; i < SCAN_I; ++i) {
     long long g = base + i;
@@ -224,35 +271,63 @@ k_scan_block(const int32_t *in, int32_t *out,
   }
 }
 
-__global__ void __launch_bounds__(SCAN_T)
-k_scan_add(int32_t *__restrict__ out, const int32_t *__restrict__ block_off, long long n_out) {
-  const int32_t add = block_off[blockIdx.x];
-  const long long base = (long long)blockIdx.x * SCAN_B + (long long)threadIdx.x * SCAN_I;
-#pragma unroll
-  for (int i = 0; i < SCAN_I; ++i) {
-    long long g = base + i;
-    if (g < n_out) out[g] += add;
+struct ScanState {
+  unsigned long long *desc = nullptr;
+  unsigned int *ticket = nullptr;
+  size_t cap = 0;
+  unsigned int base = 0;
+  unsigned long long epoch = 0;
+};
+static std::mutex g_scan_mu;
+static std::vector<std::pair<cudaStream_t, ScanState *>> g_scan;
+
+static int scan_launch(const int32_t *in, int32_t *out, long long n, bool flags, cudaStream_t s) {
+  const long long n_out = n + 1;
+  const int nb = cdiv(n_out, SCAN_B);
+  ScanState *st = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_scan_mu);
+    for (auto &e : g_scan)
+      if (e.first == s) { st = e.second; break; }
+    if (!st) {
+      st = new ScanState();
+      g_scan.emplace_back(s, st);
+    }
   }
+  // (a stream's calls are made by one host thread at a time: the state below is only touched by that thread)
+  if (!st->ticket) {
+    SCN_TRY(dev_alloc_t(&st->ticket, 4, s));
+    SCN_CUDA(cudaMemsetAsync(st->ticket, 0, 16, s));
+    st->base = 0;
+  }
+  if (st->cap < (size_t)nb) {
+    if (st->desc) dev_free(st->desc, s);
+    st->desc = nullptr;
+    size_t cap = (size_t)nb * 2;
+    if (cap < 4096) cap = 4096;
+    SCN_TRY(dev_alloc_t(&st->desc, cap, s));
+    SCN_CUDA(cudaMemsetAsync(st->desc, 0, cap * 8, s));     // epoch 0 is never used by a scan
+    st->cap = cap;
+  }
+  st->epoch = (st->epoch + 1) & ((1ull << 30) - 1);
+  if (st->epoch == 0) {                                      // wrapped (2^30 scans): restart from clean words
+    SCN_CUDA(cudaMemsetAsync(st->desc, 0, st->cap * 8, s));
+    st->epoch = 1;
+  }
+  if (flags)
+    k_scan_lookback<true><<<nb, SCAN_T, 0, s>>>(in, out, n, n_out, st->desc, st->ticket, st->base, st->epoch);
+  else
+    k_scan_lookback<false><<<nb, SCAN_T, 0, s>>>(in, out, n, n_out, st->desc, st->ticket, st->base, st->epoch);
+  st->base += (unsigned int)nb;
+  SCN_LAUNCHED();
+  return 0;
 }
 
 int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s) {
-  const long long n_out = n + 1;
-  const int nb = cdiv(n_out, SCAN_B);
-  if (nb == 1) {
-    k_scan_block<<<1, SCAN_T, 0, s>>>(in, out, nullptr, n, n_out);
-    SCN_LAUNCHED();
-    return 0;
-  }
-  int32_t *bs = nullptr;
-  SCN_TRY(dev_alloc_t(&bs, (size_t)nb + 1, s));
-  k_scan_block<<<nb, SCAN_T, 0, s>>>(in, out, bs, n, n_out);
-  SCN_LAUNCHED();
-  int r = exclusive_scan_i32(bs, bs, nb, s);
-  if (r) { dev_free(bs, s); return r; }
-  k_scan_add<<<nb, SCAN_T, 0, s>>>(out, bs, n_out);
-  SCN_LAUNCHED();
-  dev_free(bs, s);
-  return 0;
+  return scan_launch(in, out, n, false, s);
+}
+int exclusive_scan_flags_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s) {
+  return scan_launch(in, out, n, true, s);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -100,6 +100,8 @@ int num_sms();
 // ---- device-wide exclusive scan of int32 ----------------------------------------------
 // out[i] = sum_{j<i} in[j]; out has n+1 entries (out[n] = total). in may alias out.
 int exclusive_scan_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s);
+// same with in[j] replaced by (in[j] >= 0 ? 1 : 0): positions of the present partners of a neighbour table
+int exclusive_scan_flags_i32(const int32_t *in, int32_t *out, long long n, cudaStream_t s);
 
 // ---- stable LSD radix sort of (key uint32, value int32), keys limited to `bits` ----------
 // keys_out = false: only the permuted values are needed, the key buffer is left in an unspecified order

@@ -108,8 +108,53 @@ int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_o
                        const int64_t *param_tags, const float *bn_save, float *const *grads,
                        const float *const *out_grads, float *const *param_grads, uint8_t *param_written,
                        float *scratch, int64_t scratch_floats, int precision, void *stream) {
+  return scn_graph_backward_marked(m, ops, n_ops, n_values, values, rows, params, param_tags, bn_save, grads, out_grads,
+                                   param_grads, param_written, scratch, scratch_floats, precision, stream, 0, nullptr,
+                                   nullptr);
+}
+
+int scn_event_create(void **event) {
+  SCN_CHECK(event, "null argument");
+  cudaEvent_t e;
+  SCN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = (void *)e;
+  return 0;
+}
+int scn_event_destroy(void *event) {
+  if (event) SCN_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
+int scn_event_record(void *event, void *stream) {
+  SCN_CHECK(event, "null argument");
+  SCN_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return 0;
+}
+int scn_stream_wait_event(void *stream, void *event) {
+  SCN_CHECK(event, "null argument");
+  SCN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+  return 0;
+}
+
+int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_ops, int32_t n_values,
+                              float *const *values, const int64_t *rows, float *const *params,
+                              const int64_t *param_tags, const float *bn_save, float *const *grads,
+                              const float *const *out_grads, float *const *param_grads, uint8_t *param_written,
+                              float *scratch, int64_t scratch_floats, int precision, void *stream, int32_t n_marks,
+                              const int32_t *mark_ops, void *const *mark_events) {
   SCN_CHECK(m && ops && values && rows && params && grads && out_grads && param_grads && param_written, "null argument");
+  SCN_CHECK(n_marks == 0 || (mark_ops && mark_events), "null mark arrays");
   cudaStream_t s = (cudaStream_t)stream;
+  // marks: event j is recorded on the stream once the reverse sweep has passed op mark_ops[j] (whether that op ran
+  // or was skipped as a dead branch): every parameter gradient of the ops >= mark_ops[j] is then final
+  int next_mark = 0;
+  auto fire_marks = [&](int op_done) -> int {
+    while (next_mark < n_marks && mark_ops[next_mark] >= op_done) {
+      SCN_CUDA(cudaEventRecord((cudaEvent_t)mark_events[next_mark], s));
+      ++next_mark;
+    }
+    return 0;
+  };
+  for (int j = 1; j < n_marks; ++j) SCN_CHECK(mark_ops[j] <= mark_ops[j - 1], "marks must be in descending op order");
   // current gradient of every value: none yet / someone else's finished buffer (read only) / its own buffer
   enum { NONE = 0, ALIAS = 1, OWN = 2 };
   struct G { int st; const float *p; };
@@ -131,6 +176,7 @@ int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_o
     return 0;
   };
   for (int i = n_ops - 1; i >= 0; --i) {
+    SCN_TRY(fire_marks(i + 1));                        // everything above op i is finished
     const scn_graph_op_t &o = ops[i];
     if (g[o.out].st == NONE) continue;                 // dead branch: no gradient reaches this op
     const float *dY = g[o.out].p;
@@ -179,6 +225,7 @@ int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_o
     if (o.p0 >= 0 && dw) param_written[o.p0] = 1;
     if (o.p1 >= 0 && db) param_written[o.p1] = 1;
   }
+  SCN_TRY(fire_marks(0));
   return 0;
 }
 

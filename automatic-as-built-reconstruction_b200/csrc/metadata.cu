@@ -519,11 +519,7 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   int32_t *pos = nullptr, *meta = nullptr;
   SCN_TRY(dev_alloc_t(&pos, (size_t)total + 1, s));
   SCN_TRY(dev_alloc_t(&meta, (size_t)K + 8 + 2 * G, s));
-  if (total > 0) {
-    k_flag_table<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, total);
-    SCN_LAUNCHED();
-  }
-  SCN_TRY(exclusive_scan_i32(pos, pos, total, s));
+  SCN_TRY(exclusive_scan_flags_i32(rb->t_out, pos, total, s));   // pos[i] = present partners before table entry i
   k_pair_offsets<<<1, MAX_KT + 32, 0, s>>>(pos, n, K, meta);
   SCN_LAUNCHED();
   SCN_TRY(tilebook_chain_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s));

@@ -98,6 +98,13 @@ _sig = {
     "scn_graph_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                    c_void_p]),
+    "scn_graph_backward_marked": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int64, c_int, c_void_p, c_int32, c_void_p, c_void_p]),
+    "scn_event_create": (c_int, [POINTER(c_void_p)]),
+    "scn_event_destroy": (c_int, [c_void_p]),
+    "scn_event_record": (c_int, [c_void_p, c_void_p]),
+    "scn_stream_wait_event": (c_int, [c_void_p, c_void_p]),
     "scn_sparse_to_dense_forward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                             c_void_p]),
     "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,

@@ -149,6 +149,8 @@ class FPN_Net(torch.nn.Module):
             except _graph.Unsupported:
                 g = False
             self._graph_cache = g
+        if g:
+            g.grad_sink = getattr(self, "_grad_sink", None)     # a GradBucket built with module=self
         return g or None
 
     def forward_fpn_graph(self, net, g, bn_mode):

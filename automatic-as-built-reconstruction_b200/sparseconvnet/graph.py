@@ -46,6 +46,18 @@ class LayerGraph(object):
         self.save_floats = 0
         self.outputs = []
         self._c_ops = None
+        self.grad_sink = None     # GradBucket.attach(): parameter gradients are written straight into the bucket
+
+    def param_write_op(self):
+        """{id(Parameter): index of the LAST op (lowest index = latest in the reverse sweep) that writes its
+        gradient}: what a gradient bucket needs to know when a range of it is final"""
+        last = {}
+        for i, o in enumerate(self.ops):
+            for slot in ((o.p0, o.p1) if o.kind != ADD else ()):
+                if slot >= 0 and isinstance(self.params[slot], torch.nn.Parameter):
+                    k = id(self.params[slot])
+                    last[k] = min(last.get(k, i), i)
+        return last
 
     # ---- construction ---------------------------------------------------------------------
     def _param(self, t):
@@ -141,9 +153,18 @@ class LayerGraph(object):
         self._grad_slot = [self._slot[id(t)] for t in self.grad_params]
         self.sizes = sorted(set(ss for _, ss in self.values))
         self.is_weight = [False] * len(self.params)
+        writers = {}
         for o in self.ops:
             if o.kind in (SUBM, CONV, DECONV):
                 self.is_weight[o.p0] = True
+            if o.kind != ADD:
+                for slot in (o.p0, o.p1):
+                    if slot >= 0 and isinstance(self.params[slot], torch.nn.Parameter):
+                        writers[slot] = writers.get(slot, 0) + 1
+        if any(c > 1 for c in writers.values()):
+            # the reverse sweep WRITES parameter gradients (no accumulation over ops): a parameter shared by two
+            # layers runs through the per-layer Functions instead
+            raise Unsupported("a parameter is shared by several layers")
         return self
 
     def bn_mode(self, training, root):
@@ -243,20 +264,43 @@ class GraphFunction(Function):
         for i in graph._grad_slot:
             poff[i] = ptotal
             ptotal += (numel[i] + 3) // 4 * 4
+        # a GradBucket attached to the graph takes the parameter gradients directly (no AccumulateGrad pass over
+        # 85 MB, and ranges of the bucket can be all-reduced while the sweep continues: data_parallel.py)
+        sink = graph.grad_sink
+        direct = {}
+        if sink is not None:
+            for t, i in zip(graph.grad_params, graph._grad_slot):
+                view = sink.view_of(t)
+                if view is not None:
+                    direct[i] = view
+                    poff[i] = -1
+            ptotal = 0
+            for i in graph._grad_slot:
+                if i not in direct:
+                    poff[i] = ptotal
+                    ptotal += (numel[i] + 3) // 4 * 4
         pflat = x0.new_empty(max(ptotal, 1))
         pbase = pflat.data_ptr()
         pgr = (c_void_p * n)()
         for i in graph._grad_slot:
-            pgr[i] = pbase + 4 * poff[i]
+            pgr[i] = direct[i].data_ptr() if i in direct else pbase + 4 * poff[i]
         written = (c_uint8 * n)()
         scratch_n = max(rows[v] * graph.values[v][0] for v in range(nv))
         scratch = x0.new_empty(max(scratch_n, 1))
         ptrs, tags = graph._param_arrays(None)
-        _lib.check(_lib.lib.scn_graph_backward(metadata._h, graph._c_ops, len(graph.ops), nv, ctx.vals, rows, ptrs, tags,
-                                               _lib.ptr(bn_save), grads, ext, pgr, written, _lib.ptr(scratch),
-                                               scratch_n, _lib.precision(), _lib.stream()))
+        marks = sink.marks() if sink is not None else None
+        n_marks = len(marks[0]) if marks else 0
+        mark_ops = (c_int32 * max(n_marks, 1))(*(marks[0] if marks else [0]))
+        mark_evs = (c_void_p * max(n_marks, 1))(*(marks[1] if marks else [None]))
+        _lib.check(_lib.lib.scn_graph_backward_marked(metadata._h, graph._c_ops, len(graph.ops), nv, ctx.vals, rows, ptrs,
+                                                      tags, _lib.ptr(bn_save), grads, ext, pgr, written,
+                                                      _lib.ptr(scratch), scratch_n, _lib.precision(), _lib.stream(),
+                                                      n_marks, mark_ops, mark_evs))
         pg = []
         for t, i in zip(graph.grad_params, graph._grad_slot):
-            pg.append(pflat[poff[i]:poff[i] + numel[i]].view_as(t) if written[i] else None)
+            if i in direct:
+                pg.append(None)              # already in place (p.grad is the bucket view)
+            else:
+                pg.append(pflat[poff[i]:poff[i] + numel[i]].view_as(t) if written[i] else None)
         ctx.keep = None
         return (None, None, None, d_x0) + tuple(pg)

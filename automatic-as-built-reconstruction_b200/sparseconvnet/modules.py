@@ -150,6 +150,24 @@ class InputLayer(Module):
         return out
 
 
+_loader_streams = {}
+
+
+def loader_stream(device):
+    """ONE high-priority side stream per device for the integer work that runs a batch ahead (InputPrefetcher,
+    VoxelLoader): the library keeps per-stream workspaces, scan state and scheduling counters, so a fresh stream
+    per loader would re-pay their first-use allocations (a device-synchronising cudaMalloc among them: measured
+    180-280 ms for the first batch of a new loader) and never release them"""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _loader_streams.get(key)
+    if st is None:
+        # high priority: the build is a few hundred tiny launches separated by count read-backs; each must slip in
+        # beside the main stream's SM-filling kernels instead of queueing behind them
+        st = _loader_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+    return st
+
+
 class InputPrefetcher(object):
     """Runs `prepare_fn(coords)` (e.g. FPN_Net.prepare) for the NEXT batch on a side stream and a
     worker thread while the current batch's feature kernels run on the main stream - the role the
@@ -168,9 +186,7 @@ class InputPrefetcher(object):
         import threading
         self.prepare_fn = prepare_fn
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        # high priority: the build is ~500 tiny launches separated by count read-backs; each must slip in
-        # beside the main stream's SM-filling kernels instead of queueing behind them
-        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.stream = loader_stream(self.device)
         self.todo, self.done = queue.Queue(), queue.Queue()
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()

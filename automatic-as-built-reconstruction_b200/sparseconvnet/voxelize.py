@@ -80,7 +80,8 @@ class VoxelLoader(object):
         self.batches, self.prepare_fn = batches, prepare_fn
         self.args = (scale, full_scale, matrix, xyz_feature)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        from .modules import loader_stream
+        self.stream = loader_stream(self.device)
         self.done = queue.Queue(maxsize=max(1, depth))
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()

@@ -264,7 +264,7 @@ def run_b200(args, rank, local_rank, world):
     train = args.mode == "train"
     net = net.to(dev).train() if train else net.to(dev).eval()
     scn.broadcast_parameters(net)
-    bucket = scn.GradBucket(net.parameters()) if train else None
+    bucket = scn.GradBucket(net.parameters(), module=net) if train else None
     locs, feats, raw = make_batch(args.points, args.floors, args.batch, rank * args.batch, with_raw=True)   # weak scaling
     na_local = n_active0(locs)
     raw_pin = [r.pin_memory() for r in raw]                  # e2e input: the raw float32 buildings on the host

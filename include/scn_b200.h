@@ -283,6 +283,24 @@ int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_o
                        const float *const *out_grads, float *const *param_grads, uint8_t *param_written,
                        float *scratch, int64_t scratch_floats, int precision, void *stream);
 
+/* Same reverse sweep with progress marks for an overlapped gradient all-reduce (DistributedDataParallel's
+ * bucketed reduction, tools/train_net_sparse3d.py:64-69): mark_ops in DESCENDING order; event mark_events[j]
+ * (scn_event_create) is recorded on `stream` as soon as the sweep has passed op mark_ops[j], i.e. when the
+ * parameter gradients of every op with index >= mark_ops[j] are final.  param_grads may point straight into a flat
+ * gradient bucket: a collective on another stream that waits for event j may then reduce those ranges while the
+ * sweep continues. */
+int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_ops, int32_t n_values,
+                              float *const *values, const int64_t *rows, float *const *params,
+                              const int64_t *param_tags, const float *bn_save, float *const *grads,
+                              const float *const *out_grads, float *const *param_grads, uint8_t *param_written,
+                              float *scratch, int64_t scratch_floats, int precision, void *stream, int32_t n_marks,
+                              const int32_t *mark_ops, void *const *mark_events);
+/* CUDA events as opaque handles (timing disabled) for the marks above */
+int scn_event_create(void **event);
+int scn_event_destroy(void *event);
+int scn_event_record(void *event, void *stream);
+int scn_stream_wait_event(void *stream, void *event);
+
 /* ---- elementwise helper used by the data-parallel gradient bucket ------------------- */
 /* y[i] *= alpha over n fp32 values (scale the all-reduced gradient bucket by 1/world) */
 int scn_scale_inplace(float *y, float alpha, int64_t n, void *stream);

@@ -102,9 +102,9 @@ def three_way(gpu_maps, gpu_grads, ref_maps, ref_grads, truth_maps, truth_grads,
     def ok(e):
         return "missing" not in e and (e["gpu_vs_ref"] <= bound or e["gpu_vs_fp64"] <= e["ref_vs_fp64"])
 
-    def sane(e):
+    def sane(e, noise):
         return "missing" not in e and (e["gpu_vs_ref"] <= bound or
-                                       e["gpu_vs_fp64"] <= SANITY * max(e["ref_vs_fp64"], bound))
+                                       e["gpu_vs_fp64"] <= max(SANITY * max(e["ref_vs_fp64"], bound), noise))
 
     def worst(items, key):
         vals = [e[key] for e in items if key in e]
@@ -122,15 +122,19 @@ def three_way(gpu_maps, gpu_grads, ref_maps, ref_grads, truth_maps, truth_grads,
     #   (1) the whole gradient vector: relative L2 error vs float64 no larger than the reference's (or <= bound);
     #   (2) the worst tensor: max error vs float64 no larger than the reference's worst (or <= bound);
     #   (3) every tensor: within `bound` of the reference, or no further from float64 than SANITY x the
-    #       reference's own error (catches real defects, which show up as O(1));
+    #       reference's own error on that tensor, or than HALF the reference's worst error on any tensor (the
+    #       deepest layers see a handful of rows: one ReLU flip there moves a gradient by percents in either
+    #       implementation, so which tensor carries the noise differs from run to run; real defects show up as
+    #       O(1) on the tensor they touch);
     # the count of tensors that individually beat the reference is reported beside them.
     g2 = rep["gradient_vector_l2"]
     gate1 = live > 0 and g2["gpu_vs_fp64"] <= max(bound, g2["ref_vs_fp64"])
     gate2 = live > 0 and rep["gradients"]["gpu_vs_fp64"] <= max(bound, rep["gradients"]["ref_vs_fp64"])
-    insane = sorted(k for k, e in rep["grads"].items() if not sane(e))
+    noise = 0.5 * (rep["gradients"]["ref_vs_fp64"] or 0.0)
+    insane = sorted(k for k, e in rep["grads"].items() if not sane(e, noise))
     rep["gradient_gates"] = {"vector_l2_no_worse_than_reference": bool(gate1),
                              "worst_tensor_no_worse_than_reference": bool(gate2),
-                             "every_tensor_within_%gx_of_reference_error" % SANITY: not insane}
+                             "every_tensor_within_%gx_of_reference_error_or_half_its_worst" % SANITY: not insane}
     rep["gradients_ok"] = bool(gate1 and gate2 and not insane)
     rep["failing_gradients"] = insane
     rep["gradients_not_closer_than_reference"] = sorted(k for k, e in rep["grads"].items() if not ok(e))

@@ -18,7 +18,7 @@ net = scn.FPN_Net(bench.FULL_SCALE, 3, ["xyz", "color", "normal"], 1, bench.PLAN
                   fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
                   downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8], rpn_map_sizes=bench.RPN_SIZES, voxel_scale=50,
                   rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95, track_running_stats=False).to(dev).train()
-bucket = scn.GradBucket(net.parameters())
+bucket = scn.GradBucket(net.parameters(), module=net)
 locs, feats = bench.make_batch(300000, 1, 1, 0)
 ld, fd = locs.to(dev), feats.to(dev)
 pf = scn.InputPrefetcher(net.prepare)
