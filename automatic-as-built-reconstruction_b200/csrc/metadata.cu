@@ -321,12 +321,6 @@ __global__ void k_sub_table(const int32_t *__restrict__ coords, long long n, Fil
   T[idx] = r;
 }
 
-__global__ void k_flag_table(const int32_t *__restrict__ T, int32_t *__restrict__ flag,
-                             long long total) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) flag[i] = T[i] >= 0 ? 1 : 0;
-}
-
 // meta[k] = first pair of offset k, meta[K] = total pairs
 __global__ void k_pair_offsets(const int32_t *__restrict__ pos, long long n, int K,
                                int32_t *__restrict__ meta) {
@@ -358,18 +352,37 @@ __global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t 
 // ---------------------------------------------------------------------------------------
 // tile books
 // ---------------------------------------------------------------------------------------
-// mask[r] = set of offsets at which row r has a partner = the sort key: rows are ordered by mask value,
-// so a tile holds rows whose masks share their high offsets and its union mask stays small
+// mask[r] = set of offsets at which row r has a partner.  The sort key is the mask with its bits re-ordered by
+// how many pairs each offset has in this rulebook - the MOST frequent offset in bit 0, the rarest in the top bit -
+// so that rows are grouped by their rare offsets first and a tile's union mask stays small.  Measured on the
+// benchmark building (tile rows / pairs of the 3^3 submanifold books): scale 0 1.286 -> 1.208, scale 1 1.382 ->
+// 1.251, scale 2 1.192 -> 1.130 against the mask value itself as key.  pair_off (device, K + 1 running pair
+// counts) may be null: the key is then the mask.
 __global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
                             uint32_t *__restrict__ mask, uint32_t *__restrict__ key,
-                            int32_t *__restrict__ idx, int key_shift) {
+                            int32_t *__restrict__ idx, int key_shift, const int32_t *__restrict__ pair_off) {
+  __shared__ int s_cnt[MAX_K], s_rank[MAX_K];
+  if (pair_off) {
+    if (threadIdx.x < K) s_cnt[threadIdx.x] = pair_off[threadIdx.x + 1] - pair_off[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < K) {
+      int rk = 0;
+      const int c = s_cnt[threadIdx.x];
+      for (int j = 0; j < K; ++j) rk += (s_cnt[j] > c || (s_cnt[j] == c && j < (int)threadIdx.x)) ? 1 : 0;
+      s_rank[threadIdx.x] = rk;
+    }
+    __syncthreads();
+  }
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  uint32_t m = 0;
+  uint32_t m = 0, km = 0;
   for (int k = 0; k < K; ++k)
-    if (T[(long long)k * n + r] >= 0) m |= (1u << k);
+    if (T[(long long)k * n + r] >= 0) {
+      m |= (1u << k);
+      km |= (1u << (pair_off ? s_rank[k] : k));
+    }
   mask[r] = m;
-  key[r] = m >> key_shift;
+  key[r] = km >> key_shift;
   idx[r] = (int)r;
 }
 
@@ -397,12 +410,16 @@ k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ 
 }
 
 // tiles ordered by descending number of active offsets (counting sort, one block): the persistent gather-GEMM hands
-// its work items out in this order - longest first, so the last wave consists of the shortest items
+// its work items out in this order - longest first, so the last wave consists of the shortest items.  The same block
+// also writes tile_off = exclusive scan of the per-tile offset counts (n_tiles + 1 entries; a few thousand tiles).
 __global__ void __launch_bounds__(1024)
 k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restrict__ order,
-             int32_t *__restrict__ n_entries) {
+             int32_t *__restrict__ n_entries, int32_t *__restrict__ tile_off) {
   __shared__ int cnt[40], base[40];
+  __shared__ int wsum[32];
+  __shared__ int carry;
   if (threadIdx.x < 40) cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&cnt[min(tile_pop[t], 39)], 1);
   __syncthreads();
@@ -413,6 +430,36 @@ k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restr
   }
   __syncthreads();
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) order[atomicAdd(&base[min(tile_pop[t], 39)], 1)] = t;
+  // exclusive scan, 1024 tiles per round
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int t0 = 0; t0 <= n_tiles; t0 += 1024) {
+    const int t = t0 + threadIdx.x;
+    const int v = t < n_tiles ? tile_pop[t] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      const int w = wsum[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += u;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const int c = carry;
+    if (t <= n_tiles) tile_off[t] = c + wsum[wid] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + wsum[wid] + inc;
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(TILE_M)
@@ -433,7 +480,7 @@ k_fill_entries(const int32_t *__restrict__ T, long long n, const int32_t *__rest
 // Phase 1 (no host knowledge needed): masks, grouping, per-tile offsets. meta_slot receives
 // the entry total.  Phase 2 after the read-back: allocate + fill the entry lists.
 static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows,
-                           int64_t n_partner, int32_t *meta_slot, cudaStream_t s) {
+                           int64_t n_partner, int32_t *meta_slot, cudaStream_t s, const int32_t *pair_off = nullptr) {
   tb.K = K;
   tb.n_rows = n_rows;
   tb.n_partner = n_partner;
@@ -451,7 +498,7 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   // agree on them end up adjacent; the low offsets are left unsorted inside such a group
   static const int sort_bits = getenv("SCN_B200_SORT_BITS") ? atoi(getenv("SCN_B200_SORT_BITS")) : 27;
   const int kbits = K < sort_bits ? K : sort_bits;
-  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx, K - kbits);
+  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx, K - kbits, pair_off);
   SCN_LAUNCHED();
   // (books of at most 4 tiles keep the natural row order: nothing to group, and the sort is ~15 launches)
   if (g_tile_grouping && K > 1 && n_rows > 4 * TILE_M) SCN_TRY(radix_sort_pairs(key, idx, n_rows, kbits, s, false));
@@ -462,9 +509,8 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   k_tile_masks<<<tb.n_tiles, TILE_M, 0, s>>>(mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
   SCN_LAUNCHED();
   SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles, s));
-  k_tile_order<<<1, 1024, 0, s>>>(pop, tb.n_tiles, tb.order, meta_slot);
+  k_tile_order<<<1, 1024, 0, s>>>(pop, tb.n_tiles, tb.order, meta_slot, tb.tile_off);
   SCN_LAUNCHED();
-  SCN_TRY(exclusive_scan_i32(pop, tb.tile_off, tb.n_tiles, s));
   dev_free(mask, s);
   dev_free(key, s);
   dev_free(idx, s);
@@ -487,7 +533,7 @@ static int tilebook_phase2(TileBook &tb, const int32_t *T, int64_t n_entries, cu
 // the chain of tile books over a table T [K, n_rows]: one book per group of <= MAX_K offsets (phase 1 of each;
 // meta_slot + g receives the entry total of book g)
 static int tilebook_chain_phase1(TileBook &head, const int32_t *T, int K, int64_t n_rows, int64_t n_partner,
-                                 int32_t *meta_slot, cudaStream_t s) {
+                                 int32_t *meta_slot, cudaStream_t s, const int32_t *pair_off = nullptr) {
   TileBook *tb = &head;
   for (int k0 = 0, g = 0; k0 < K; k0 += MAX_K, ++g) {
     if (g > 0) {
@@ -495,7 +541,8 @@ static int tilebook_chain_phase1(TileBook &head, const int32_t *T, int K, int64_
       tb = tb->next;
     }
     tb->k_base = k0;
-    SCN_TRY(tilebook_phase1(*tb, T + (long long)k0 * n_rows, std::min(MAX_K, K - k0), n_rows, n_partner, meta_slot + g, s));
+    SCN_TRY(tilebook_phase1(*tb, T + (long long)k0 * n_rows, std::min(MAX_K, K - k0), n_rows, n_partner, meta_slot + g, s,
+                            pair_off ? pair_off + k0 : nullptr));
   }
   return 0;
 }
@@ -522,11 +569,11 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   SCN_TRY(exclusive_scan_flags_i32(rb->t_out, pos, total, s));   // pos[i] = present partners before table entry i
   k_pair_offsets<<<1, MAX_KT + 32, 0, s>>>(pos, n, K, meta);
   SCN_LAUNCHED();
-  SCN_TRY(tilebook_chain_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s));
+  SCN_TRY(tilebook_chain_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s, meta));
   // strided rulebooks also carry the in-stationary lists (conv dX, deconv forward); building them
   // here shares this read-back, so the backward pass never synchronises
   const bool both = rb->kind == 1 && rb->t_in != nullptr;
-  if (both) SCN_TRY(tilebook_chain_phase1(rb->tb_in, rb->t_in, K, rb->n_in, rb->n_out, meta + K + 1 + G, s));
+  if (both) SCN_TRY(tilebook_chain_phase1(rb->tb_in, rb->t_in, K, rb->n_in, rb->n_out, meta + K + 1 + G, s, meta));
   int64_t *hs = host_scratch((size_t)(K + 8 + 2 * G) / 2 + 8);
   int32_t *h32 = (int32_t *)hs;
   SCN_CUDA(cudaMemcpyAsync(h32, meta, (size_t)(K + 1 + 2 * G) * 4, cudaMemcpyDeviceToHost, s));
