@@ -1497,7 +1497,20 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
       };
       const float4 *srca = reinterpret_cast<const float4 *>(smem + L.a + stage * L.a_stage);
       float4 *dsta = reinterpret_cast<float4 *>(smem + L.a + (NSTAGE + stl) * L.a_stage);
-      for (int i = ct; i < a16; i += DW_CW * 32) dsta[i] = lo4(srca[i]);
+      if (CA == MA) {
+        for (int i = ct; i < a16; i += DW_CW * 32) dsta[i] = lo4(srca[i]);
+      } else {
+        // M is padded to 128 (Cin = 32 / 64): only the CA real 32-channel atoms of each k-atom carry data; the
+        // padding atoms of the low-order stages were zeroed at kernel start and stay zero (converting them was
+        // 50 - 75 % of this role's shared-memory traffic)
+        const int sh = __ffs(CA) - 1 + 5;                 // CA is a power of two (host check)
+        const int real16 = KA << sh;                      // 16-byte units: KA k-atoms x CA atoms x 512 B
+        for (int i = ct; i < real16; i += DW_CW * 32) {
+          const int ka = i >> sh, r = i & ((1 << sh) - 1);
+          const int o = ka * (MA * 32) + r;
+          dsta[o] = lo4(srca[o]);
+        }
+      }
       const float4 *srcb = reinterpret_cast<const float4 *>(smem + L.b + stage * L.b_stage);
       float4 *dstb = reinterpret_cast<float4 *>(smem + L.b + (NSTAGE + stl) * L.b_stage);
       for (int i = ct; i < b16; i += DW_CW * 32) dstb[i] = lo4(srcb[i]);
