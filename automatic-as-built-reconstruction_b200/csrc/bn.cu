@@ -14,6 +14,14 @@ namespace scn {
 
 constexpr int BN_T = 256;
 
+// y = lrelu(fmaf(x, w, b)) with w = invstd * gamma, b = fma(-mean, w, beta): ONE definition for the forward apply and
+// for the backward pass, which recomputes the sign of the pre-activation from x instead of reading y back (the
+// same fp32 operations on the same saved mean / invstd give the same bits, hence the same ReLU mask)
+__device__ __forceinline__ void bn_affine(float mean, float invstd, float gamma, float beta, float &w, float &b) {
+  w = invstd * gamma;
+  b = __fmaf_rn(-mean, w, beta);
+}
+
 // ---- statistics: q0 = sum a, q1 = sum b over rows, per channel ---------------------------
 // forward:  a = x,  b = x*x
 // backward: a = d,  b = (x-mean)*d   with d = dy * (y > 0 ? 1 : leak)
@@ -21,7 +29,7 @@ template <bool BWD>
 __device__ __forceinline__ void bn_terms(float x, float y, float dy, float mean, float leak,
                                          float &a, float &b) {
   if (BWD) {
-    const float d = dy * (y > 0.f ? 1.f : leak);
+    const float d = dy * (y > 0.f ? 1.f : leak);   // y: the BN output, or the recomputed pre-activation (same sign)
     a = d;
     b = (x - mean) * d;
   } else {
@@ -31,18 +39,30 @@ __device__ __forceinline__ void bn_terms(float x, float y, float dy, float mean,
 }
 
 // vector path: C % 4 == 0 and 1024 % C == 0; thread owns one channel quad for all its rows
+// Yo == nullptr (backward): the ReLU mask comes from the recomputed pre-activation fmaf(x, w, b) with
+// (w, b) = bn_affine(mean, invstd, gamma, beta) - one tensor less to read
 template <bool BWD>
 __global__ void __launch_bounds__(BN_T)
 k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
-               long long n, int C, double *__restrict__ acc) {
+               long long n, int C, double *__restrict__ acc, const float *__restrict__ invstd = nullptr,
+               const float *__restrict__ gamma = nullptr, const float *__restrict__ beta = nullptr) {
   __shared__ double red[2][BN_T * 4];
   const int qpr = C >> 2;               // quads per row
   const int rpb = BN_T / qpr;           // rows per block iteration (>= 1 since C <= 1024)
   const int cq = threadIdx.x % qpr, rs = threadIdx.x / qpr;
   float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
-  float4 mu = make_float4(0, 0, 0, 0);
+  float4 mu = make_float4(0, 0, 0, 0), aw = mu, ab = mu;
   if (BWD) mu = reinterpret_cast<const float4 *>(mean)[cq];
+  const bool recompute = BWD && Yo == nullptr;
+  if (recompute) {
+    const float4 is = reinterpret_cast<const float4 *>(invstd)[cq];
+    const int c = cq * 4;
+    bn_affine(mu.x, is.x, gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, aw.x, ab.x);
+    bn_affine(mu.y, is.y, gamma ? gamma[c + 1] : 1.f, beta ? beta[c + 1] : 0.f, aw.y, ab.y);
+    bn_affine(mu.z, is.z, gamma ? gamma[c + 2] : 1.f, beta ? beta[c + 2] : 0.f, aw.z, ab.z);
+    bn_affine(mu.w, is.w, gamma ? gamma[c + 3] : 1.f, beta ? beta[c + 3] : 0.f, aw.w, ab.w);
+  }
   if (rs < rpb) {
 #pragma unroll 4   // independent 128-bit loads of 4 row slots in flight per thread
     for (long long r = (long long)blockIdx.x * rpb + rs; r < n; r += (long long)gridDim.x * rpb) {
@@ -50,7 +70,10 @@ k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
       const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + o);
       float4 y = x, d = x;
       if (BWD) {
-        y = __ldg(reinterpret_cast<const float4 *>(Yo) + o);
+        if (recompute)
+          y = make_float4(fmaf(x.x, aw.x, ab.x), fmaf(x.y, aw.y, ab.y), fmaf(x.z, aw.z, ab.z), fmaf(x.w, aw.w, ab.w));
+        else
+          y = __ldg(reinterpret_cast<const float4 *>(Yo) + o);
         d = __ldg(reinterpret_cast<const float4 *>(dY) + o);
       }
       float a, b;
@@ -134,9 +157,10 @@ __device__ __forceinline__ void bn_fwd_coef(const double *__restrict__ acc, long
     save_mean[c] = mean;
     save_invstd[c] = invstd;
   }
-  const float w = invstd * (weight ? weight[c] : 1.f);
+  float w, b;
+  bn_affine(mean, invstd, weight ? weight[c] : 1.f, bias ? bias[c] : 0.f, w, b);
   coef[c] = w;
-  coef[C + c] = -mean * w + (bias ? bias[c] : 0.f);
+  coef[C + c] = b;
 }
 
 // backward (:86-106): coef = [gradMean, k, invstd*gamma]
@@ -210,14 +234,17 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ mean, const double *__restrict__ acc,
                const float *__restrict__ save_invstd, const float *__restrict__ weight,
                float *d_weight, float *d_bias, float leak, long long n, int C, double *zero_buf, int zero_n,
-               const float *R) {
-  extern __shared__ float coef[];  // [3C] then mean [C]
+               const float *R, const float *__restrict__ beta) {
+  extern __shared__ float coef[];  // [3C] then mean [C], then (Yo == nullptr) the forward's [w, b] [2C]
   float *smean = coef + 3 * C;
+  float *aff = coef + 4 * C;
+  const bool recompute = Yo == nullptr;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < zero_n; i += BN_T) zero_buf[i] = 0.0;
   for (int c = threadIdx.x; c < C; c += BN_T) {
     bn_bwd_coef(acc, n, C, c, save_invstd, weight, d_weight, d_bias, blockIdx.x == 0, coef);
     smean[c] = mean[c];
+    if (recompute) bn_affine(mean[c], save_invstd[c], weight ? weight[c] : 1.f, beta ? beta[c] : 0.f, aff[c], aff[C + c]);
   }
   __syncthreads();
   const long long total = n * C;
@@ -228,7 +255,14 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
     for (; i < nq; i += st) {
       const int c = (int)((i << 2) % C);
       const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + i);
-      const float4 y = __ldg(reinterpret_cast<const float4 *>(Yo) + i);
+      float4 y;
+      if (recompute) {
+        const float4 w = *reinterpret_cast<const float4 *>(aff + c);
+        const float4 b = *reinterpret_cast<const float4 *>(aff + C + c);
+        y = make_float4(fmaf(x.x, w.x, b.x), fmaf(x.y, w.y, b.y), fmaf(x.z, w.z, b.z), fmaf(x.w, w.w, b.w));
+      } else {
+        y = __ldg(reinterpret_cast<const float4 *>(Yo) + i);
+      }
       const float4 d = __ldg(reinterpret_cast<const float4 *>(dY) + i);
       const float4 mu = *reinterpret_cast<const float4 *>(smean + c);
       const float4 gm = *reinterpret_cast<const float4 *>(coef + c);
@@ -248,7 +282,8 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
   } else {
     for (; i < total; i += st) {
       const int c = (int)(i % C);
-      const float d = dY[i] * (Yo[i] > 0.f ? 1.f : leak);
+      const float yv = recompute ? fmaf(X[i], aff[c], aff[C + c]) : Yo[i];
+      const float d = dY[i] * (yv > 0.f ? 1.f : leak);
       dX[i] = (d - coef[c] - (X[i] - smean[c]) * coef[C + c]) * coef[2 * C + c] + (R ? R[i] : 0.f);
     }
   }
@@ -359,6 +394,15 @@ int scn_batchnorm_backward_add(const float *in, float *d_in, const float *out, c
                                const float *save_mean, const float *save_invstd, const float *weight,
                                float *d_weight, float *d_bias, float leakiness, int64_t n, int64_t C64,
                                const float *residual, void *stream) {
+  SCN_CHECK(out || n == 0, "null feature pointer");
+  return scn_batchnorm_backward_fused(in, d_in, out, d_out, save_mean, save_invstd, weight, nullptr, 0, d_weight, d_bias,
+                                      leakiness, n, C64, residual, stream);
+}
+
+int scn_batchnorm_backward_fused(const float *in, float *d_in, const float *out, const float *d_out,
+                                 const float *save_mean, const float *save_invstd, const float *weight,
+                                 const float *bias, int recompute_mask, float *d_weight, float *d_bias,
+                                 float leakiness, int64_t n, int64_t C64, const float *residual, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)C64;
   SCN_CHECK(C > 0 && C <= 4096 && save_mean && save_invstd, "bad BN arguments");
@@ -367,27 +411,34 @@ int scn_batchnorm_backward_add(const float *in, float *d_in, const float *out, c
     if (d_bias) SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)C * 4, s));
     return 0;
   }
-  SCN_CHECK(in && d_in && out && d_out, "null feature pointer");
+  SCN_CHECK(in && d_in && d_out, "null feature pointer");
   const bool vec = vec_ok(n, C, in, d_in, out, d_out) && (((uintptr_t)save_mean & 15) == 0) &&
-                   (((uintptr_t)residual & 15) == 0);
+                   (((uintptr_t)save_invstd & 15) == 0) && (((uintptr_t)residual & 15) == 0);
+  // recompute_mask: `weight` / `bias` are the forward's gamma / beta (NULL = 1 / 0), so the sign of the
+  // pre-activation can be recomputed from `in` and `out` need not be read (vector path only)
+  if (!(recompute_mask && vec)) SCN_CHECK(out, "null feature pointer");
+  else out = nullptr;
   prof_begin(PROF_BN, s);
   double *acc = nullptr, *other = nullptr;
   int other_used = 0;
   SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
   if (vec)
-    k_bn_stats_vec<true><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, acc);
+    k_bn_stats_vec<true><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, acc,
+                                                                        save_invstd, weight, bias);
   else
     k_bn_stats_gen<true><<<dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, out, d_out, save_mean,
                                                                                    leakiness, n, C, acc);
   SCN_LAUNCHED();
   const long long total = (long long)n * C;
-  const size_t sm = (size_t)4 * C * sizeof(float);
+  const size_t sm = (size_t)6 * C * sizeof(float);
   if (vec)
     k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
-                                                              weight, d_weight, d_bias, leakiness, n, C, other, other_used, residual);
+                                                              weight, d_weight, d_bias, leakiness, n, C, other, other_used,
+                                                              residual, bias);
   else
     k_bn_bwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
-                                                           weight, d_weight, d_bias, leakiness, n, C, other, other_used, residual);
+                                                           weight, d_weight, d_bias, leakiness, n, C, other, other_used,
+                                                           residual, bias);
   SCN_LAUNCHED();
   prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;

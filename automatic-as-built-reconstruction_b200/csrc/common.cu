@@ -346,11 +346,18 @@ k_rs_hist(const uint32_t *__restrict__ keys, int32_t *__restrict__ H, long long 
   for (int d = lane; d < RS_BINS; d += 32) hist[w][d] = 0;
   __syncwarp();
   if (chunk < n_chunks) {
+    // all 16 keys of the lane first (independent coalesced loads: the kernel runs ~4 warps per SM, so a load inside
+    // the loop was a full memory latency per iteration), then the shared-memory atomics
     const long long b = (long long)chunk * RS_CHUNK;
-    for (int it = 0; it < RS_CHUNK; it += 32) {
-      long long g = b + it + lane;
-      if (g < n) atomicAdd(&hist[w][(keys[g] >> shift) & (RS_BINS - 1)], 1);
+    uint32_t kreg[RS_CHUNK / 32];
+#pragma unroll
+    for (int i = 0; i < RS_CHUNK / 32; ++i) {
+      const long long g = b + i * 32 + lane;
+      kreg[i] = g < n ? keys[g] : 0u;
     }
+#pragma unroll
+    for (int i = 0; i < RS_CHUNK / 32; ++i)
+      if (b + i * 32 + lane < n) atomicAdd(&hist[w][(kreg[i] >> shift) & (RS_BINS - 1)], 1);
   }
   __syncwarp();
   if (chunk < n_chunks)
@@ -369,11 +376,20 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals
   __syncwarp();
   const long long b = (long long)chunk * RS_CHUNK;
   const unsigned lt = (1u << lane) - 1u;
-  for (int it = 0; it < RS_CHUNK; it += 32) {
-    long long g = b + it + lane;
+  uint32_t kreg[RS_CHUNK / 32];
+  int32_t vreg[RS_CHUNK / 32];
+#pragma unroll
+  for (int i = 0; i < RS_CHUNK / 32; ++i) {               // (see k_rs_hist: loads hoisted out of the ranking loop)
+    const long long g = b + i * 32 + lane;
+    kreg[i] = g < n ? keys[g] : 0u;
+    vreg[i] = g < n ? vals[g] : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < RS_CHUNK / 32; ++i) {
+    const long long g = b + i * 32 + lane;
     const bool valid = g < n;
-    uint32_t key = valid ? keys[g] : 0u;
-    int32_t val = valid ? vals[g] : 0;
+    const uint32_t key = kreg[i];
+    const int32_t val = vreg[i];
     const int d = valid ? (int)((key >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & lt);

@@ -553,6 +553,8 @@ int bias_grad(const float *d_out, float *d_bias, long long n, int C, cudaStream_
   return 0;
 }
 
+extern thread_local bool g_defer_dw_join, g_dw_join_pending;
+
 static double macs_of(const RuleBook *rb, int64_t cin, int64_t cout) {
   return (double)rb->total_pairs * (double)cin * (double)cout;
 }
@@ -581,8 +583,23 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
     SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s, mirror ? rb->K - 1 : -1,
                    weight_tag));
   if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, fork ? ss->stream : s));
-  if (fork) SCN_TRY(side_join(s, ss));
+  // (layer-graph reverse sweep: the join is deferred to the sweep's progress marks / its end, so the weight
+  // gradients of the latency-bound coarse scales run under the following layers instead of holding them up)
+  if (fork && !g_defer_dw_join) SCN_TRY(side_join(s, ss));
+  if (fork && g_defer_dw_join) g_dw_join_pending = true;
   SCN_TRY(bias_grad(d_out, d_bias, n_dout_rows, Cout, s));
+  return 0;
+}
+
+thread_local bool g_defer_dw_join = false;
+thread_local bool g_dw_join_pending = false;
+
+int dw_join_pending(cudaStream_t s) {
+  if (!g_dw_join_pending) return 0;
+  SideStream *ss = nullptr;
+  SCN_TRY(side_stream(s, &ss));
+  SCN_TRY(side_join(s, ss));
+  g_dw_join_pending = false;
   return 0;
 }
 

@@ -49,4 +49,9 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
                 int precision, cudaStream_t s);
 int bias_grad(const float *d_out, float *d_bias, long long n, int C, cudaStream_t s);
 
+// Weight gradients run on the companion stream of `s`.  Per-layer calls join it before returning; while
+// g_defer_dw_join is set (layer-graph reverse sweep, per host thread) the join is left to dw_join_pending(s).
+extern thread_local bool g_defer_dw_join, g_dw_join_pending;
+int dw_join_pending(cudaStream_t s);
+
 }  // namespace scn

@@ -149,11 +149,19 @@ int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int3
   int next_mark = 0;
   auto fire_marks = [&](int op_done) -> int {
     while (next_mark < n_marks && mark_ops[next_mark] >= op_done) {
+      SCN_TRY(dw_join_pending(s));                     // the weight gradients queued on the companion stream so far
       SCN_CUDA(cudaEventRecord((cudaEvent_t)mark_events[next_mark], s));
       ++next_mark;
     }
     return 0;
   };
+  // weight gradients run on the companion stream WITHOUT a join per layer: they only have to be complete at the
+  // marks and when the sweep returns (the join also runs on the error paths)
+  struct DeferJoin {
+    cudaStream_t s;
+    explicit DeferJoin(cudaStream_t st) : s(st) { g_defer_dw_join = true; }
+    ~DeferJoin() { g_defer_dw_join = false; dw_join_pending(s); }
+  } defer_join(s);
   for (int j = 1; j < n_marks; ++j) SCN_CHECK(mark_ops[j] <= mark_ops[j - 1], "marks must be in descending op order");
   // current gradient of every value: none yet / someone else's finished buffer (read only) / its own buffer
   enum { NONE = 0, ALIAS = 1, OWN = 2 };
@@ -192,9 +200,10 @@ int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int3
     if (o.kind == 4) {
       SCN_CHECK(grads[v], "graph op %d: BatchNorm input needs a gradient buffer", i);
       // BN gradient + whatever already arrived for the same value (skip connection), in one pass
-      SCN_TRY(scn_batchnorm_backward_add(values[v], grads[v], values[o.out], dY, bn_save + o.save_off,
-                                         bn_save + o.save_off + o.n_out_planes, w, dw, db, o.leakiness, rows[v],
-                                         o.n_out_planes, g[v].st == NONE ? nullptr : g[v].p, stream));
+      SCN_TRY(scn_batchnorm_backward_fused(values[v], grads[v], values[o.out], dY, bn_save + o.save_off,
+                                           bn_save + o.save_off + o.n_out_planes, w, o.p1 >= 0 ? params[o.p1] : nullptr,
+                                           1, dw, db, o.leakiness, rows[v], o.n_out_planes,
+                                           g[v].st == NONE ? nullptr : g[v].p, stream));
       g[v] = G{OWN, grads[v]};
     } else {
       float *d_in = nullptr;
@@ -226,6 +235,7 @@ int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int3
     if (o.p1 >= 0 && db) param_written[o.p1] = 1;
   }
   SCN_TRY(fire_marks(0));
+  SCN_TRY(dw_join_pending(s));
   return 0;
 }
 

@@ -93,6 +93,9 @@ _sig = {
     "scn_batchnorm_backward_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64,
                                            c_void_p, c_void_p]),
+    "scn_batchnorm_backward_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_int, c_void_p, c_void_p, c_float, c_int64, c_int64, c_void_p,
+                                             c_void_p]),
     "scn_graph_forward": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_void_p, POINTER(c_double)]),
     "scn_graph_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

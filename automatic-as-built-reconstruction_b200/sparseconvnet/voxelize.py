@@ -23,7 +23,7 @@ def quantize_points(xyz, scale, full_scale, batch_idx=0):
     return coords[:kept.value], keep.bool()
 
 
-def voxelize_batch(buildings, scale, full_scale, matrix=None, xyz_feature=True, device=None):
+def voxelize_batch(buildings, scale, full_scale, matrix=None, xyz_feature=True, device=None, buffers=None):
     """The dataset's quantisation + collate for a whole batch on the GPU (reference:
     SUNCGDataset.__getitem__, data3d/suncg_utils/suncg_dataset.py:126-188 + trainMerge, data3d/data.py:25-37).
 
@@ -32,7 +32,9 @@ def voxelize_batch(buildings, scale, full_scale, matrix=None, xyz_feature=True, 
     eye(3) * scale, i.e. no zoom / flip / rotation augmentation).  Returns (coords int64 [N,4] CUDA with the
     building index in column 3, feats float32 [N,C] CUDA with feats[:, 0:3] = voxel-space position / scale when
     xyz_feature) - what `net([coords, feats])` takes.  One H2D copy of 4 C bytes per point (36 B for the 9-column
-    SUNCG elements) replaces numpy's float64 passes and the 32 B/point int64 coordinate upload."""
+    SUNCG elements) replaces numpy's float64 passes and the 32 B/point int64 coordinate upload.
+    buffers: optional dict reused across calls (grow-only staging / output tensors; the returned tensors are then
+    views of it - VoxelLoader's ring)."""
     import numpy as np
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if len(buildings) == 0:
@@ -44,7 +46,16 @@ def voxelize_batch(buildings, scale, full_scale, matrix=None, xyz_feature=True, 
     counts = [int(b.size(0)) for b in buildings]
     first = torch.tensor([0] + list(np.cumsum(counts)[:-1]), dtype=torch.int64)
     n = sum(counts)
-    pts = torch.empty(n, C, dtype=torch.float32, device=device)
+    if buffers is not None:
+        if buffers.get("cap", -1) < n or buffers.get("C") != C:
+            cap = n + n // 8
+            buffers.setdefault("retired", []).append([buffers.get(k) for k in ("pts", "coords", "feats")])
+            buffers.update(cap=cap, C=C, pts=torch.empty(cap, C, dtype=torch.float32, device=device),
+                           coords=torch.empty(cap, 4, dtype=torch.int64, device=device),
+                           feats=torch.empty(cap, C, dtype=torch.float32, device=device))
+        pts = buffers["pts"][:n]
+    else:
+        pts = torch.empty(n, C, dtype=torch.float32, device=device)
     off = 0
     for b, k in zip(buildings, counts):                       # one async copy per building into the batch buffer
         pts[off:off + k].copy_(b, non_blocking=True)
@@ -53,8 +64,11 @@ def voxelize_batch(buildings, scale, full_scale, matrix=None, xyz_feature=True, 
     m = np.eye(3) * float(scale) if matrix is None else np.asarray(matrix, dtype=np.float64).reshape(3, 3)
     from ctypes import c_double
     mat = (c_double * 9)(*m.reshape(-1).tolist())
-    coords = torch.empty(n, 4, dtype=torch.int64, device=device)
-    feats = torch.empty(n, C, dtype=torch.float32, device=device)
+    if buffers is not None:
+        coords, feats = buffers["coords"][:n], buffers["feats"][:n]
+    else:
+        coords = torch.empty(n, 4, dtype=torch.int64, device=device)
+        feats = torch.empty(n, C, dtype=torch.float32, device=device)
     kept = c_int64()
     check(lib.scn_voxelize_batch(ptr(pts), n, C, ptr(first_dev), len(buildings), mat, float(scale), i64x3(full_scale),
                                  1 if xyz_feature else 0, ptr(coords), ptr(feats), byref(kept), stream()))
@@ -72,7 +86,9 @@ class VoxelLoader(object):
         for prepared, feats in loader:
             rpn_maps, roi_maps = net([prepared, feats])
 
-    `batches`: an iterable of lists of float32 [n_i, C] tensors (pinned host memory recommended)."""
+    `batches`: an iterable of lists of float32 [n_i, C] tensors (pinned host memory recommended).  The returned
+    feature tensor is a view of the loader's buffer ring: use it within the step it was handed out for (clone it to
+    keep it longer)."""
 
     def __init__(self, batches, prepare_fn, scale, full_scale, matrix=None, xyz_feature=True, device=None, depth=1):
         import queue
@@ -82,6 +98,16 @@ class VoxelLoader(object):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         from .modules import loader_stream
         self.stream = loader_stream(self.device)
+        # One batch waits in the queue, one is being built, one is in use by the consumer: a ring of depth + 2
+        # buffer sets, reused without any allocation per batch (a fresh torch allocation per batch on the side
+        # stream could not be recycled before the consumer's stream had passed it, and fell through to cudaMalloc -
+        # a device-wide stall every few batches).  Set k is rewritten for batch i + ring only after the consumer has
+        # asked for batch i + 1, i.e. after every use of batch i has been enqueued: the consumer records an event
+        # then and the loader's stream waits for it.
+        self.ring = max(1, depth) + 2
+        self.sets = [dict() for _ in range(self.ring)]
+        self.free_ev = [None] * self.ring
+        self.taken = 0
         self.done = queue.Queue(maxsize=max(1, depth))
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -89,10 +115,14 @@ class VoxelLoader(object):
     def _run(self):
         torch.cuda.set_device(self.device)
         try:
-            for buildings in self.batches:
+            for i, buildings in enumerate(self.batches):
                 with torch.cuda.stream(self.stream):
+                    k = i % self.ring
+                    if self.free_ev[k] is not None:
+                        self.stream.wait_event(self.free_ev[k])
                     scale, full_scale, matrix, xyz_feature = self.args
-                    coords, feats = voxelize_batch(buildings, scale, full_scale, matrix, xyz_feature, self.device)
+                    coords, feats = voxelize_batch(buildings, scale, full_scale, matrix, xyz_feature, self.device,
+                                                   buffers=self.sets[k])
                     prepared = self.prepare_fn(coords)
                     ev = torch.cuda.Event()
                     ev.record()
@@ -105,12 +135,16 @@ class VoxelLoader(object):
         return self
 
     def __next__(self):
+        if self.taken > 0:                                  # everything that uses the previous batch is enqueued
+            fe = torch.cuda.Event()
+            fe.record()
+            self.free_ev[(self.taken - 1) % self.ring] = fe
         r = self.done.get()
         if r is None:
             raise StopIteration
         if isinstance(r, Exception):
             raise r
         prepared, feats, ev = r
+        self.taken += 1
         torch.cuda.current_stream().wait_event(ev)          # the features were written on the loader's stream
-        feats.record_stream(torch.cuda.current_stream())
         return prepared, feats

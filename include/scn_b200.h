@@ -235,6 +235,14 @@ int scn_batchnorm_backward_add(const float *in, float *d_in, const float *out, c
                                const float *weight, float *d_weight, float *d_bias,
                                float leakiness, int64_t n_rows, int64_t n_planes,
                                const float *residual, void *stream);
+/* Same, given the forward's affine parameters: with recompute_mask != 0 `weight` / `bias` are the layer's gamma /
+ * beta (NULL = 1 / 0) and the (Leaky)ReLU mask is taken from the sign of the recomputed pre-activation
+ * fmaf(in, invstd * gamma, fma(-mean, invstd * gamma, beta)) - bit-identical to the forward's - so `out` is not
+ * read (5 instead of 7 tensor passes over [n, C]); `out` may then be NULL.  Used by the layer-graph executor. */
+int scn_batchnorm_backward_fused(const float *in, float *d_in, const float *out, const float *d_out,
+                                 const float *save_mean, const float *save_invstd, const float *weight,
+                                 const float *bias, int recompute_mask, float *d_weight, float *d_bias,
+                                 float leakiness, int64_t n, int64_t C, const float *residual, void *stream);
 
 /* ---- SparseToDense (replaces SparseToDense_updateOutput / _updateGradInput,
  *      pybind.cpp:124-133, CPU/SparseToDense.cpp:35-87) --------------------------------
