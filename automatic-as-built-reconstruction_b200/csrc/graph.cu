@@ -34,6 +34,8 @@ static int add_into(const float *a, const float *b, float *out, long long n, cud
   return 0;
 }
 
+static bool g_graph_defer_dw = true;   // scn_set_graph_overlap (the roofline pass of bench.py turns it off)
+
 static const int64_t *tag_of(const int64_t *tags, int p) {
   return (tags && p >= 0 && tags[2 * p] != 0) ? tags + 2 * p : nullptr;
 }
@@ -113,6 +115,11 @@ int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_o
                                    nullptr);
 }
 
+int scn_set_graph_overlap(int enabled) {
+  g_graph_defer_dw = enabled != 0;
+  return 0;
+}
+
 int scn_event_create(void **event) {
   SCN_CHECK(event, "null argument");
   cudaEvent_t e;
@@ -159,7 +166,7 @@ int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int3
   // marks and when the sweep returns (the join also runs on the error paths)
   struct DeferJoin {
     cudaStream_t s;
-    explicit DeferJoin(cudaStream_t st) : s(st) { g_defer_dw_join = true; }
+    explicit DeferJoin(cudaStream_t st) : s(st) { g_defer_dw_join = g_graph_defer_dw; }
     ~DeferJoin() { g_defer_dw_join = false; dw_join_pending(s); }
   } defer_join(s);
   for (int j = 1; j < n_marks; ++j) SCN_CHECK(mark_ops[j] <= mark_ops[j - 1], "marks must be in descending op order");
