@@ -554,6 +554,7 @@ int bias_grad(const float *d_out, float *d_bias, long long n, int C, cudaStream_
 }
 
 extern thread_local bool g_defer_dw_join, g_dw_join_pending;
+extern bool g_dw_companion;
 
 static double macs_of(const RuleBook *rb, int64_t cin, int64_t cout) {
   return (double)rb->total_pairs * (double)cin * (double)cout;
@@ -574,7 +575,7 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
   // dX and dW are independent: the weight gradient runs on the companion stream, so the many small
   // (latency-bound, few-CTA) launches of the coarse scales overlap instead of queueing
   SideStream *ss = nullptr;
-  const bool fork = d_in && d_weight;
+  const bool fork = d_in && d_weight && g_dw_companion;
   if (fork) {
     SCN_TRY(side_stream(s, &ss));
     SCN_TRY(side_fork(s, ss));
@@ -591,6 +592,7 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
   return 0;
 }
 
+bool g_dw_companion = true;              // false: weight gradients on the caller's stream (scn_set_graph_overlap(0))
 thread_local bool g_defer_dw_join = false;
 thread_local bool g_dw_join_pending = false;
 

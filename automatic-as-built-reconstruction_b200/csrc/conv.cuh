@@ -52,6 +52,7 @@ int bias_grad(const float *d_out, float *d_bias, long long n, int C, cudaStream_
 // Weight gradients run on the companion stream of `s`.  Per-layer calls join it before returning; while
 // g_defer_dw_join is set (layer-graph reverse sweep, per host thread) the join is left to dw_join_pending(s).
 extern thread_local bool g_defer_dw_join, g_dw_join_pending;
+extern bool g_dw_companion;
 int dw_join_pending(cudaStream_t s);
 
 }  // namespace scn

@@ -115,8 +115,9 @@ int scn_graph_backward(scn_metadata_t *m, const scn_graph_op_t *ops, int32_t n_o
                                    nullptr);
 }
 
-int scn_set_graph_overlap(int enabled) {
-  g_graph_defer_dw = enabled != 0;
+int scn_set_graph_overlap(int mode) {
+  g_graph_defer_dw = mode >= 2;
+  g_dw_companion = mode >= 1;
   return 0;
 }
 

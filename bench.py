@@ -389,8 +389,8 @@ def run_b200(args, rank, local_rank, world):
     na_total = float(na_t.item())
 
     # per-kernel-class roofline pass (CUDA events around each launch group, outside the headline timing)
-    # (weight gradients joined per layer here, so that the classes' event times do not overlap each other; the
-    # rulebook build runs inline on the same stream)
+    # (everything on one stream here - weight gradients included - so that the classes' event times are the
+    # kernels' own durations and do not overlap each other; the rulebook build runs inline on the same stream)
     from sparseconvnet import _lib as _scn_lib
     _scn_lib.lib.scn_set_graph_overlap(0)
     scn.SCN.prof_enable(True)
@@ -400,7 +400,7 @@ def run_b200(args, rank, local_rank, world):
         step(locs_dev, feats_dev)
     prof = scn.SCN.prof_read()
     scn.SCN.prof_enable(False)
-    _scn_lib.lib.scn_set_graph_overlap(1)
+    _scn_lib.lib.scn_set_graph_overlap(2)
 
     if rank == 0:
         peaks = {}
@@ -452,10 +452,10 @@ def run_b200(args, rank, local_rank, world):
                          "unit": "GB/s", "frac": ach / hbm_peak if hbm_peak else None, "traffic": traffic,
                          "launches_per_step": g["regions"] // 2, "ms_per_step": g["ms"] / 2},
             "kernel_classes": classes,
-            "kernel_classes_note": "separate pass (2 steps, rulebook build inline, one weight-gradient join per layer): "
-                                   "CUDA-event time per launch group on its own stream; a layer's weight gradient "
-                                   "runs on a companion stream beside its dX gather-GEMM, so those two classes' times "
-                                   "overlap and their sum exceeds the step; dX and dW each count the dY / pair-list / "
+            "kernel_classes_note": "separate pass (2 steps) with every kernel on ONE stream (rulebook build inline, weight "
+                                   "gradients not on their companion stream): CUDA-event time per launch group = the "
+                                   "kernels' own durations; in the timed steps the rulebook build and the weight "
+                                   "gradients overlap the rest, so the classes' sum exceeds ms_per_step; dX and dW each count the dY / pair-list / "
                                    "weight bytes they read, so the classes' algorithmic bytes sum to more than the "
                                    "8.81 GB per-building contract of SURVEY 8d",
             "grad_allreduce_bytes": bucket.nbytes() if (world > 1 and train) else 0,

@@ -303,10 +303,11 @@ int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int3
                               const float *const *out_grads, float *const *param_grads, uint8_t *param_written,
                               float *scratch, int64_t scratch_floats, int precision, void *stream, int32_t n_marks,
                               const int32_t *mark_ops, void *const *mark_events);
-/* 1 (default): the reverse sweep leaves the weight gradients on the companion stream until its marks / its end, so
- * they run under the following layers; 0: one join per layer (the kernel classes of a step then do not overlap -
- * what the per-class roofline pass of bench.py measures) */
-int scn_set_graph_overlap(int enabled);
+/* 2 (default): the reverse sweep leaves the weight gradients on the companion stream until its marks / its end, so
+ * they run under the following layers; 1: companion stream with one join per layer (the per-layer calls' behaviour);
+ * 0: everything on the caller's stream - no two kernels of a step overlap, which is what the per-class roofline
+ * pass of bench.py wants to time */
+int scn_set_graph_overlap(int mode);
 /* CUDA events as opaque handles (timing disabled) for the marks above */
 int scn_event_create(void **event);
 int scn_event_destroy(void *event);

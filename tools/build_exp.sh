@@ -11,5 +11,5 @@ mkdir -p "$ROOT/tools/_exp"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 \
   -DSCN_EXPERIMENT_$V -c "$C/conv_tc.cu" -o "/tmp/conv_tc_$V.o"
 /usr/local/cuda/bin/nvcc -shared -o "$ROOT/tools/_exp/libscn_$V.so" "$C/build/common.o" "$C/build/metadata.o" "$C/build/conv.o" \
-  "/tmp/conv_tc_$V.o" "$C/build/bn.o" "$C/build/io.o" "$C/build/graph.o"
+  "/tmp/conv_tc_$V.o" "$C/build/bn.o" "$C/build/io.o" "$C/build/graph.o" "$C/build/roi.o" "$C/build/rpn.o" "$C/build/nms.o"
 echo "built $ROOT/tools/_exp/libscn_$V.so"
