@@ -47,6 +47,7 @@ k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
                long long n, int C, double *__restrict__ acc, const float *__restrict__ invstd = nullptr,
                const float *__restrict__ gamma = nullptr, const float *__restrict__ beta = nullptr) {
+  pdl_sync();
   __shared__ double red[2][BN_T * 4];
   const int qpr = C >> 2;               // quads per row
   const int rpb = BN_T / qpr;           // rows per block iteration (>= 1 since C <= 1024)
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(BN_T)
 k_bn_stats_gen(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
                long long n, int C, double *__restrict__ acc) {
+  pdl_sync();
   __shared__ double red[2][8][33];
   const int c = blockIdx.y * 32 + threadIdx.x;
   double s0 = 0, s1 = 0;
@@ -195,6 +197,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(BN_T)
 k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, float leak,
                long long n, int C) {
+  pdl_sync();
   extern __shared__ float coef[];  // [2C]
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < a.zero_n; i += BN_T) a.zero_buf[i] = 0.0;
@@ -235,6 +238,7 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ save_invstd, const float *__restrict__ weight,
                float *d_weight, float *d_bias, float leak, long long n, int C, double *zero_buf, int zero_n,
                const float *R, const float *__restrict__ beta) {
+  pdl_sync();
   extern __shared__ float coef[];  // [3C] then mean [C], then (Yo == nullptr) the forward's [w, b] [2C]
   float *smean = coef + 3 * C;
   float *aff = coef + 4 * C;
@@ -366,17 +370,18 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
   if (train) {
     SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
     if (vec)
-      k_bn_stats_vec<false><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, nullptr, nullptr, nullptr, 0.f, n, C, acc);
+      SCN_LAUNCH((k_bn_stats_vec<false>), stats_grid(n, BN_T / (C / 4)), BN_T, 0, s, in, nullptr, nullptr, nullptr, 0.f, n, C, acc,
+                 nullptr, nullptr, nullptr);
     else
-      k_bn_stats_gen<false><<<dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, nullptr, nullptr, nullptr,
+      SCN_LAUNCH((k_bn_stats_gen<false>), dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s, in, nullptr, nullptr, nullptr,
                                                                                      0.f, n, C, acc);
     SCN_LAUNCHED();
   }
   BnFwdArgs a{other, other_used, acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train};
   const long long total = (long long)n * C;
   const size_t sm = (size_t)2 * C * sizeof(float);
-  if (vec) k_bn_fwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
-  else k_bn_fwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, a, leakiness, n, C);
+  if (vec) SCN_LAUNCH((k_bn_fwd_apply<true>), apply_grid(total / 4), BN_T, sm, s, in, out, a, leakiness, n, C);
+  else SCN_LAUNCH((k_bn_fwd_apply<false>), apply_grid(total), BN_T, sm, s, in, out, a, leakiness, n, C);
   SCN_LAUNCHED();
   prof_end(PROF_BN, s, (train ? 3.0 : 2.0) * 4.0 * (double)n * C, 0);  // 3 n C s
   return 0;
@@ -423,20 +428,20 @@ int scn_batchnorm_backward_fused(const float *in, float *d_in, const float *out,
   int other_used = 0;
   SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
   if (vec)
-    k_bn_stats_vec<true><<<stats_grid(n, BN_T / (C / 4)), BN_T, 0, s>>>(in, out, d_out, save_mean, leakiness, n, C, acc,
+    SCN_LAUNCH((k_bn_stats_vec<true>), stats_grid(n, BN_T / (C / 4)), BN_T, 0, s, in, out, d_out, save_mean, leakiness, n, C, acc,
                                                                         save_invstd, weight, bias);
   else
-    k_bn_stats_gen<true><<<dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s>>>(in, out, d_out, save_mean,
+    SCN_LAUNCH((k_bn_stats_gen<true>), dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s, in, out, d_out, save_mean,
                                                                                    leakiness, n, C, acc);
   SCN_LAUNCHED();
   const long long total = (long long)n * C;
   const size_t sm = (size_t)6 * C * sizeof(float);
   if (vec)
-    k_bn_bwd_apply<true><<<apply_grid(total / 4), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
+    SCN_LAUNCH((k_bn_bwd_apply<true>), apply_grid(total / 4), BN_T, sm, s, in, out, d_out, d_in, save_mean, acc, save_invstd,
                                                               weight, d_weight, d_bias, leakiness, n, C, other, other_used,
                                                               residual, bias);
   else
-    k_bn_bwd_apply<false><<<apply_grid(total), BN_T, sm, s>>>(in, out, d_out, d_in, save_mean, acc, save_invstd,
+    SCN_LAUNCH((k_bn_bwd_apply<false>), apply_grid(total), BN_T, sm, s, in, out, d_out, d_in, save_mean, acc, save_invstd,
                                                            weight, d_weight, d_bias, leakiness, n, C, other, other_used,
                                                            residual, bias);
   SCN_LAUNCHED();

@@ -20,6 +20,8 @@ void set_error(const char *fmt, ...) {
 
 // ---- profiling regions ----------------------------------------------------------------------
 bool g_prof_on = false;
+// programmatic dependent launch (common.cuh launch_k): 1 = every kernel (default), 2 = all but the tensor-core GEMMs, 0 = off
+int g_pdl = getenv("SCN_B200_PDL") ? atoi(getenv("SCN_B200_PDL")) : 1;
 struct ProfSeg { int cls; cudaEvent_t a, b; double bytes, flops; };
 static std::vector<ProfSeg> g_prof_segs;
 static std::vector<cudaEvent_t> g_prof_open[PROF_N];
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(SCAN_T)
 k_scan_lookback(const int32_t *in, int32_t *out, long long n_in, long long n_out,
                 volatile unsigned long long *desc, unsigned int *ticket, unsigned int ticket_base,
                 unsigned long long epoch) {
+  pdl_sync();
   __shared__ int32_t warp_tot[SCAN_T / 32];
   __shared__ unsigned int s_tile;
   __shared__ int32_t s_prefix;
@@ -315,9 +318,9 @@ static int scan_launch(const int32_t *in, int32_t *out, long long n, bool flags,
     st->epoch = 1;
   }
   if (flags)
-    k_scan_lookback<true><<<nb, SCAN_T, 0, s>>>(in, out, n, n_out, st->desc, st->ticket, st->base, st->epoch);
+    SCN_LAUNCH((k_scan_lookback<true>), nb, SCAN_T, 0, s, in, out, n, n_out, st->desc, st->ticket, st->base, st->epoch);
   else
-    k_scan_lookback<false><<<nb, SCAN_T, 0, s>>>(in, out, n, n_out, st->desc, st->ticket, st->base, st->epoch);
+    SCN_LAUNCH((k_scan_lookback<false>), nb, SCAN_T, 0, s, in, out, n, n_out, st->desc, st->ticket, st->base, st->epoch);
   st->base += (unsigned int)nb;
   SCN_LAUNCHED();
   return 0;
@@ -340,6 +343,7 @@ constexpr int RS_WARPS = 4, RS_CHUNK = 512, RS_BITS = 9, RS_BINS = 1 << RS_BITS;
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rs_hist(const uint32_t *__restrict__ keys, int32_t *__restrict__ H, long long n, int shift,
           int n_chunks) {
+  pdl_sync();
   __shared__ int32_t hist[RS_WARPS][RS_BINS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * RS_WARPS + w;
@@ -368,6 +372,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals,
              uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out,
              const int32_t *__restrict__ Hs, long long n, int shift, int n_chunks) {
+  pdl_sync();
   __shared__ int32_t cnt[RS_WARPS][RS_BINS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * RS_WARPS + w;
@@ -424,10 +429,10 @@ int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaS
   uint32_t *ka = keys, *kb = k2;
   int32_t *va = vals, *vb = v2;
   for (int p = 0; p < passes; ++p) {
-    k_rs_hist<<<nb, RS_WARPS * 32, 0, s>>>(ka, H, n, p * RS_BITS, n_chunks);
+    SCN_LAUNCH(k_rs_hist, nb, RS_WARPS * 32, 0, s, ka, H, n, p * RS_BITS, n_chunks);
     SCN_LAUNCHED();
     SCN_TRY(exclusive_scan_i32(H, H, (long long)RS_BINS * n_chunks, s));
-    k_rs_scatter<<<nb, RS_WARPS * 32, 0, s>>>(ka, va, kb, vb, H, n, p * RS_BITS, n_chunks);
+    SCN_LAUNCH(k_rs_scatter, nb, RS_WARPS * 32, 0, s, ka, va, kb, vb, H, n, p * RS_BITS, n_chunks);
     SCN_LAUNCHED();
     uint32_t *tk = ka; ka = kb; kb = tk;
     int32_t *tv = va; va = vb; vb = tv;
@@ -443,6 +448,7 @@ int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaS
 }
 
 __global__ void k_scale(float *y, float a, long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long st = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += st) y[i] *= a;
@@ -455,6 +461,10 @@ const char *scn_last_error(void) { return scn::g_err; }
 int scn_version(void) { return 100; }
 int scn_n_rulebook_bits(void) { return 32; }
 int64_t scn_launch_count(void) { return scn::g_launches.load(); }
+int scn_set_pdl(int mode) {
+  scn::g_pdl = mode;
+  return 0;
+}
 int scn_prof_enable(int on) {
   scn::g_prof_on = on != 0;
   return 0;
@@ -482,7 +492,7 @@ int scn_scale_inplace(float *y, float alpha, int64_t n, void *stream) {
   int nb = scn::cdiv(n, 256);
   int cap = scn::num_sms() * 8;
   if (nb > cap) nb = cap;
-  scn::k_scale<<<nb, 256, 0, (cudaStream_t)stream>>>(y, alpha, n);
+  SCN_LAUNCH(scn::k_scale, nb, 256, 0, (cudaStream_t)stream, y, alpha, n);
   SCN_LAUNCHED();
   return 0;
 }

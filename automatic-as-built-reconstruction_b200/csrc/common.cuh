@@ -8,6 +8,7 @@
 #include <string.h>
 #include <atomic>
 #include <string>
+#include <utility>
 
 namespace scn {
 
@@ -95,6 +96,36 @@ static inline void prof_end(int cls, cudaStream_t s, double bytes, double flops)
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- kernel launches: programmatic dependent launch ---------------------------------------------
+// A backbone step is ~1000 small DEPENDENT kernels; between two of them on one stream the GPU idles for the launch
+// latency (measured, tools/pdl_probe.cu: 4.0 us per trivial kernel, 2.5 us with programmatic stream serialization).
+// Every kernel of this library therefore starts with pdl_sync(): griddepcontrol.launch_dependents (the NEXT kernel of
+// the stream may be scheduled as soon as every CTA of this one has started) followed by griddepcontrol.wait (block
+// until the PREVIOUS kernel has completed and its writes are visible).  No kernel touches global memory before its
+// wait, and every thread executes it, so "kernel N complete" still implies "kernel N-1 complete": events, memcpys
+// and foreign (torch) kernels that follow in the stream see exactly the ordinary stream order.
+// g_pdl (SCN_B200_PDL): 0 = plain launches, 1 = every kernel, 2 = every kernel except the persistent tensor-core
+// GEMMs (whose early-scheduled CTAs would hold the SMs of a finishing GEMM against the companion streams).
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (g_pdl == 1 || (g_pdl == 2 && pdl_class == 0)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+// SCN_LAUNCH(kernel, grid, block, smem, stream, args...): class 0 (ordinary kernel)
+#define SCN_LAUNCH(kernel, ...) scn::launch_k(0, kernel, __VA_ARGS__)
+#define SCN_LAUNCH_GEMM(kernel, ...) scn::launch_k(1, kernel, __VA_ARGS__)
 int num_sms();
 
 // ---- device-wide exclusive scan of int32 ----------------------------------------------
@@ -109,6 +140,10 @@ int radix_sort_pairs(uint32_t *keys, int32_t *vals, long long n, int bits, cudaS
 
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__
+// first statement of every kernel (see launch_k); a no-op for a kernel launched without the attribute
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 k_osgemm_ffma(const float *__restrict__ X, const float *__restrict__ W,
               const float *__restrict__ bias, float *__restrict__ Y, int Cin, int Cout,
               long long n_rows, TileView tb) {
+  pdl_sync();
   constexpr int TN = BN / 16;
   __shared__ __align__(16) float As[BK][LDA];
   __shared__ __align__(16) float Bs[BK][BN];
@@ -198,9 +199,9 @@ static int launch_osgemm_ffma(const float *X, const float *W, const float *bias,
   dim3 grid(tv.n_tiles, cdiv(Cout, BN));
   const bool va = (Cin % 4 == 0) && ((uintptr_t)X % 16 == 0);
   const bool vb = (Cout % 4 == 0) && ((uintptr_t)W % 16 == 0);
-  if (va && vb) k_osgemm_ffma<BN, true, true><<<grid, 256, 0, s>>>(X, W, bias, Y, Cin, Cout, n_rows, tv);
-  else if (!va && vb) k_osgemm_ffma<BN, false, true><<<grid, 256, 0, s>>>(X, W, bias, Y, Cin, Cout, n_rows, tv);
-  else k_osgemm_ffma<BN, false, false><<<grid, 256, 0, s>>>(X, W, bias, Y, Cin, Cout, n_rows, tv);
+  if (va && vb) SCN_LAUNCH((k_osgemm_ffma<BN, true, true>), grid, 256, 0, s, X, W, bias, Y, Cin, Cout, n_rows, tv);
+  else if (!va && vb) SCN_LAUNCH((k_osgemm_ffma<BN, false, true>), grid, 256, 0, s, X, W, bias, Y, Cin, Cout, n_rows, tv);
+  else SCN_LAUNCH((k_osgemm_ffma<BN, false, false>), grid, 256, 0, s, X, W, bias, Y, Cin, Cout, n_rows, tv);
   SCN_LAUNCHED();
   return 0;
 }
@@ -222,6 +223,7 @@ TileView make_view(const TileBook &tb, int k_flip) {
 // dst[r][0..cp) = src[r][0..c), zero beyond: narrow feature rows (the 9-channel stem input) padded to one
 // 32-channel slice so that they take the tensor-core kernels
 __global__ void k_pad_cols(const float *__restrict__ src, float *__restrict__ dst, long long rows, int c, int cp) {
+  pdl_sync();
   const long long total = rows * cp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cp;
@@ -231,6 +233,7 @@ __global__ void k_pad_cols(const float *__restrict__ src, float *__restrict__ ds
 }
 // Wp[k][0..cp)[co] = W[k][0..c)[co], zero rows beyond
 __global__ void k_pad_w_rows(const float *__restrict__ W, float *__restrict__ Wp, int K, int c, int cp, int cout) {
+  pdl_sync();
   const int total = K * cp * cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / (cp * cout), r = i - k * cp * cout, ci = r / cout, co = r - ci * cout;
@@ -245,12 +248,13 @@ static int pad_rows(const float *X, long long rows, int Cin, float **out, cudaSt
   SCN_TRY(workspace_t(out, WS_PAD_X, (size_t)rows * PAD_C, s));
   long long blocks = (rows * PAD_C + 255) / 256;
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
-  k_pad_cols<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, s>>>(X, *out, rows, Cin, PAD_C);
+  SCN_LAUNCH(k_pad_cols, (int)(blocks < 1 ? 1 : blocks), 256, 0, s, X, *out, rows, Cin, PAD_C);
   SCN_LAUNCHED();
   return 0;
 }
 
 __global__ void k_accumulate(float *__restrict__ y, const float *__restrict__ t, long long n) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] += t[i];
 }
@@ -266,7 +270,7 @@ static int osgemm_book(const float *X, const float *W, const float *bias, float 
     float *xp = nullptr, *wp = nullptr;
     SCN_TRY(pad_rows(X, tb.n_partner, Cin, &xp, s));
     SCN_TRY(workspace_t(&wp, WS_PAD_W, (size_t)K * PAD_C * Cout, s));
-    k_pad_w_rows<<<cdiv((long long)K * PAD_C * Cout, 256), 256, 0, s>>>(W, wp, K, Cin, PAD_C, Cout);
+    SCN_LAUNCH(k_pad_w_rows, cdiv((long long)K * PAD_C * Cout, 256), 256, 0, s, W, wp, K, Cin, PAD_C, Cout);
     SCN_LAUNCHED();
     r = osgemm_tc(xp, wp, bias, Y, PAD_C, Cout, tb.n_rows, tv, K, tb.K, precision, 0, s, bytes, flops, nullptr);
   } else if (precision != SCN_PRECISION_FP32)
@@ -312,7 +316,7 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
     SCN_TRY(osgemm_book(X, W, nullptr, part, Cin, Cout, *b, K, 0.0, 0.0, precision, transpose_w, s, k_flip, weight_tag));
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    k_accumulate<<<(int)blocks, 256, 0, s>>>(Y, part, n);
+    SCN_LAUNCH(k_accumulate, (int)blocks, 256, 0, s, Y, part, n);
     SCN_LAUNCHED();
   }
   return 0;
@@ -321,6 +325,7 @@ int osgemm(const float *X, const float *W, const float *bias, float *Y, int Cin,
 // Wt[k][co][ci] = W[k][ci][co]
 __global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int K, int Cin,
                               int Cout) {
+  pdl_sync();
   __shared__ float t[32][33];
   const int k = blockIdx.z;
   const float *w = W + (long long)k * Cin * Cout;
@@ -339,7 +344,7 @@ __global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ W
 
 int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, cudaStream_t s) {
   dim3 grid(cdiv(Cout, 32), cdiv(Cin, 32), K), block(32, 8);
-  k_transpose_w<<<grid, block, 0, s>>>(W, Wt, K, Cin, Cout);
+  SCN_LAUNCH(k_transpose_w, grid, block, 0, s, W, Wt, K, Cin, Cout);
   SCN_LAUNCHED();
   return 0;
 }
@@ -356,6 +361,7 @@ k_dw_partial(const float *__restrict__ X, const float *__restrict__ dY,
              const int32_t *__restrict__ pairs, const DwWork *__restrict__ work,
              float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
              long long ident_n, int ident_chunk) {
+  pdl_sync();
   constexpr int CI = 16 * TI, CO = 16 * TJ;
   __shared__ __align__(16) float Xs[DW_P][CI];
   __shared__ __align__(16) float Ys[DW_P][CO];
@@ -439,6 +445,7 @@ struct KFirst { int v[MAX_KT + 1]; };
 // first Cin rows of a partial are the real ones)
 __global__ void k_dw_reduce(const float *__restrict__ partial, float *__restrict__ dW, KFirst first,
                             int cc /* Cin*Cout */, int ccp) {
+  pdl_sync();
   const int k = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cc) return;
@@ -453,7 +460,7 @@ static int launch_dw_partial(const float *X, const float *dY, const int32_t *pai
                              int ycol, int n_work, long long ident_n, int ident_chunk,
                              cudaStream_t s) {
   dim3 grid(n_work, cdiv(Cin, 16 * TI), cdiv(Cout, 16 * TJ));
-  k_dw_partial<TI, TJ><<<grid, 256, 0, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol,
+  SCN_LAUNCH((k_dw_partial<TI, TJ>), grid, 256, 0, s, X, dY, pairs, work, partial, Cin, Cout, xcol, ycol,
                                             ident_n, ident_chunk);
   SCN_LAUNCHED();
   return 0;
@@ -524,7 +531,7 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
     if (r) return 1;
   }
   dim3 grid(cdiv(cc, 256), K);
-  k_dw_reduce<<<grid, 256, 0, s>>>(partial, dW, first, cc, ccp);
+  SCN_LAUNCH(k_dw_reduce, grid, 256, 0, s, partial, dW, first, cc, ccp);
   SCN_LAUNCHED();
   prof_end(PROF_DW, s, dw_bytes, dw_flops);
   return 0;
@@ -532,6 +539,7 @@ int weight_grad(const float *X, const float *dY, float *dW, int Cin, int Cout, R
 
 // d_bias[c] = sum_rows d_out[row][c]  (CPU/Convolution.cpp:99-100)
 __global__ void k_colsum(const float *__restrict__ A, float *__restrict__ out, long long n, int C) {
+  pdl_sync();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -548,7 +556,7 @@ __global__ void k_colsum(const float *__restrict__ A, float *__restrict__ out, l
 
 int bias_grad(const float *d_out, float *d_bias, long long n, int C, cudaStream_t s) {
   if (!d_bias) return 0;
-  k_colsum<<<cdiv(C, 32), dim3(32, 8), 0, s>>>(d_out, d_bias, n, C);
+  SCN_LAUNCH(k_colsum, cdiv(C, 32), dim3(32, 8), 0, s, d_out, d_bias, n, C);
   SCN_LAUNCHED();
   return 0;
 }

@@ -316,6 +316,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
               float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched, int ms) {
   // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool X3 = MODE == 1, BF = MODE == 2, CONV = MODE != 0;
   const Smem L(N, K, NSA, NSB, MODE, ms);
@@ -377,6 +378,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barrier init and the TMEM allocation overlap the previous kernel's tail; nothing global before this point
+  pdl_wait();
 
   if (warp == META_W) {
     // ===== metadata loader =====
@@ -825,6 +828,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 // Y[perm[slot]] = bias + sum_s Ypart[s][slot]   (fixed summation order)
 __global__ void k_splitk_reduce(const float *__restrict__ Ypart, const float *__restrict__ bias, float *__restrict__ Y,
                                 int N, int splits, long long n_slots, long long n_rows, TileView tb) {
+  pdl_sync();
   const int q = N >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots * q) return;
@@ -871,6 +875,7 @@ __device__ __forceinline__ void pack_element(const float *__restrict__ W, float 
 
 __global__ void k_pack_weights_both(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wb,
                                     int K, int Cin, int Cout, int do_f, int do_b, int x3) {
+  pdl_sync();
   const long long total = (long long)K * Cin * Cout;
   for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
        i2 += (long long)gridDim.x * blockDim.x)
@@ -900,6 +905,7 @@ __device__ __forceinline__ void pack_element_bf16(const float *__restrict__ W, _
 
 __global__ void k_pack_weights_bf16(const float *__restrict__ W, __nv_bfloat16 *__restrict__ Wf, __nv_bfloat16 *__restrict__ Wb,
                                     int K, int Cin, int Cout, int do_f, int do_b) {
+  pdl_sync();
   const long long total = (long long)K * Cin * Cout;
   for (long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < 2 * total;
        i2 += (long long)gridDim.x * blockDim.x)
@@ -917,6 +923,7 @@ struct PackBatch { PackJob job[PACK_JOBS]; };
 // of the same 128-byte line.  Forward image (row n = output channel, reduction = input channels): the tile is
 // transposed through shared memory.  bf16 images keep the element-wise path.
 __global__ void __launch_bounds__(256) k_pack_weights_batch(const __grid_constant__ PackBatch b, int x3) {
+  pdl_sync();
   const PackJob &j = b.job[blockIdx.y];
   if (x3 == 2) {
     const long long total = (long long)j.K * j.Cin * j.Cout;
@@ -1039,10 +1046,10 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     int pb = cdiv(2 * (long long)total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
     if (x3 == 2)
-      k_pack_weights_bf16<<<pb, 256, 0, s>>>(W, reinterpret_cast<__nv_bfloat16 *>(e->wf), reinterpret_cast<__nv_bfloat16 *>(e->wb),
+      SCN_LAUNCH(k_pack_weights_bf16, pb, 256, 0, s, W, reinterpret_cast<__nv_bfloat16 *>(e->wf), reinterpret_cast<__nv_bfloat16 *>(e->wb),
                                              K, Cin, Cout, e->has_f, e->has_b);
     else
-      k_pack_weights_both<<<pb, 256, 0, s>>>(W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b, x3);
+      SCN_LAUNCH(k_pack_weights_both, pb, 256, 0, s, W, e->wf, e->wb, K, Cin, Cout, e->has_f, e->has_b, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SCN_CUDA(cudaGetLastError());
     e->version = tag[1];
@@ -1070,7 +1077,7 @@ int prepack_weights_batch(int n, const int64_t *const *tags, const float *const 
   int nj = 0;
   auto flush = [&]() -> int {
     if (nj == 0) return 0;
-    k_pack_weights_batch<<<dim3(num_sms(), nj), 256, 0, s>>>(b, x3);
+    SCN_LAUNCH(k_pack_weights_batch, dim3(num_sms(), nj), 256, 0, s, b, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SCN_CUDA(cudaGetLastError());
     nj = 0;
@@ -1136,10 +1143,10 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     int pb = cdiv(2 * total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
     if (x3 == 2)
-      k_pack_weights_bf16<<<pb, 256, 0, s>>>(W, reinterpret_cast<__nv_bfloat16 *>(wp), reinterpret_cast<__nv_bfloat16 *>(wp), K,
+      SCN_LAUNCH(k_pack_weights_bf16, pb, 256, 0, s, W, reinterpret_cast<__nv_bfloat16 *>(wp), reinterpret_cast<__nv_bfloat16 *>(wp), K,
                                              cin, cout, !transpose_w, transpose_w);
     else
-      k_pack_weights_both<<<pb, 256, 0, s>>>(W, wp, wp, K, cin, cout, !transpose_w, transpose_w, x3);
+      SCN_LAUNCH(k_pack_weights_both, pb, 256, 0, s, W, wp, wp, K, cin, cout, !transpose_w, transpose_w, x3);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   // ring depths: 2-3 weight-slice stages, then as many gathered-row stages as fit beside the metadata
@@ -1211,7 +1218,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   if (sched_counters(&sched, s)) return -1;
   prof_begin(PROF_GEMM, s);
 #define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
-  k_osgemm_tf32<D, T3><<<grid, T3 ? NT_P3 : NT_P, L.total, s>>>(X, wp, bias, Y, Kd, NW, N, Kb, n_rows, tv, cols, ypart, \
+  SCN_LAUNCH_GEMM((k_osgemm_tf32<D, T3>), grid, T3 ? NT_P3 : NT_P, L.total, s, X, wp, bias, Y, Kd, NW, N, Kb, n_rows, tv, cols, ypart, \
                                                                 n_items, splits, nsb, sched, ms)
 #define SCN_OSGEMM_DEPTH(T3)                                                                                  \
   switch (depth) {                                                                                            \
@@ -1230,7 +1237,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   cudaError_t e = cudaGetLastError();
   if (splits > 1 && e == cudaSuccess) {
     const long long work = n_slots * (N >> 2);
-    k_splitk_reduce<<<cdiv(work, 256), 256, 0, s>>>(ypart, bias, Y, N, splits, n_slots, n_rows, tv);
+    SCN_LAUNCH(k_splitk_reduce, cdiv(work, 256), 256, 0, s, ypart, bias, Y, N, splits, n_slots, n_rows, tv);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaGetLastError();
   }
@@ -1297,6 +1304,7 @@ __global__ void __launch_bounds__(X3 ? NT_DW3 : NT_DW)
 k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32_t *__restrict__ pairs,
           const DwWork *__restrict__ work, float *__restrict__ partial, int Cin, int Cout, int xcol, int ycol,
           long long ident_n, int ident_chunk, int KP, uint32_t tmem_cols) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int CA = Cin >> 5, CB = Cout >> 5;        // real 32-channel atoms
   const int MA = Cin > 128 ? CA : 4;              // atoms per k-atom of A (M padded to 128)
@@ -1317,18 +1325,6 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   const int KA = KP >> 2;                          // k-atoms (4 pairs) per step
   const uint32_t sbo_a = MA * 512, sbo_b = CB * 512;
 
-  long long start;
-  int len, out_slot = blockIdx.x;
-  if (work) {
-    const DwWork w = work[blockIdx.x];
-    start = w.start;
-    len = w.len;
-    out_slot = w.slot;                               // launch order != partial order (ensure_dw_work)
-  } else {
-    start = (long long)blockIdx.x * ident_chunk;
-    len = (int)min((long long)ident_chunk, ident_n - start);
-  }
-  const int steps = (len + KP - 1) / KP;
   // zero the atoms that pad M up to 128 (never written by the gathers)
   if (CA < MA) {
     const int per_ka = (MA - CA) * 32;             // 16-byte units per k-atom
@@ -1362,6 +1358,20 @@ k_dw_tf32(const float *__restrict__ X, const float *__restrict__ dY, const int32
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  // shared-memory set-up and the TMEM allocation overlap the previous kernel's tail; nothing global before this point
+  pdl_wait();
+  long long start;
+  int len, out_slot = blockIdx.x;
+  if (work) {
+    const DwWork w = work[blockIdx.x];
+    start = w.start;
+    len = w.len;
+    out_slot = w.slot;                               // launch order != partial order (ensure_dw_work)
+  } else {
+    start = (long long)blockIdx.x * ident_chunk;
+    len = (int)min((long long)ident_chunk, ident_n - start);
+  }
+  const int steps = (len + KP - 1) / KP;
 
   if (warp == DW_LOAD_W) {
     // ===== pair-list loader: lane l carries pairs l and l+32 of a step, 4 steps ahead in registers =====
@@ -1630,7 +1640,7 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   uint32_t cols = 32;
   while ((int)cols < Cout * (Cin > 128 ? 2 : 1)) cols <<= 1;
 #define SCN_DW_LAUNCH(NS, T3)                                                                                       \
-  k_dw_tf32<NS, T3><<<n_work, T3 ? NT_DW3 : NT_DW, L.total, s>>>(X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, \
+  SCN_LAUNCH_GEMM((k_dw_tf32<NS, T3>), n_work, T3 ? NT_DW3 : NT_DW, L.total, s, X, dY, pairs, work, partial, Cin, Cout, xcol, ycol, \
                                                                  ident_n, ident_chunk, KP, cols)
   if (x3) {
     if (ns == 3) SCN_DW_LAUNCH(3, true);

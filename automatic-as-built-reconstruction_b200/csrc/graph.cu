@@ -11,6 +11,7 @@
 namespace scn {
 
 __global__ void k_add(const float *a, const float *b, float *out, long long n4, long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long st = (long long)gridDim.x * blockDim.x;
   for (long long q = i; q < n4; q += st) {
@@ -29,7 +30,7 @@ static int add_into(const float *a, const float *b, float *out, long long n, cud
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_add<<<(int)blocks, 256, 0, s>>>(a, b, out, n4, n);
+  SCN_LAUNCH(k_add, (int)blocks, 256, 0, s, a, b, out, n4, n);
   SCN_LAUNCHED();
   return 0;
 }

@@ -12,6 +12,7 @@ namespace scn {
 __global__ void k_input_fwd(const float *__restrict__ in, float *__restrict__ out,
                             const int32_t *__restrict__ csr_off, const int32_t *__restrict__ members,
                             long long n_rows, int C, int mode) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * C) return;
   const long long row = i / C;
@@ -32,6 +33,7 @@ __global__ void k_input_bwd(float *__restrict__ d_in, const float *__restrict__ 
                             const int32_t *__restrict__ point_row, const int32_t *__restrict__ csr_off,
                             const int32_t *__restrict__ members, long long n_points, int C, int mode,
                             int average) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points * C) return;
   const long long p = i / C;
@@ -49,6 +51,7 @@ __global__ void k_input_bwd(float *__restrict__ d_in, const float *__restrict__ 
 __global__ void k_output_bwd(float *__restrict__ d_in, const float *__restrict__ d_out,
                              const int32_t *__restrict__ csr_off, const int32_t *__restrict__ members,
                              long long n_rows, int C, int mode) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * C) return;
   const long long row = i / C;
@@ -67,6 +70,7 @@ __global__ void k_output_bwd(float *__restrict__ d_in, const float *__restrict__
 __global__ void k_s2d_fwd(const float *__restrict__ in, float *__restrict__ out,
                           const int32_t *__restrict__ coords, long long n, int C, long long Y,
                           long long Z, long long V) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * C) return;
   // consecutive threads take consecutive rows of one plane: reads stride C, writes follow the
@@ -80,6 +84,7 @@ __global__ void k_s2d_fwd(const float *__restrict__ in, float *__restrict__ out,
 __global__ void k_s2d_bwd(float *__restrict__ d_in, const float *__restrict__ d_out,
                           const int32_t *__restrict__ coords, long long n, int C, long long Y,
                           long long Z, long long V) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * C) return;
   const int c = (int)(i / n);
@@ -101,6 +106,7 @@ __device__ __forceinline__ void atomic_min_double(double *addr, double v) {
 }
 
 __global__ void k_quant_min(const double *__restrict__ xyz, long long n, double scale, double *mn) {
+  pdl_sync();
   __shared__ double sm[3][256];
   double m[3] = {1e300, 1e300, 1e300};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -122,6 +128,7 @@ struct Full3 { long long v[3]; };
 __global__ void k_quant_flag(const double *__restrict__ xyz, long long n, double scale,
                              const double *__restrict__ mn, Full3 full, uint8_t *__restrict__ keep,
                              int32_t *__restrict__ flag) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   bool k = true;
@@ -138,6 +145,7 @@ __global__ void k_quant_flag(const double *__restrict__ xyz, long long n, double
 __global__ void k_quant_emit(const double *__restrict__ xyz, long long n, double scale,
                              const double *__restrict__ mn, const int32_t *__restrict__ pos,
                              long long batch_idx, int64_t *__restrict__ coords) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int p = pos[i];
@@ -155,6 +163,7 @@ __global__ void k_quant_emit(const double *__restrict__ xyz, long long n, double
 struct Vox { double m[9]; long long full[3]; double scale; };
 
 __global__ void k_fill_double(double *p, double v, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -182,6 +191,7 @@ constexpr int VOX_PER_BLOCK = 256 * 8;
 __global__ void __launch_bounds__(256)
 k_vox_min(const float *__restrict__ pts, int C, long long n, const int64_t *__restrict__ first, int B,
           Vox v, double *__restrict__ mn /* [B,3] */) {
+  pdl_sync();
   __shared__ double sm[3][256];
   const long long p0 = (long long)blockIdx.x * VOX_PER_BLOCK;
   const long long p1 = min(p0 + VOX_PER_BLOCK, n);
@@ -214,6 +224,7 @@ k_vox_min(const float *__restrict__ pts, int C, long long n, const int64_t *__re
 
 __global__ void k_vox_flag(const float *__restrict__ pts, int C, long long n, const int64_t *__restrict__ first, int B,
                            Vox v, const double *__restrict__ mn, int32_t *__restrict__ flag) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double a[3];
@@ -231,6 +242,7 @@ __global__ void k_vox_flag(const float *__restrict__ pts, int C, long long n, co
 __global__ void k_vox_emit(const float *__restrict__ pts, int C, long long n, const int64_t *__restrict__ first, int B,
                            Vox v, const double *__restrict__ mn, const int32_t *__restrict__ pos,
                            int64_t *__restrict__ coords, float *__restrict__ feats, int xyz_feature) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int p = pos[i];
@@ -264,8 +276,7 @@ int scn_input_layer_forward(scn_metadata_t *m, const float *in, float *out, int6
   const long long total = ir.n_active * C;
   if (total == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
-  k_input_fwd<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      in, out, ir.csr_off, ir.members, ir.n_active, (int)C, ir.mode == 0 ? 3 : ir.mode);
+  SCN_LAUNCH(k_input_fwd, cdiv(total, 256), 256, 0, (cudaStream_t)stream, in, out, ir.csr_off, ir.members, ir.n_active, (int)C, ir.mode == 0 ? 3 : ir.mode);
   SCN_LAUNCHED();
   return 0;
 }
@@ -277,8 +288,7 @@ int scn_input_layer_backward(scn_metadata_t *m, float *d_in, const float *d_out,
   const long long total = ir.n_points * C;
   if (total == 0) return 0;
   SCN_CHECK(d_in && d_out, "null feature pointer");
-  k_input_bwd<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      d_in, d_out, ir.point_row, ir.csr_off, ir.members, ir.n_points, (int)C,
+  SCN_LAUNCH(k_input_bwd, cdiv(total, 256), 256, 0, (cudaStream_t)stream, d_in, d_out, ir.point_row, ir.csr_off, ir.members, ir.n_points, (int)C,
       ir.mode == 0 ? 3 : ir.mode, ir.mode == 4);
   SCN_LAUNCHED();
   return 0;
@@ -292,8 +302,7 @@ int scn_output_layer_forward(scn_metadata_t *m, const float *in, float *out, int
   const long long total = ir.n_points * C;
   if (total == 0) return 0;
   SCN_CHECK(in && out, "null feature pointer");
-  k_input_bwd<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      out, in, ir.point_row, ir.csr_off, ir.members, ir.n_points, (int)C,
+  SCN_LAUNCH(k_input_bwd, cdiv(total, 256), 256, 0, (cudaStream_t)stream, out, in, ir.point_row, ir.csr_off, ir.members, ir.n_points, (int)C,
       ir.mode == 0 ? 3 : ir.mode, 0);
   SCN_LAUNCHED();
   return 0;
@@ -307,8 +316,7 @@ int scn_output_layer_backward(scn_metadata_t *m, float *d_in, const float *d_out
   const long long total = ir.n_active * C;
   if (total == 0) return 0;
   SCN_CHECK(d_in && d_out, "null feature pointer");
-  k_output_bwd<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      d_in, d_out, ir.csr_off, ir.members, ir.n_active, (int)C, ir.mode == 0 ? 3 : ir.mode);
+  SCN_LAUNCH(k_output_bwd, cdiv(total, 256), 256, 0, (cudaStream_t)stream, d_in, d_out, ir.csr_off, ir.members, ir.n_active, (int)C, ir.mode == 0 ? 3 : ir.mode);
   SCN_LAUNCHED();
   return 0;
 }
@@ -323,7 +331,7 @@ int scn_sparse_to_dense_forward(scn_metadata_t *m, const int64_t *ss, const floa
   if (!g || g->n_active == 0) return 0;
   SCN_CHECK(in, "null feature pointer");
   const long long total = g->n_active * C;
-  k_s2d_fwd<<<cdiv(total, 256), 256, 0, s>>>(in, out, g->coords, g->n_active, (int)C, ss[1], ss[2], V);
+  SCN_LAUNCH(k_s2d_fwd, cdiv(total, 256), 256, 0, s, in, out, g->coords, g->n_active, (int)C, ss[1], ss[2], V);
   SCN_LAUNCHED();
   return 0;
 }
@@ -337,7 +345,7 @@ int scn_sparse_to_dense_backward(scn_metadata_t *m, const int64_t *ss, float *d_
   SCN_CHECK(d_in && d_out, "null feature pointer");
   const long long V = ss[0] * ss[1] * ss[2];
   const long long total = g->n_active * C;
-  k_s2d_bwd<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, g->coords, g->n_active,
+  SCN_LAUNCH(k_s2d_bwd, cdiv(total, 256), 256, 0, (cudaStream_t)stream, d_in, d_out, g->coords, g->n_active,
                                                               (int)C, ss[1], ss[2], V);
   SCN_LAUNCHED();
   return 0;
@@ -359,14 +367,14 @@ int scn_quantize_points(const double *xyz, int64_t n, double scale, const int64_
   SCN_CUDA(cudaMemcpyAsync(mn, big, 24, cudaMemcpyHostToDevice, s));
   int gb = cdiv(n, 256);
   if (gb > num_sms() * 4) gb = num_sms() * 4;
-  k_quant_min<<<gb, 256, 0, s>>>(xyz, n, scale, mn);
+  SCN_LAUNCH(k_quant_min, gb, 256, 0, s, xyz, n, scale, mn);
   SCN_LAUNCHED();
   Full3 f;
   for (int d = 0; d < 3; ++d) f.v[d] = full_scale[d];
-  k_quant_flag<<<cdiv(n, 256), 256, 0, s>>>(xyz, n, scale, mn, f, keep_out, pos);
+  SCN_LAUNCH(k_quant_flag, cdiv(n, 256), 256, 0, s, xyz, n, scale, mn, f, keep_out, pos);
   SCN_LAUNCHED();
   SCN_TRY(exclusive_scan_i32(pos, pos, n, s));
-  k_quant_emit<<<cdiv(n, 256), 256, 0, s>>>(xyz, n, scale, mn, pos, batch_idx, coords_out);
+  SCN_LAUNCH(k_quant_emit, cdiv(n, 256), 256, 0, s, xyz, n, scale, mn, pos, batch_idx, coords_out);
   SCN_LAUNCHED();
   int32_t *h32 = (int32_t *)host_scratch(16);
   SCN_CUDA(cudaMemcpyAsync(h32, pos + n, 4, cudaMemcpyDeviceToHost, s));
@@ -396,15 +404,15 @@ int scn_voxelize_batch(const float *points, int64_t n, int64_t n_cols, const int
   int32_t *pos = nullptr;
   SCN_TRY(dev_alloc_t(&mn, (size_t)n_buildings * 3, s));
   SCN_TRY(dev_alloc_t(&pos, (size_t)n + 1, s));
-  k_fill_double<<<cdiv(n_buildings * 3, 256), 256, 0, s>>>(mn, 1e300, n_buildings * 3);
+  SCN_LAUNCH(k_fill_double, cdiv(n_buildings * 3, 256), 256, 0, s, mn, 1e300, n_buildings * 3);
   SCN_LAUNCHED();
   const int C = (int)n_cols, B = (int)n_buildings;
-  k_vox_min<<<cdiv(n, VOX_PER_BLOCK), 256, 0, s>>>(points, C, n, first_dev, B, v, mn);
+  SCN_LAUNCH(k_vox_min, cdiv(n, VOX_PER_BLOCK), 256, 0, s, points, C, n, first_dev, B, v, mn);
   SCN_LAUNCHED();
-  k_vox_flag<<<cdiv(n, 256), 256, 0, s>>>(points, C, n, first_dev, B, v, mn, pos);
+  SCN_LAUNCH(k_vox_flag, cdiv(n, 256), 256, 0, s, points, C, n, first_dev, B, v, mn, pos);
   SCN_LAUNCHED();
   SCN_TRY(exclusive_scan_i32(pos, pos, n, s));
-  k_vox_emit<<<cdiv(n, 256), 256, 0, s>>>(points, C, n, first_dev, B, v, mn, pos, coords_out, feats_out, xyz_feature);
+  SCN_LAUNCH(k_vox_emit, cdiv(n, 256), 256, 0, s, points, C, n, first_dev, B, v, mn, pos, coords_out, feats_out, xyz_feature);
   SCN_LAUNCHED();
   int32_t *h32 = (int32_t *)host_scratch(16);
   SCN_CUDA(cudaMemcpyAsync(h32, pos + n, 4, cudaMemcpyDeviceToHost, s));

@@ -98,6 +98,7 @@ static void metadata_clear(scn_metadata *m, cudaStream_t s) {
 __global__ void k_in_insert(const int64_t *__restrict__ coords, long long n, int ncols,
                             uint64_t *hk, int32_t *hv, uint32_t mask, int32_t *pslot,
                             int32_t *stat, int take_max) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t *c = coords + i * ncols;
@@ -119,6 +120,7 @@ __global__ void k_in_insert(const int64_t *__restrict__ coords, long long n, int
 
 __global__ void k_in_flag(const int32_t *__restrict__ pslot, const int32_t *__restrict__ hv,
                           int32_t *__restrict__ flag, long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[i] = (hv[pslot[i]] == (int)i) ? 1 : 0;
 }
@@ -127,6 +129,7 @@ __global__ void k_in_flag(const int32_t *__restrict__ pslot, const int32_t *__re
 __global__ void k_in_assign(const int64_t *__restrict__ coords, long long n, int ncols,
                             const int32_t *__restrict__ rank, const int32_t *__restrict__ pslot,
                             int32_t *hv, int32_t *__restrict__ site_coords) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int r = rank[i];
@@ -139,6 +142,7 @@ __global__ void k_in_assign(const int64_t *__restrict__ coords, long long n, int
 
 __global__ void k_in_rows(const int32_t *__restrict__ pslot, const int32_t *__restrict__ hv,
                           int32_t *__restrict__ prow, int32_t *cnt, long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int r = hv[pslot[i]];
@@ -148,6 +152,7 @@ __global__ void k_in_rows(const int32_t *__restrict__ pslot, const int32_t *__re
 
 __global__ void k_in_fill(const int32_t *__restrict__ prow, const int32_t *__restrict__ csr_off,
                           int32_t *cursor, int32_t *__restrict__ members, long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int r = prow[i];
@@ -159,6 +164,7 @@ __global__ void k_in_fill(const int32_t *__restrict__ prow, const int32_t *__res
 // ascending point order (IOLayersRules.h:92) - restore that (lists are 1-3 long in practice)
 __global__ void k_in_sort_members(const int32_t *__restrict__ csr_off, int32_t *members,
                                   long long n_rows, int32_t *max_active) {
+  pdl_sync();
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const int b = csr_off[r], e = csr_off[r + 1];
@@ -172,12 +178,14 @@ __global__ void k_in_sort_members(const int32_t *__restrict__ csr_off, int32_t *
 }
 
 __global__ void k_iota(int32_t *a, long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = (int)i;
 }
 
 __global__ void k_in_mode0(const int64_t *__restrict__ coords, long long n, int ncols,
                            int32_t *__restrict__ site_coords) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t *c = coords + i * ncols;
@@ -226,7 +234,7 @@ static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t
   SCN_CUDA(cudaMemsetAsync(stat, 0, 32, s));
   SCN_TRY(grid_alloc_table(g, n, mode == 0 ? 0x80 : 0x7F, s));
   const int T = 256, nb = cdiv(n, T);
-  k_in_insert<<<nb, T, 0, s>>>(dcoords, n, ncols, g->hkeys, g->hvals, g->hcap - 1, pslot, stat,
+  SCN_LAUNCH(k_in_insert, nb, T, 0, s, dcoords, n, ncols, g->hkeys, g->hvals, g->hcap - 1, pslot, stat,
                                mode == 0);
   SCN_LAUNCHED();
   int64_t *hs = host_scratch(16);
@@ -239,22 +247,22 @@ static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t
     SCN_CHECK(hs32[0] == 0, "InputLayer: coordinate outside [0,65535] or batch outside [0,32767]");
     g->n_active = n;
     SCN_TRY(dev_alloc_t(&g->coords, (size_t)n * 4, s));
-    k_in_mode0<<<nb, T, 0, s>>>(dcoords, n, ncols, g->coords);
+    SCN_LAUNCH(k_in_mode0, nb, T, 0, s, dcoords, n, ncols, g->coords);
     SCN_LAUNCHED();
     SCN_TRY(dev_alloc_t(&ir.point_row, (size_t)n, s));
     SCN_TRY(dev_alloc_t(&ir.members, (size_t)n, s));
     SCN_TRY(dev_alloc_t(&ir.csr_off, (size_t)n + 1, s));
-    k_iota<<<nb, T, 0, s>>>(ir.point_row, n);
+    SCN_LAUNCH(k_iota, nb, T, 0, s, ir.point_row, n);
     SCN_LAUNCHED();
-    k_iota<<<nb, T, 0, s>>>(ir.members, n);
+    SCN_LAUNCH(k_iota, nb, T, 0, s, ir.members, n);
     SCN_LAUNCHED();
-    k_iota<<<cdiv(n + 1, T), T, 0, s>>>(ir.csr_off, n + 1);
+    SCN_LAUNCH(k_iota, cdiv(n + 1, T), T, 0, s, ir.csr_off, n + 1);
     SCN_LAUNCHED();
     ir.n_active = n;
     ir.max_active = 1;
   } else {
     SCN_TRY(dev_alloc_t(&rank, (size_t)n + 1, s));
-    k_in_flag<<<nb, T, 0, s>>>(pslot, g->hvals, rank, n);
+    SCN_LAUNCH(k_in_flag, nb, T, 0, s, pslot, g->hvals, rank, n);
     SCN_LAUNCHED();
     SCN_TRY(exclusive_scan_i32(rank, rank, n, s));
     SCN_CUDA(cudaMemcpyAsync(hs32, stat, 16, cudaMemcpyDeviceToHost, s));
@@ -265,7 +273,7 @@ static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t
     g->n_active = na;
     ir.n_active = na;
     SCN_TRY(dev_alloc_t(&g->coords, (size_t)na * 4, s));
-    k_in_assign<<<nb, T, 0, s>>>(dcoords, n, ncols, rank, pslot, g->hvals, g->coords);
+    SCN_LAUNCH(k_in_assign, nb, T, 0, s, dcoords, n, ncols, rank, pslot, g->hvals, g->coords);
     SCN_LAUNCHED();
     int32_t *cnt = nullptr;
     SCN_TRY(dev_alloc_t(&ir.point_row, (size_t)n, s));
@@ -273,14 +281,14 @@ static int input_layer_prepare(scn_metadata *m, const int64_t *ss, const int64_t
     SCN_TRY(dev_alloc_t(&ir.members, (size_t)n, s));
     SCN_TRY(dev_alloc_t(&cnt, (size_t)na + 2, s));
     SCN_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)na + 2) * 4, s));
-    k_in_rows<<<nb, T, 0, s>>>(pslot, g->hvals, ir.point_row, cnt, n);
+    SCN_LAUNCH(k_in_rows, nb, T, 0, s, pslot, g->hvals, ir.point_row, cnt, n);
     SCN_LAUNCHED();
     SCN_TRY(exclusive_scan_i32(cnt, ir.csr_off, na, s));
     SCN_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)na + 2) * 4, s));
-    k_in_fill<<<nb, T, 0, s>>>(ir.point_row, ir.csr_off, cnt, ir.members, n);
+    SCN_LAUNCH(k_in_fill, nb, T, 0, s, ir.point_row, ir.csr_off, cnt, ir.members, n);
     SCN_LAUNCHED();
     int32_t *mx = cnt + na + 1;  // zeroed above, untouched by k_in_fill
-    k_in_sort_members<<<cdiv(na, T), T, 0, s>>>(ir.csr_off, ir.members, na, mx);
+    SCN_LAUNCH(k_in_sort_members, cdiv(na, T), T, 0, s, ir.csr_off, ir.members, na, mx);
     SCN_LAUNCHED();
     SCN_CUDA(cudaMemcpyAsync(stat + 4, mx, 4, cudaMemcpyDeviceToDevice, s));
     ir.max_active = -1;  // stat[4] on the device; fetched lazily (scn_input_rulebook_header)
@@ -308,6 +316,7 @@ struct Filter3 { int size[3]; int stride[3]; int out_size[3]; };
 __global__ void k_sub_table(const int32_t *__restrict__ coords, long long n, Filter3 f, int K,
                             const uint64_t *__restrict__ hk, const int32_t *__restrict__ hv,
                             uint32_t mask, int32_t *__restrict__ T) {
+  pdl_sync();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * K) return;
   const int k = (int)(idx / n);
@@ -324,12 +333,14 @@ __global__ void k_sub_table(const int32_t *__restrict__ coords, long long n, Fil
 // meta[k] = first pair of offset k, meta[K] = total pairs
 __global__ void k_pair_offsets(const int32_t *__restrict__ pos, long long n, int K,
                                int32_t *__restrict__ meta) {
+  pdl_sync();
   int k = threadIdx.x;
   if (k <= K) meta[k] = pos[(long long)k * n];
 }
 
 __global__ void k_emit_pairs(const int32_t *__restrict__ T, const int32_t *__restrict__ pos,
                              long long n, long long total, int32_t *__restrict__ pairs) {
+  pdl_sync();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int t = T[idx];
@@ -341,6 +352,7 @@ __global__ void k_emit_pairs(const int32_t *__restrict__ T, const int32_t *__res
 // T_in[k*n_in + in] = out for every pair (each in row occurs at most once per offset)
 __global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t *__restrict__ poff,
                                int K, long long n_in, int32_t *__restrict__ t_in) {
+  pdl_sync();
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= poff[K]) return;
   int k = 0;
@@ -361,6 +373,7 @@ __global__ void k_scatter_t_in(const int32_t *__restrict__ pairs, const int32_t 
 __global__ void k_row_masks(const int32_t *__restrict__ T, long long n, int K,
                             uint32_t *__restrict__ mask, uint32_t *__restrict__ key,
                             int32_t *__restrict__ idx, int key_shift, const int32_t *__restrict__ pair_off) {
+  pdl_sync();
   __shared__ int s_cnt[MAX_K], s_rank[MAX_K];
   if (pair_off) {
     if (threadIdx.x < K) s_cnt[threadIdx.x] = pair_off[threadIdx.x + 1] - pair_off[threadIdx.x];
@@ -391,6 +404,7 @@ __global__ void __launch_bounds__(TILE_M)
 k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ sorted_idx,
              long long n, int32_t *__restrict__ perm, uint32_t *__restrict__ tile_mask,
              int32_t *__restrict__ tile_pop) {
+  pdl_sync();
   __shared__ uint32_t wm[TILE_M / 32];
   const long long slot = (long long)blockIdx.x * TILE_M + threadIdx.x;
   uint32_t m = 0;
@@ -415,6 +429,7 @@ k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ 
 __global__ void __launch_bounds__(1024)
 k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restrict__ order,
              int32_t *__restrict__ n_entries, int32_t *__restrict__ tile_off) {
+  pdl_sync();
   __shared__ int cnt[40], base[40];
   __shared__ int wsum[32];
   __shared__ int carry;
@@ -466,6 +481,7 @@ __global__ void __launch_bounds__(TILE_M)
 k_fill_entries(const int32_t *__restrict__ T, long long n, const int32_t *__restrict__ perm,
                const uint32_t *__restrict__ tile_mask, const int32_t *__restrict__ tile_off,
                int32_t *__restrict__ entries) {
+  pdl_sync();
   const int row = perm[(long long)blockIdx.x * TILE_M + threadIdx.x];
   uint32_t m = tile_mask[blockIdx.x];
   long long e = tile_off[blockIdx.x];
@@ -498,7 +514,7 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   // agree on them end up adjacent; the low offsets are left unsorted inside such a group
   static const int sort_bits = getenv("SCN_B200_SORT_BITS") ? atoi(getenv("SCN_B200_SORT_BITS")) : 27;
   const int kbits = K < sort_bits ? K : sort_bits;
-  k_row_masks<<<cdiv(n_rows, 256), 256, 0, s>>>(T, n_rows, K, mask, key, idx, K - kbits, pair_off);
+  SCN_LAUNCH(k_row_masks, cdiv(n_rows, 256), 256, 0, s, T, n_rows, K, mask, key, idx, K - kbits, pair_off);
   SCN_LAUNCHED();
   // (books of at most 4 tiles keep the natural row order: nothing to group, and the sort is ~15 launches)
   if (g_tile_grouping && K > 1 && n_rows > 4 * TILE_M) SCN_TRY(radix_sort_pairs(key, idx, n_rows, kbits, s, false));
@@ -506,10 +522,10 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
   SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
   SCN_TRY(dev_alloc_t(&pop, (size_t)tb.n_tiles + 1, s));
-  k_tile_masks<<<tb.n_tiles, TILE_M, 0, s>>>(mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
+  SCN_LAUNCH(k_tile_masks, tb.n_tiles, TILE_M, 0, s, mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
   SCN_LAUNCHED();
   SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles, s));
-  k_tile_order<<<1, 1024, 0, s>>>(pop, tb.n_tiles, tb.order, meta_slot, tb.tile_off);
+  SCN_LAUNCH(k_tile_order, 1, 1024, 0, s, pop, tb.n_tiles, tb.order, meta_slot, tb.tile_off);
   SCN_LAUNCHED();
   dev_free(mask, s);
   dev_free(key, s);
@@ -522,7 +538,7 @@ static int tilebook_phase2(TileBook &tb, const int32_t *T, int64_t n_entries, cu
   tb.n_entries = n_entries;
   SCN_TRY(dev_alloc_t(&tb.entries, (size_t)n_entries * TILE_M, s));
   if (tb.n_tiles > 0 && n_entries > 0) {
-    k_fill_entries<<<tb.n_tiles, TILE_M, 0, s>>>(T, tb.n_rows, tb.perm, tb.tile_mask, tb.tile_off,
+    SCN_LAUNCH(k_fill_entries, tb.n_tiles, TILE_M, 0, s, T, tb.n_rows, tb.perm, tb.tile_mask, tb.tile_off,
                                                  tb.entries);
     SCN_LAUNCHED();
   }
@@ -567,7 +583,7 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   SCN_TRY(dev_alloc_t(&pos, (size_t)total + 1, s));
   SCN_TRY(dev_alloc_t(&meta, (size_t)K + 8 + 2 * G, s));
   SCN_TRY(exclusive_scan_flags_i32(rb->t_out, pos, total, s));   // pos[i] = present partners before table entry i
-  k_pair_offsets<<<1, MAX_KT + 32, 0, s>>>(pos, n, K, meta);
+  SCN_LAUNCH(k_pair_offsets, 1, MAX_KT + 32, 0, s, pos, n, K, meta);
   SCN_LAUNCHED();
   SCN_TRY(tilebook_chain_phase1(rb->tb_out, rb->t_out, K, rb->n_out, rb->n_in, meta + K + 1, s, meta));
   // strided rulebooks also carry the in-stationary lists (conv dX, deconv forward); building them
@@ -583,7 +599,7 @@ static int finish_rulebook(RuleBook *rb, cudaStream_t s) {
   rb->total_pairs = h32[K];
   SCN_TRY(dev_alloc_t(&rb->pairs, (size_t)rb->total_pairs * 2, s));
   if (total > 0) {
-    k_emit_pairs<<<cdiv(total, 256), 256, 0, s>>>(rb->t_out, pos, n, total, rb->pairs);
+    SCN_LAUNCH(k_emit_pairs, cdiv(total, 256), 256, 0, s, rb->t_out, pos, n, total, rb->pairs);
     SCN_LAUNCHED();
   }
   SCN_TRY(tilebook_chain_phase2(rb->tb_out, rb->t_out, h32 + K + 1, rb->total_pairs, s));
@@ -606,7 +622,7 @@ static int build_t_in(RuleBook *rb, cudaStream_t s) {
     for (int k = 0; k <= rb->K; ++k) h[k] = (int32_t)rb->pair_off[k];
     // pageable source: the copy is staged before return, so the stack array may die
     SCN_CUDA(cudaMemcpyAsync(poff, h, (size_t)(rb->K + 1) * 4, cudaMemcpyHostToDevice, s));
-    k_scatter_t_in<<<cdiv(rb->total_pairs, 256), 256, 0, s>>>(rb->pairs, poff, rb->K, rb->n_in,
+    SCN_LAUNCH(k_scatter_t_in, cdiv(rb->total_pairs, 256), 256, 0, s, rb->pairs, poff, rb->K, rb->n_in,
                                                              rb->t_in);
     SCN_LAUNCHED();
     dev_free(poff, s);
@@ -742,7 +758,7 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
   if (total > 0) {
     Filter3 f;
     for (int d = 0; d < 3; ++d) { f.size[d] = (int)filter[d]; f.stride[d] = 1; f.out_size[d] = (int)ss[d]; }
-    k_sub_table<<<cdiv(total, 256), 256, 0, s>>>(g->coords, g->n_active, f, rb->K, g->hkeys,
+    SCN_LAUNCH(k_sub_table, cdiv(total, 256), 256, 0, s, g->coords, g->n_active, f, rb->K, g->hkeys,
                                                  g->hvals, g->hcap - 1, rb->t_out);
     SCN_LAUNCHED();
   }
@@ -786,6 +802,7 @@ struct R3s { int v[3]; };
 __global__ void k_conv_insert(const int32_t *__restrict__ coords, long long n_in, Filter3 f,
                               R3s R3, int R, uint64_t *hk, int32_t *hv, uint32_t mask,
                               int32_t *__restrict__ pslot) {
+  pdl_sync();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_in * R) return;
   const long long i = idx / R;
@@ -801,6 +818,7 @@ __global__ void k_conv_insert(const int32_t *__restrict__ coords, long long n_in
 
 __global__ void k_conv_flag(const int32_t *__restrict__ pslot, const int32_t *__restrict__ hv,
                             int32_t *__restrict__ flag, long long total) {
+  pdl_sync();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int sl = pslot[idx];
@@ -811,6 +829,7 @@ __global__ void k_conv_assign(const int32_t *__restrict__ coords, long long n_in
                               R3s R3, int R, const int32_t *__restrict__ rank,
                               const int32_t *__restrict__ pslot, int32_t *hv,
                               int32_t *__restrict__ out_coords) {
+  pdl_sync();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_in * R) return;
   const int r0 = rank[idx];
@@ -828,11 +847,13 @@ __global__ void k_conv_assign(const int32_t *__restrict__ coords, long long n_in
 // relabel rows by a permutation new_of_old (batch-contiguity fix-up)
 __global__ void k_relabel_table(int32_t *hv, uint32_t cap, const uint64_t *__restrict__ hk,
                                 const int32_t *__restrict__ new_of_old) {
+  pdl_sync();
   uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x;
   if (sl < cap && hk[sl] != EMPTY_KEY) hv[sl] = new_of_old[hv[sl]];
 }
 __global__ void k_batch_keys(const int32_t *__restrict__ coords, long long n,
                              uint32_t *__restrict__ key, int32_t *__restrict__ idx) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   key[i] = (uint32_t)coords[i * 4 + 3];
@@ -841,6 +862,7 @@ __global__ void k_batch_keys(const int32_t *__restrict__ coords, long long n,
 __global__ void k_permute_coords(const int32_t *__restrict__ src, const int32_t *__restrict__ old_of_new,
                                  int32_t *__restrict__ dst, int32_t *__restrict__ new_of_old,
                                  long long n) {
+  pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int o = old_of_new[i];
@@ -852,6 +874,7 @@ __global__ void k_conv_tables(const int32_t *__restrict__ coords, long long n_in
                               Filter3 f, R3s R3, int R, const int32_t *__restrict__ pslot,
                               const int32_t *__restrict__ hv, int32_t *__restrict__ t_out,
                               int32_t *__restrict__ t_in) {
+  pdl_sync();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_in * R) return;
   const int sl = pslot[idx];
@@ -920,10 +943,10 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   SCN_TRY(dev_alloc_t(&rank, (size_t)total + 1, s));
   int64_t n_out = 0;
   if (total > 0) {
-    k_conv_insert<<<cdiv(total, 256), 256, 0, s>>>(gi->coords, n_in, f, R3, R, go->hkeys,
+    SCN_LAUNCH(k_conv_insert, cdiv(total, 256), 256, 0, s, gi->coords, n_in, f, R3, R, go->hkeys,
                                                    go->hvals, go->hcap - 1, pslot);
     SCN_LAUNCHED();
-    k_conv_flag<<<cdiv(total, 256), 256, 0, s>>>(pslot, go->hvals, rank, total);
+    SCN_LAUNCH(k_conv_flag, cdiv(total, 256), 256, 0, s, pslot, go->hvals, rank, total);
     SCN_LAUNCHED();
     SCN_TRY(exclusive_scan_i32(rank, rank, total, s));
     int32_t *h32 = (int32_t *)host_scratch(16);
@@ -935,7 +958,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   rb->n_out = n_out;
   SCN_TRY(dev_alloc_t(&go->coords, (size_t)n_out * 4, s));
   if (total > 0) {
-    k_conv_assign<<<cdiv(total, 256), 256, 0, s>>>(gi->coords, n_in, f, R3, R, rank, pslot,
+    SCN_LAUNCH(k_conv_assign, cdiv(total, 256), 256, 0, s, gi->coords, n_in, f, R3, R, rank, pslot,
                                                    go->hvals, go->coords);
     SCN_LAUNCHED();
   }
@@ -948,12 +971,12 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
     SCN_TRY(dev_alloc_t(&old_of_new, (size_t)n_out, s));
     SCN_TRY(dev_alloc_t(&new_of_old, (size_t)n_out, s));
     SCN_TRY(dev_alloc_t(&c2, (size_t)n_out * 4, s));
-    k_batch_keys<<<cdiv(n_out, 256), 256, 0, s>>>(go->coords, n_out, bk, old_of_new);
+    SCN_LAUNCH(k_batch_keys, cdiv(n_out, 256), 256, 0, s, go->coords, n_out, bk, old_of_new);
     SCN_LAUNCHED();
     SCN_TRY(radix_sort_pairs(bk, old_of_new, n_out, 16, s));
-    k_permute_coords<<<cdiv(n_out, 256), 256, 0, s>>>(go->coords, old_of_new, c2, new_of_old, n_out);
+    SCN_LAUNCH(k_permute_coords, cdiv(n_out, 256), 256, 0, s, go->coords, old_of_new, c2, new_of_old, n_out);
     SCN_LAUNCHED();
-    k_relabel_table<<<cdiv(go->hcap, 256), 256, 0, s>>>(go->hvals, go->hcap, go->hkeys, new_of_old);
+    SCN_LAUNCH(k_relabel_table, cdiv(go->hcap, 256), 256, 0, s, go->hvals, go->hcap, go->hkeys, new_of_old);
     SCN_LAUNCHED();
     dev_free(go->coords, s);
     go->coords = c2;
@@ -968,7 +991,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   SCN_CUDA(cudaMemsetAsync(rb->t_out, 0xFF, (size_t)(t_out_n ? t_out_n : 1) * 4, s));
   SCN_CUDA(cudaMemsetAsync(rb->t_in, 0xFF, (size_t)(t_in_n ? t_in_n : 1) * 4, s));
   if (total > 0) {
-    k_conv_tables<<<cdiv(total, 256), 256, 0, s>>>(gi->coords, n_in, n_out, f, R3, R, pslot,
+    SCN_LAUNCH(k_conv_tables, cdiv(total, 256), 256, 0, s, gi->coords, n_in, n_out, f, R3, R, pslot,
                                                    go->hvals, rb->t_out, rb->t_in);
     SCN_LAUNCHED();
   }

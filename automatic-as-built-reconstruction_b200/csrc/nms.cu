@@ -144,6 +144,7 @@ __device__ float rotate_iou_eval(const float *r1, const float *r2, int criterion
 // iou[n * K + k] = rotate_iou_eval(query[k], boxes[n])   (rotate_iou_kernel_eval, :626-664)
 __global__ void k_rotate_iou(const float *__restrict__ boxes, const float *__restrict__ query, long long N, long long K,
                              int criterion, float *__restrict__ iou) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   const long long n = i / K, k = i - n * K;
@@ -156,6 +157,7 @@ __global__ void k_rotate_iou(const float *__restrict__ boxes, const float *__res
 // ---- NMS ---------------------------------------------------------------------------------------------------
 // key = score as an order-preserving uint32, inverted so that an ascending sort is descending in score
 __global__ void k_score_keys(const float *__restrict__ scores, long long n, uint32_t *__restrict__ key, int32_t *__restrict__ idx) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t u = __float_as_uint(scores[i]);
@@ -165,6 +167,7 @@ __global__ void k_score_keys(const float *__restrict__ scores, long long n, uint
 }
 __global__ void k_gather_boxes(const float *__restrict__ boxes, const int32_t *__restrict__ order, long long m,
                                float *__restrict__ sorted) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m * 5) return;
   sorted[i] = boxes[(long long)order[i / 5] * 5 + i % 5];
@@ -172,6 +175,7 @@ __global__ void k_gather_boxes(const float *__restrict__ boxes, const int32_t *_
 // mask[i * col_blocks + cb] bit t: sorted box i suppresses sorted box cb * 64 + t (t after i)
 __global__ void __launch_bounds__(64)
 k_nms_mask(const float *__restrict__ sorted, int m, float thresh, unsigned long long *__restrict__ mask) {
+  pdl_sync();
   __shared__ float cb[64 * 5];
   const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64, tx = threadIdx.x;
   if (col0 < row0) return;                                 // only the upper triangle is ever read
@@ -195,6 +199,7 @@ k_nms_mask(const float *__restrict__ sorted, int m, float thresh, unsigned long 
 __global__ void __launch_bounds__(32)
 k_nms_scan(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order, int m, int col_blocks,
            int post_max, int64_t *__restrict__ keep, int32_t *__restrict__ n_keep) {
+  pdl_sync();
   extern __shared__ unsigned long long remv[];              // [col_blocks]
   const int lane = threadIdx.x;
   for (int j = lane; j < col_blocks; j += 32) remv[j] = 0ull;
@@ -222,7 +227,7 @@ int scn_rotate_iou(const float *boxes, int64_t n_boxes, const float *query, int6
   cudaStream_t s = (cudaStream_t)stream;
   if (n_boxes == 0 || n_query == 0) return 0;
   SCN_CHECK(boxes && query && iou_out, "null pointer");
-  k_rotate_iou<<<cdiv(n_boxes * n_query, 128), 128, 0, s>>>(boxes, query, n_boxes, n_query, criterion, iou_out);
+  SCN_LAUNCH(k_rotate_iou, cdiv(n_boxes * n_query, 128), 128, 0, s, boxes, query, n_boxes, n_query, criterion, iou_out);
   SCN_LAUNCHED();
   return 0;
 }
@@ -247,15 +252,15 @@ int scn_rotate_nms(const float *boxes, const float *scores, int64_t n, float iou
   SCN_TRY(dev_alloc_t(&cnt, 4, s));
   SCN_TRY(dev_alloc_t(&sorted, (size_t)m * 5, s));
   SCN_TRY(dev_alloc_t(&mask, (size_t)m * col_blocks, s));
-  k_score_keys<<<cdiv(n, 256), 256, 0, s>>>(scores, n, key, order);
+  SCN_LAUNCH(k_score_keys, cdiv(n, 256), 256, 0, s, scores, n, key, order);
   SCN_LAUNCHED();
   SCN_TRY(radix_sort_pairs(key, order, n, 32, s, false));         // stable: equal scores keep their input order
-  k_gather_boxes<<<cdiv((long long)m * 5, 256), 256, 0, s>>>(boxes, order, m, sorted);
+  SCN_LAUNCH(k_gather_boxes, cdiv((long long)m * 5, 256), 256, 0, s, boxes, order, m, sorted);
   SCN_LAUNCHED();
   SCN_CUDA(cudaMemsetAsync(mask, 0, (size_t)m * col_blocks * 8, s));
-  k_nms_mask<<<dim3(col_blocks, col_blocks), 64, 0, s>>>(sorted, m, iou_threshold, mask);
+  SCN_LAUNCH(k_nms_mask, dim3(col_blocks, col_blocks), 64, 0, s, sorted, m, iou_threshold, mask);
   SCN_LAUNCHED();
-  k_nms_scan<<<1, 32, (size_t)col_blocks * 8, s>>>(mask, order, m, col_blocks, post, keep_out, cnt);
+  SCN_LAUNCH(k_nms_scan, 1, 32, (size_t)col_blocks * 8, s, mask, order, m, col_blocks, post, keep_out, cnt);
   SCN_LAUNCHED();
   int32_t *h32 = (int32_t *)host_scratch(16);
   SCN_CUDA(cudaMemcpyAsync(h32, cnt, 4, cudaMemcpyDeviceToHost, s));

@@ -28,6 +28,7 @@ constexpr int ROI_WARPS = 8;
 
 // ext[d] = max active coordinate + 1 per axis (tools_3d_2d.py:16-18), ext[3] = max batch index + 1
 __global__ void k_coord_extent(const int32_t *__restrict__ coords, long long n, int32_t *__restrict__ ext) {
+  pdl_sync();
   int4 m = make_int4(0, 0, 0, 0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int4 c = reinterpret_cast<const int4 *>(coords)[i];
@@ -99,6 +100,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(ROI_WARPS * 32)
 k_roi_align(RoiArgs a, float *__restrict__ out /* FWD: output; BWD: feature gradient */,
             const float *__restrict__ dout) {
+  pdl_sync();
   extern __shared__ float tile[];                 // [ROI_BINS][C + 1]
   const int n = blockIdx.x, bin0 = blockIdx.y * ROI_BINS;
   const int bins = a.PH * a.PW * a.PZ, C = a.C, ldt = C + 1;
@@ -217,7 +219,7 @@ static int roi_setup(scn_metadata_t *m, const int64_t *ss, const float *rois, in
   if (g->n_active > 0) {
     int blocks = cdiv(g->n_active, 256);
     if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-    k_coord_extent<<<blocks, 256, 0, s>>>(g->coords, g->n_active, *ext);
+    SCN_LAUNCH(k_coord_extent, blocks, 256, 0, s, g->coords, g->n_active, *ext);
     SCN_LAUNCHED();
   }
   a->rois = rois; a->ext = *ext; a->hk = g->hkeys; a->hv = g->hvals; a->hmask = g->hcap - 1;
@@ -247,7 +249,7 @@ int scn_roi_align_rotated_3d_forward(scn_metadata_t *m, const int64_t *ss, const
     attr = true;
   }
   prof_begin(PROF_IO, s);
-  k_roi_align<false><<<dim3((unsigned)n_rois, cdiv(bins, ROI_BINS)), ROI_WARPS * 32, sm, s>>>(a, out, nullptr);
+  SCN_LAUNCH((k_roi_align<false>), dim3((unsigned)n_rois, cdiv(bins, ROI_BINS)), ROI_WARPS * 32, sm, s, a, out, nullptr);
   SCN_LAUNCHED();
   prof_end(PROF_IO, s, 4.0 * ((double)g->n_active * a.C + (double)n_rois * a.C * bins) + 32.0 * n_rois, 0);
   dev_free(ext, s);
@@ -280,7 +282,7 @@ int scn_roi_align_rotated_3d_backward(scn_metadata_t *m, const int64_t *ss, cons
     attr = true;
   }
   prof_begin(PROF_IO, s);
-  k_roi_align<true><<<dim3((unsigned)n_rois, cdiv(bins, ROI_BINS)), ROI_WARPS * 32, sm, s>>>(a, d_feats, d_out);
+  SCN_LAUNCH((k_roi_align<true>), dim3((unsigned)n_rois, cdiv(bins, ROI_BINS)), ROI_WARPS * 32, sm, s, a, d_feats, d_out);
   SCN_LAUNCHED();
   prof_end(PROF_IO, s, 4.0 * ((double)g->n_active * a.C + (double)n_rois * a.C * bins) + 32.0 * n_rois, 0);
   dev_free(ext, s);

@@ -25,6 +25,7 @@ namespace scn {
 struct Stride3 { float v[3]; };
 __global__ void k_grid_anchors(const int32_t *__restrict__ coords, long long n, const float *__restrict__ base, int A,
                                float voxel_scale, Stride3 st, float *__restrict__ out) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over n * A * 7
   if (i >= n * A * 7) return;
   const int j = (int)(i % 7);
@@ -37,6 +38,7 @@ __global__ void k_grid_anchors(const int32_t *__restrict__ coords, long long n, 
 }
 // scope[b] = {first row of sample b, one past its last row} * A  (rows are batch-contiguous ascending)
 __global__ void k_example_scope(const int32_t *__restrict__ coords, long long n, int B, int A, int64_t *__restrict__ scope) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   auto lower = [&](int v) {          // first row with batch >= v
@@ -52,15 +54,18 @@ __global__ void k_example_scope(const int32_t *__restrict__ coords, long long n,
 }
 
 __global__ void k_relu_inplace(float *__restrict__ x, long long n) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] = fmaxf(x[i], 0.f);
 }
 // d *= (y > 0)   (gradient of ReLU from its output)
 __global__ void k_relu_mask(float *__restrict__ d, const float *__restrict__ y, long long n) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (!(y[i] > 0.f)) d[i] = 0.f;
 }
 __global__ void k_add_inplace(float *__restrict__ y, const float *__restrict__ t, long long n) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] += t[i];
 }
@@ -105,12 +110,12 @@ int scn_grid_anchors(scn_metadata_t *m, const int64_t *ss, const float *base_anc
   if (total > 0) {
     SCN_CHECK(base_anchors && anchors_out, "null pointer");
     Stride3 st{{stride[0], stride[1], stride[2]}};
-    k_grid_anchors<<<cdiv(total, 256), 256, 0, s>>>(g->coords, g->n_active, base_anchors, (int)n_anchors, voxel_scale, st,
+    SCN_LAUNCH(k_grid_anchors, cdiv(total, 256), 256, 0, s, g->coords, g->n_active, base_anchors, (int)n_anchors, voxel_scale, st,
                                                    anchors_out);
     SCN_LAUNCHED();
   }
   if (scope_out && batch_size > 0) {
-    k_example_scope<<<cdiv(batch_size, 128), 128, 0, s>>>(g->coords, g->n_active, (int)batch_size, (int)n_anchors, scope_out);
+    SCN_LAUNCH(k_example_scope, cdiv(batch_size, 128), 128, 0, s, g->coords, g->n_active, (int)batch_size, (int)n_anchors, scope_out);
     SCN_LAUNCHED();
   }
   return 0;
@@ -126,7 +131,7 @@ int scn_rpn_head_forward(const float *x, int64_t n, int64_t C, const float *w_co
   SCN_CHECK(x && w_conv && w_cls && w_box && hidden && logits && reg, "null pointer");
   const TileBook tb = identity_book(n);
   SCN_TRY(osgemm(x, w_conv, b_conv, hidden, (int)C, (int)C, tb, precision, /*transpose_w=*/1, s));
-  k_relu_inplace<<<ew_grid(n * C), 256, 0, s>>>(hidden, n * C);
+  SCN_LAUNCH(k_relu_inplace, ew_grid(n * C), 256, 0, s, hidden, n * C);
   SCN_LAUNCHED();
   SCN_TRY(osgemm(hidden, w_cls, b_cls, logits, (int)C, (int)n_cls, tb, precision, 1, s));
   SCN_TRY(osgemm(hidden, w_box, b_box, reg, (int)C, (int)n_box, tb, precision, 1, s));
@@ -157,14 +162,14 @@ int scn_rpn_head_backward(const float *x, const float *hidden, int64_t n, int64_
   SCN_TRY(workspace_t(&part, WS_CHAIN, (size_t)n * C, s));
   SCN_TRY(osgemm(d_logits, w_cls, nullptr, d_hidden, (int)n_cls, (int)C, tb, precision, 0, s));
   SCN_TRY(osgemm(d_reg, w_box, nullptr, part, (int)n_box, (int)C, tb, precision, 0, s));
-  k_add_inplace<<<ew_grid(n * C), 256, 0, s>>>(d_hidden, part, n * C);
+  SCN_LAUNCH(k_add_inplace, ew_grid(n * C), 256, 0, s, d_hidden, part, n * C);
   SCN_LAUNCHED();
   // head weights: dW [Cout, Cin] = d_out^T hidden
   if (dw_cls) SCN_TRY(weight_grad(d_logits, hidden, dw_cls, (int)n_cls, (int)C, &rb, 0, 1, precision, s));
   if (dw_box) SCN_TRY(weight_grad(d_reg, hidden, dw_box, (int)n_box, (int)C, &rb, 0, 1, precision, s));
   SCN_TRY(bias_grad(d_logits, db_cls, n, (int)n_cls, s));
   SCN_TRY(bias_grad(d_reg, db_box, n, (int)n_box, s));
-  k_relu_mask<<<ew_grid(n * C), 256, 0, s>>>(d_hidden, hidden, n * C);
+  SCN_LAUNCH(k_relu_mask, ew_grid(n * C), 256, 0, s, d_hidden, hidden, n * C);
   SCN_LAUNCHED();
   if (dw_conv) SCN_TRY(weight_grad(d_hidden, x, dw_conv, (int)C, (int)C, &rb, 0, 1, precision, s));
   SCN_TRY(bias_grad(d_hidden, db_conv, n, (int)C, s));

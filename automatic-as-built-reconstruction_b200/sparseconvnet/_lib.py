@@ -105,6 +105,7 @@ _sig = {
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int, c_void_p, c_int32, c_void_p, c_void_p]),
     "scn_set_graph_overlap": (c_int, [c_int]),
+    "scn_set_pdl": (c_int, [c_int]),
     "scn_event_create": (c_int, [POINTER(c_void_p)]),
     "scn_event_destroy": (c_int, [c_void_p]),
     "scn_event_record": (c_int, [c_void_p, c_void_p]),

@@ -308,6 +308,10 @@ int scn_graph_backward_marked(scn_metadata_t *m, const scn_graph_op_t *ops, int3
  * 0: everything on the caller's stream - no two kernels of a step overlap, which is what the per-class roofline
  * pass of bench.py wants to time */
 int scn_set_graph_overlap(int mode);
+/* Programmatic dependent launch of the library's kernels (every kernel opens with griddepcontrol.launch_dependents +
+ * griddepcontrol.wait, so the launch latency of kernel N+1 hides under kernel N; stream order is unchanged):
+ * 1 (default, env SCN_B200_PDL): every kernel; 2: all but the persistent tensor-core GEMMs; 0: plain launches */
+int scn_set_pdl(int mode);
 /* CUDA events as opaque handles (timing disabled) for the marks above */
 int scn_event_create(void **event);
 int scn_event_destroy(void *event);
