@@ -68,6 +68,25 @@ static void rulebook_free(RuleBook *rb, cudaStream_t s) {
   delete rb;
 }
 
+// A rulebook (and the output grid of a strided one) is registered in the metadata before it is built, because the
+// build's helpers look it up; this guard takes a half-built entry out again when the build fails (out of memory, a
+// size check), so that a later find_rulebook / find_grid never returns it.
+struct BuildGuard {
+  scn_metadata *m;
+  RuleBook *rb;
+  Grid *grid;
+  cudaStream_t s;
+  bool ok = false;
+  ~BuildGuard() {
+    if (ok) return;
+    for (size_t i = 0; i < m->rulebooks.size(); ++i)
+      if (m->rulebooks[i] == rb) { m->rulebooks.erase(m->rulebooks.begin() + i); rulebook_free(rb, s); break; }
+    if (grid)
+      for (size_t i = 0; i < m->grids.size(); ++i)
+        if (m->grids[i] == grid) { m->grids.erase(m->grids.begin() + i); grid_free(grid, s); break; }
+  }
+};
+
 static bool same3(const int64_t *a, const int64_t *b) {
   return a[0] == b[0] && a[1] == b[1] && a[2] == b[2];
 }
@@ -741,6 +760,7 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
   memset(rb->counts, 0, sizeof(rb->counts));
   memset(rb->pair_off, 0, sizeof(rb->pair_off));
   m->rulebooks.push_back(rb);
+  BuildGuard guard{m, rb, nullptr, s};
   if (rb->K == 1) {
     // 1x1x1: pairs are (i,i); no hashing, no lists (the reference still probes, same result)
     rb->identity = true;
@@ -748,6 +768,7 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
     rb->pair_off[1] = g->n_active;
     rb->total_pairs = g->n_active;
     SCN_TRY(ensure_tilebook(rb, true, s));
+    guard.ok = true;
     *out = rb;
     return 0;
   }
@@ -765,6 +786,7 @@ int get_submanifold_rulebook(scn_metadata *m, const int64_t *ss, const int64_t *
   SCN_TRY(finish_rulebook(rb, s));
   // algorithmic bytes: K probes x 12 B + one 12 B entry per site
   prof_end(PROF_RULES, s, (double)g->n_active * (12.0 + 12.0 * rb->K), 0);
+  guard.ok = true;
   *out = rb;
   return 0;
 }
@@ -915,6 +937,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   const int64_t n_in = gi->n_active;
   const long long total = (long long)n_in * R;
   SCN_CHECK(total < (1LL << 30), "strided rulebook too large");
+  SCN_CHECK(!same3(in_ss, out_ss), "convolution input and output spatial sizes coincide");
   // (re)create the output grid (ConvolutionRules.h:66-70 clears it)
   for (size_t i = 0; i < m->grids.size(); ++i)
     if (same3(m->grids[i]->ss, out_ss) && m->grids[i] != gi) {
@@ -922,7 +945,6 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
       m->grids.erase(m->grids.begin() + i);
       break;
     }
-  SCN_CHECK(!same3(in_ss, out_ss), "convolution input and output spatial sizes coincide");
   Grid *go = new Grid();
   memcpy(go->ss, out_ss, 24);
   m->grids.push_back(go);
@@ -935,6 +957,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   memset(rb->counts, 0, sizeof(rb->counts));
   memset(rb->pair_off, 0, sizeof(rb->pair_off));
   m->rulebooks.push_back(rb);
+  BuildGuard guard{m, rb, go, s};
 
   prof_begin(PROF_RULES, s);
   SCN_TRY(grid_alloc_table(go, total, 0x7F, s));
@@ -999,6 +1022,7 @@ int get_conv_rulebook(scn_metadata *m, const int64_t *in_ss, const int64_t *out_
   dev_free(rank, s);
   SCN_TRY(finish_rulebook(rb, s));
   prof_end(PROF_RULES, s, (double)n_in * (12.0 + 12.0 * R) + 12.0 * n_out, 0);
+  guard.ok = true;
   *out = rb;
   return 0;
 }

@@ -239,6 +239,10 @@ class GraphFunction(Function):
     @staticmethod
     def backward(ctx, *gouts):
         graph, metadata = ctx.graph, ctx.metadata_
+        if ctx.keep is None:
+            raise RuntimeError("sparseconvnet layer graph: backward called a second time - the step's value arena is released "
+                               "after the first backward (retain_graph=True is not supported; set use_layer_graph = False "
+                               "on the network for that)")
         x0, arena, bn_save, outs = ctx.keep
         rows, nv = ctx.rows, len(graph.values)
         # gradient buffers: one arena laid out like the value arena, separate buffers for the outputs

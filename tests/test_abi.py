@@ -45,3 +45,14 @@ def test_cpu_tensor_is_rejected_loudly():
     t = scn.SparseConvNetTensor(torch.zeros(3, 4), scn.Metadata(3), torch.tensor([8, 8, 8]))
     with pytest.raises(RuntimeError, match="CUDA"):
         conv(t)
+
+
+def test_reference_import_paths_resolve():
+    """the import lines of the reference files around the path work unchanged: `import sparseconvnet as scn`
+    (fpn_net.py:6) and `from SparseConvNet.sparseconvnet.tools_3d_2d import sparse_3d_to_dense_2d`
+    (maskrcnn_benchmark/layers/roi_align_rotated_3d.py:7)"""
+    import sparseconvnet as scn
+    from SparseConvNet.sparseconvnet.tools_3d_2d import sparse_3d_to_dense_2d
+    import SparseConvNet.sparseconvnet as scn2
+    assert scn2 is scn and callable(sparse_3d_to_dense_2d)
+    assert scn2.FPN_Net is scn.FPN_Net
