@@ -372,7 +372,11 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
 
   if (tid == 0) {
     for (int i = 0; i < NSA; ++i) {
+#ifdef SCN_EXPERIMENT_FEWARRIVE     // timing experiment only (wrong results): one arrival per producer WARP, copies untracked
+      mbar_init(bar_fullA + i * 8, GP_W);
+#else
       mbar_init(bar_fullA + i * 8, GP_W * 32);
+#endif
       mbar_init(bar_emptyA + i * 8, 1);
     }
     for (int i = 0; i < NSB; ++i) {
@@ -501,8 +505,13 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         }
         // the stage's barrier completes when every producer thread has passed here AND its copies have
         // landed - the thread itself never waits for them
+#ifdef SCN_EXPERIMENT_FEWARRIVE
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_fullA + stage * 8);
+#else
         cp_async_mbar_arrive(bar_fullA + stage * 8);
         mbar_arrive(bar_fullA + stage * 8);
+#endif
         if (++stage == NSA) { stage = 0; phE ^= 1; first_use = false; }
         c += splits;
         while (c >= kchunks) { c -= kchunks; ++e; }
