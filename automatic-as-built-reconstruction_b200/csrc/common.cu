@@ -337,7 +337,8 @@ int exclusive_scan_flags_i32(const int32_t *in, int32_t *out, long long n, cudaS
 // stable LSD radix sort, 9-bit digits (27-bit neighbour masks = 3 passes); every warp owns one contiguous chunk
 // ---------------------------------------------------------------------------------------
 // 4 warps x 512 keys per block: a 278k-row scale gives 136 blocks (chunks of 2048 keys left 131 of
-// the 148 SMs idle)
+// the 148 SMs idle; chunks of 128 keys - 8 warps per block - halve the scatter's time but quadruple the
+// bin-offset table the three kernels of a pass move: rulebook build 3.24 -> 3.42 ms, measured and reverted)
 constexpr int RS_WARPS = 4, RS_CHUNK = 512, RS_BITS = 9, RS_BINS = 1 << RS_BITS;
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
@@ -402,8 +403,16 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const int32_t *__restrict__ vals
     const bool valid = g < n;
     const uint32_t key = kreg[i];
     const int32_t val = vreg[i];
-    const int d = valid ? (int)((key >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int d = valid ? (int)((key >> shift) & (RS_BINS - 1)) : 0;
+    // lanes holding the same digit, by one ballot per digit bit: __match_any_sync serialises over the DISTINCT values
+    // in the warp (~70 cycles each; 9-bit digits are mostly distinct), which made a round cost ~2300 cycles and every
+    // launch of this kernel ~20 us whatever its size (ncu launch list, round 2)
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < RS_BITS; ++b) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
+      peers &= ((d >> b) & 1) ? bal : ~bal;
+    }
     const int rank = __popc(peers & lt);
     if (valid) {
       const int pos = cnt[w][d] + rank;

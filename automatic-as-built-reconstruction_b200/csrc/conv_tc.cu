@@ -203,8 +203,7 @@ constexpr int NSA_MAX = 8, NSB_MAX = 4;      // ring depths: A (gathered rows) /
 constexpr int GP_W = 8, MMA_W = 8, WL_W = 9, META_W = 10, EPI_W = 12, CONV_W = 16;
 constexpr int NT_P = 16 * 32;
 constexpr int NT_P3 = 20 * 32;
-constexpr int NT_P4 = 24 * 32;               // MODE 3: 8 converter warps, each 32 rows x 16 of a stage's 32 values
-__host__ __device__ constexpr int gemm_threads(int mode) { return mode == 3 ? NT_P4 : (mode ? NT_P3 : NT_P); }
+__host__ __device__ constexpr int gemm_threads(int mode) { return mode ? NT_P3 : NT_P; }
 constexpr int NLO = 2;                       // stages of low-order halves (3xTF32 mode, weight-gradient kernel: shared memory)
 // 3xTF32 gather-GEMM: the low-order halves of the gathered rows live in TENSOR MEMORY (row r in lane r, the
 // 32 values of a step in 32 columns; tools/tmem_a_probe.cu) and feed tcgen05.mma as its A operand from there.
@@ -229,11 +228,8 @@ constexpr bool HI_TMEM = false;
 struct Smem {
   // offsets (bytes) into the dynamic shared memory block, computed identically on host and device
   int a, alo, b, stage, meta, meta_bytes, bars, tmem_slot, total;
-  // mode 0: tf32, 1: 3xTF32 (a weight stage = hi slice + lo slice), 2: bf16 (a weight stage = N x 32 bf16),
-  // 3: tf32 + two bf16 correction terms (a weight stage = tf32 hi slice + bf16(w) slice + bf16(w - hi) slice)
-  __host__ __device__ static int b_stage_bytes(int N, int mode) {
-    return (mode == 1 || mode == 3) ? 2 * NCORE * N * 16 : (mode == 2 ? N * 64 : NCORE * N * 16);
-  }
+  // mode 0: tf32, 1: 3xTF32 (a weight stage = hi slice + lo slice), 2: bf16 (a weight stage = N x 32 bf16)
+  __host__ __device__ static int b_stage_bytes(int N, int mode) { return mode == 1 ? 2 * NCORE * N * 16 : (mode == 2 ? N * 64 : NCORE * N * 16); }
   __host__ __device__ Smem(int N, int K, int nsa, int nsb, int mode, int ms) {
     a = 0;
     alo = a + nsa * A_STAGE;                // 3xTF32 with the low-order halves in shared memory: NLO stages
@@ -339,7 +335,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
   constexpr int NSA = DEPTH + 2;
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr bool X3 = MODE == 1, BF = MODE == 2, XB = MODE == 3, CONV = MODE != 0;
+  constexpr bool X3 = MODE == 1, BF = MODE == 2, CONV = MODE != 0;
   const Smem L(N, K, NSA, NSB, MODE, ms);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_slot);
   const uint32_t a_base = smem_u32(smem + L.a), b_base = smem_u32(smem + L.b);
@@ -385,10 +381,10 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     }
     for (int i = 0; i < ms; ++i) {
       mbar_init(bar_mfull + i * 8, 1);
-      mbar_init(bar_mempty + i * 8, GP_W + 6 + (XB ? 8 : (CONV ? 4 : 0)));   // producer + 4 epilogue warps + MMA + weight loader (+ converters)
+      mbar_init(bar_mempty + i * 8, GP_W + 6 + (CONV ? 4 : 0));   // producer + 4 epilogue warps + MMA + weight loader (+ 4 converters)
     }
     if (CONV)
-      for (int i = 0; i < 4; ++i) mbar_init(bar_fullL + i * 8, XB ? 8 : 4);     // one arrival per converter warp
+      for (int i = 0; i < 4; ++i) mbar_init(bar_fullL + i * 8, 4);     // one arrival per converter warp
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
       mbar_init(bar_tempty + i * 8, 4);      // 4 epilogue warps
@@ -396,11 +392,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   // accumulators: 2 x acc_cols; 3xTF32 with the low-order halves in TMEM: the whole 512 columns
-  const uint32_t tmem_cols = ((X3 && LO_TMEM) || BF || XB) ? 512u : 2 * acc_cols;
-  constexpr int NLT = (LO_TMEM || BF || XB) ? (NSA >= 4 ? 4 : 2) : NLO;      // low-order stages (never deeper than the A ring)
-  // MODE 3: 64 TMEM columns per converted stage, two halves of 32 (values [16h, 16h + 16) of the step, written by converter
-  // warp set h): [0,16) hi = rn_tf32(x), [16,24) bf16 pairs of lo = x - hi, [24,32) bf16 pairs of hi
-  constexpr int XB_COLS = 64;
+  const uint32_t tmem_cols = ((X3 && LO_TMEM) || BF) ? 512u : 2 * acc_cols;
+  constexpr int NLT = (LO_TMEM || BF) ? (NSA >= 4 ? 4 : 2) : NLO;      // low-order stages (never deeper than the A ring)
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -580,21 +573,6 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const uint64_t dl = desc_hi | (uint64_t)((sl & 0x3FFFFu) >> 4);
           const uint64_t db_lo = desc_hi | (uint64_t)(((sb + B_SLICE) & 0x3FFFFu) >> 4);
           if (elect_one()) {
-          if (XB) {
-            // x w = hi whi (tf32, 4 x K = 8) + lo w (bf16, 2 x K = 16) + hi wlo (bf16, 2 x K = 16): 8 tensor-pipe slots per
-            // step instead of the 12 of 3xTF32; every A operand comes from tensor memory
-            const uint32_t ta = tmem_base + 2 * acc_cols + (uint32_t)(stl * XB_COLS);
-#pragma unroll
-            for (int kk = 0; kk < KC / 8; ++kk)
-              mma_tf32_ts(tmem_d, ta + (kk >> 1) * 32 + (kk & 1) * 8, db + 2 * kk, idesc, (lst > 0 || kk > 0) ? 1u : 0u);
-            const uint32_t sw = sb + NCORE * N * 16;           // bf16(w) slice, then bf16(w - whi) slice (N x 64 B each)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-              mma_bf16_ts(tmem_d, ta + kk * 32 + 16, desc_bf + (uint64_t)(((sw + kk * 2 * N * 16) & 0x3FFFFu) >> 4), idesc_bf, 1u);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-              mma_bf16_ts(tmem_d, ta + kk * 32 + 24, desc_bf + (uint64_t)(((sw + N * 64 + kk * 2 * N * 16) & 0x3FFFFu) >> 4), idesc_bf, 1u);
-          }
           if (BF) {
             // A (bf16 pairs) from TMEM: 16 columns per step, 8 per K = 16 instruction; B: no-swizzle K-major,
             // core matrices N*16 B apart along K (LBO), 8-row groups 128 B apart (SBO)
@@ -608,7 +586,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (lst == 0) mma_tf32(tmem_d, make_desc_sw128(sa), make_desc_sw128(sb), idesc, 0u);
           for (int kk = 0; kk < 0; ++kk) {
 #else
-          for (int kk = 0; kk < ((BF || XB) ? 0 : KC / 8); ++kk) { // K = 8 per instruction: 32 bytes (2 descriptor units) further along the 128-byte rows
+          for (int kk = 0; kk < (BF ? 0 : KC / 8); ++kk) { // K = 8 per instruction: 32 bytes (2 descriptor units) further along the 128-byte rows
 #endif
             if (X3 && HI_TMEM) {
               const uint32_t ta = tmem_base + 2 * acc_cols + (uint32_t)(stl * KC + kk * 8);
@@ -681,11 +659,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           if (g >= NSB) { mbar_arrive(bar_fullB + stage * 8); continue; }
 #endif
           mbar_expect_tx(bar_fullB + stage * 8, bytes);
-          if (XB) {   // image [k][c][column block][N x 64 floats]: tf32 hi slice + two bf16 slices, one contiguous stage
-            const int ncb = ldn / N;
-            const float *src = Wp + (((long long)kw * kchunks + c) * ncb + col0 / N) * (long long)N * 64;
-            bulk_copy_g2s(b_base + stage * B_STAGE, src, bytes, bar_fullB + stage * 8);
-          } else if (BF) {   // bf16 image [k][c][column block][core j][N][8]: one contiguous slice per (k, c, block)
+if (BF) {   // bf16 image [k][c][column block][core j][N][8]: one contiguous slice per (k, c, block)
             const int ncb = ldn / N;
             const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(Wp) +
                                        (((long long)kw * kchunks + c) * ncb + col0 / N) * (long long)N * KC;
@@ -721,35 +695,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
           const int stage = g % NSA, stl = g % NLT;
           MBW(bar_fullA + stage * 8, (g / NSA) & 1, 2);
           if (g >= NLT) MBW(bar_emptyA + ((g - NLT) % NSA) * 8, ((g - NLT) / NSA) & 1, 1);
-          if (XB) {
-            // thread = (row r, half h of the step's 32 values): hi = rn_tf32(x) -> 16 columns, bf16 pairs of lo = x - hi (exact)
-            // and of hi -> 8 + 8 columns; one 32-column store per thread.  Eight warps, because ONE warp per 32 rows needed
-            // ~800 cycles per step for its dependent chain (loads -> ~230 instructions -> two 32-column stores) and paced
-            // the kernel (tools/gemm_stalls.py); integer arithmetic only (cvt.rna.tf32 / cvt.rn.bf16x2 run on the
-            // quarter-rate conversion pipe): hi = (bits + 0x1000) & ~0x1fff rounds to tf32 (ties away), |lo| <= 2^-12 |x|;
-            // the bf16 halves of lo and hi are their upper 16 bits (truncation: 2^-8 of a term that is itself <= 2^-12 of
-            // the product; the weights' bf16 slices are rounded when packed)
-            tc_fence_after();
-            const int r = ct & 127, h = ct >> 7;
-            const float4 *row = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE + (r >> 3) * 1024 + (r & 7) * 128);
-            uint32_t w[32];
-#pragma unroll
-            for (int jc = 0; jc < 4; ++jc) {
-              const float4 v = row[(4 * h + jc) ^ (r & 7)];
-              const uint32_t h0 = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u, h1 = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u;
-              const uint32_t h2 = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u, h3 = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u;
-              w[4 * jc + 0] = h0; w[4 * jc + 1] = h1; w[4 * jc + 2] = h2; w[4 * jc + 3] = h3;
-              const uint32_t l0 = __float_as_uint(v.x - __uint_as_float(h0)), l1 = __float_as_uint(v.y - __uint_as_float(h1));
-              const uint32_t l2 = __float_as_uint(v.z - __uint_as_float(h2)), l3 = __float_as_uint(v.w - __uint_as_float(h3));
-              w[16 + 2 * jc] = __byte_perm(l0, l1, 0x7632);          // {hi16(l0), hi16(l1)}: element 0 in the low half
-              w[16 + 2 * jc + 1] = __byte_perm(l2, l3, 0x7632);
-              w[24 + 2 * jc] = __byte_perm(h0, h1, 0x7632);
-              w[24 + 2 * jc + 1] = __byte_perm(h2, h3, 0x7632);
-            }
-            tmem_st32(tmem_base + 2 * acc_cols + (uint32_t)(stl * XB_COLS + h * 32) + ((uint32_t)((warp & 3) * 32) << 16), w);
-            tmem_st_wait();
-            tc_fence_before();
-          } else if (BF) {
+          if (BF) {
             // thread = row ct: its 8 chunks (un-swizzled by index) -> 16 bf16 pairs -> 16 columns of TMEM lane ct
             tc_fence_after();
             const float4 *row = reinterpret_cast<const float4 *>(smem + L.a + stage * A_STAGE + (ct >> 3) * 1024 + (ct & 7) * 128);
@@ -1001,33 +947,6 @@ __global__ void k_pack_weights_bf16(const float *__restrict__ W, __nv_bfloat16 *
     pack_element_bf16(W, Wf, Wb, K, Cin, Cout, do_f, do_b, i2);
 }
 
-// mode 3 operand images: [k][chunk c][column block][NW x 64 floats] = one weight stage per (k, c, block):
-//   NW rows x 32 tf32 (hi = rna_tf32(w), K-major SWIZZLE_128B), then bf16(w) and bf16(w - hi), each in the no-swizzle
-//   K-major bf16 layout [core j = 4][NW rows][8]
-__device__ __forceinline__ void xb_store(float *__restrict__ img, int k, int kch, int c, int kin, int N, int n, float v) {
-  const int NW = N > 128 ? 128 : N, ncb = N / NW, cb = n / NW, nb = n % NW;
-  float *blk = img + (((long long)k * kch + c) * ncb + cb) * (long long)NW * 64;
-  const float hi = to_tf32(v);
-  blk[nb * KC + ((((kin >> 2) ^ (nb & 7)) << 2) | (kin & 3))] = hi;
-  __nv_bfloat16 *b16 = reinterpret_cast<__nv_bfloat16 *>(blk + NW * KC);
-  const int o = (((kin >> 3) * NW + nb) << 3) + (kin & 7);
-  b16[o] = __float2bfloat16(v);
-  b16[NW * KC + o] = __float2bfloat16(v - hi);
-}
-__global__ void k_pack_weights_xb(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wb,
-                                  int K, int Cin, int Cout, int do_f, int do_b) {
-  pdl_sync();
-  const long long per_k = (long long)Cin * Cout, total = (long long)K * per_k;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i / per_k);
-    const long long r = i - (long long)k * per_k;
-    const int ci = (int)(r / Cout), co = (int)(r - (long long)ci * Cout);
-    const float v = W[i];
-    if (do_f) xb_store(Wf, k, Cin / KC, ci / KC, ci % KC, Cout, co, v);     // forward: reduction = input channels
-    if (do_b) xb_store(Wb, k, Cout / KC, co / KC, co % KC, Cin, ci, v);     // dX: reduction = output channels
-  }
-}
-
 // every convolution weight of a layer graph in ONE launch (blockIdx.y = tensor): the per-layer pack launches were
 // ~45 x 7 us of a backbone step
 struct PackJob { const float *W; float *wf, *wb; int K, Cin, Cout, flags; };     // flags: 1 forward image, 2 dX image
@@ -1052,51 +971,6 @@ __global__ void __launch_bounds__(256) k_pack_weights_batch(const __grid_constan
   __shared__ float tile[8][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int Cin = j.Cin, Cout = j.Cout;
-  if (x3 == 3) {
-    // mode 3 images (see xb_store): a warp moves one 32 x 32 tile (32 reduction indices x 32 operand rows) through shared
-    // memory as tile[reduction][row]; the tf32 rows leave as 128-byte lines, the bf16 core-matrix rows as 16 bytes per lane
-    const int tiles_b = (j.flags & 2) ? j.K * (Cout >> 5) * (Cin >> 5) : 0;
-    const int tiles_f = (j.flags & 1) ? j.K * (Cin >> 5) * (Cout >> 5) : 0;
-    for (int t = blockIdx.x * 8 + w; t < tiles_b + tiles_f; t += gridDim.x * 8) {
-      const bool back = t < tiles_b;
-      const int tf = back ? t : t - tiles_b;
-      const int N = back ? Cin : Cout, Kd = back ? Cout : Cin;        // operand rows, reduction length
-      const int ng = tf % (N >> 5), c = (tf / (N >> 5)) % (Kd >> 5), k = tf / ((N >> 5) * (Kd >> 5));
-      __syncwarp();
-      if (back) {
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r)         // operand row = input channel ng*32 + r, lane = reduction index (output channel)
-          tile[w][lane][r] = j.W[((long long)k * Cin + ng * 32 + r) * Cout + c * KC + lane];
-      } else {
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r)         // r = reduction index (input channel), lane = operand row (output channel)
-          tile[w][r][lane] = j.W[((long long)k * Cin + c * KC + r) * Cout + ng * 32 + lane];
-      }
-      __syncwarp();
-      const int NW = N > 128 ? 128 : N, ncb = N / NW, n0 = ng * 32, cb = n0 / NW, nb0 = n0 % NW;
-      float *blk = (back ? j.wb : j.wf) + (((long long)k * (Kd >> 5) + c) * ncb + cb) * (long long)NW * 64;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {         // tf32 hi: operand row nb0 + r, lane = reduction index within the chunk
-        const int nb = nb0 + r;
-        blk[nb * KC + ((((lane >> 2) ^ (nb & 7)) << 2) | (lane & 3))] = to_tf32(tile[w][lane][r]);
-      }
-      uint4 *b16 = reinterpret_cast<uint4 *>(blk + NW * KC);        // [core][NW rows] x 16 bytes, then the low-order slice
-#pragma unroll
-      for (int jc = 0; jc < 4; ++jc) {       // lane = operand row nb0 + lane: 8 consecutive reduction indices = 16 bytes
-        uint32_t a[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v0 = tile[w][jc * 8 + 2 * e][lane], v1 = tile[w][jc * 8 + 2 * e + 1][lane];
-          const __nv_bfloat162 pa = __floats2bfloat162_rn(v0, v1), pl = __floats2bfloat162_rn(v0 - to_tf32(v0), v1 - to_tf32(v1));
-          a[e] = *reinterpret_cast<const uint32_t *>(&pa);
-          l[e] = *reinterpret_cast<const uint32_t *>(&pl);
-        }
-        b16[jc * NW + nb0 + lane] = make_uint4(a[0], a[1], a[2], a[3]);
-        b16[(NW * KC * 2) / 16 + jc * NW + nb0 + lane] = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-    }
-    return;
-  }
   // tiles of the dX image: K x (Cout/32 chunks) x (Cin/32 row groups); of the forward image: K x (Cin/32) x (Cout/32)
   const int tiles_b = (j.flags & 2) ? j.K * (Cout >> 5) * (Cin >> 5) : 0;
   const int tiles_f = (j.flags & 1) ? j.K * (Cin >> 5) * (Cout >> 5) : 0;
@@ -1154,7 +1028,7 @@ static uint64_t g_batch_id = 0;      // current prepack batch (layer-graph forwa
 static uint64_t g_batch_seq = 0;
 
 static int gemm_mode(int precision) {
-  return precision == SCN_PRECISION_FP32_3XTF32 ? 1 : (precision == SCN_PRECISION_BF16 ? 2 : (precision == SCN_PRECISION_FP32_SPLIT ? 3 : 0));
+  return precision == SCN_PRECISION_FP32_3XTF32 ? 1 : (precision == SCN_PRECISION_BF16 ? 2 : 0);
 }
 static bool layout_ok(int Kd, int N) { return Kd >= KC && Kd % KC == 0 && N >= 16 && N % 16 == 0 && N <= 256; }
 
@@ -1209,9 +1083,7 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
     e->has_b = layout_ok(Cout, Cin);
     int pb = cdiv(2 * (long long)total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
-    if (x3 == 3)
-      SCN_LAUNCH(k_pack_weights_xb, pb, 256, 0, s, W, e->wf, e->wb, K, Cin, Cout, (int)e->has_f, (int)e->has_b);
-    else if (x3 == 2)
+    if (x3 == 2)
       SCN_LAUNCH(k_pack_weights_bf16, pb, 256, 0, s, W, reinterpret_cast<__nv_bfloat16 *>(e->wf), reinterpret_cast<__nv_bfloat16 *>(e->wb),
                                              K, Cin, Cout, e->has_f, e->has_b);
     else
@@ -1235,8 +1107,7 @@ static int cached_pack(const int64_t *tag, const float *W, int K, int Cin, int C
 int prepack_weights_batch(int n, const int64_t *const *tags, const float *const *W, const int *K, const int *Cin,
                           const int *Cout, int precision, cudaStream_t s) {
   using namespace tc;
-  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16 &&
-      precision != SCN_PRECISION_FP32_SPLIT) return 0;
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 0;
   const int x3 = gemm_mode(precision);
   std::lock_guard<std::mutex> lk(g_pack_mu);
   g_batch_id = ++g_batch_seq;
@@ -1291,10 +1162,9 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
               const TileView &tv, int K, int Kb, int precision, int transpose_w, cudaStream_t s, double prof_bytes,
               double prof_flops, const int64_t *weight_tag) {
   using namespace tc;
-  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16 &&
-      precision != SCN_PRECISION_FP32_SPLIT) return 1;
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 1;
   if (!tf32_shape_ok(X, W, bias, Y, Kd, N)) return 1;
-  // kernel mode: 0 tf32, 1 3xTF32, 2 bf16, 3 tf32 + bf16 correction terms
+  // kernel mode: 0 tf32, 1 3xTF32, 2 bf16
   const int x3 = gemm_mode(precision);
   // 3xTF32 / bf16: a work item covers <= 128 output columns (TMEM also holds converted A stages)
   const int ncb = (x3 && N > 128) ? N / 128 : 1;
@@ -1307,12 +1177,10 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     if (r) return r > 0 ? -1 : r;
   } else {
     const long long total = (long long)K * Kd * N;
-    if (workspace_t(&wp, WS_PACKED_W, (size_t)total * ((x3 == 1 || x3 == 3) ? 2 : 1), s)) return -1;
+    if (workspace_t(&wp, WS_PACKED_W, (size_t)total * (x3 == 1 ? 2 : 1), s)) return -1;
     int pb = cdiv(2 * total, 256);
     if (pb > num_sms() * 8) pb = num_sms() * 8;
-    if (x3 == 3)
-      SCN_LAUNCH(k_pack_weights_xb, pb, 256, 0, s, W, wp, wp, K, cin, cout, (int)!transpose_w, (int)transpose_w);
-    else if (x3 == 2)
+    if (x3 == 2)
       SCN_LAUNCH(k_pack_weights_bf16, pb, 256, 0, s, W, reinterpret_cast<__nv_bfloat16 *>(wp), reinterpret_cast<__nv_bfloat16 *>(wp), K,
                                              cin, cout, !transpose_w, transpose_w);
     else
@@ -1356,7 +1224,6 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     SCN_SETATTR_MODE(0)
     SCN_SETATTR_MODE(1)
     SCN_SETATTR_MODE(2)
-    SCN_SETATTR_MODE(3)
 #undef SCN_SETATTR_MODE
     if (ae != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_osgemm_tf32) failed: %s", cudaGetErrorString(ae));
@@ -1400,7 +1267,7 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
     case 2: SCN_OSGEMM_LAUNCH(2, T3); break;                                                                  \
     default: SCN_OSGEMM_LAUNCH(1, T3); break;                                                                 \
   }
-  if (x3 == 3) { SCN_OSGEMM_DEPTH(3) } else if (x3 == 2) { SCN_OSGEMM_DEPTH(2) } else if (x3 == 1) { SCN_OSGEMM_DEPTH(1) } else { SCN_OSGEMM_DEPTH(0) }
+  if (x3 == 2) { SCN_OSGEMM_DEPTH(2) } else if (x3 == 1) { SCN_OSGEMM_DEPTH(1) } else { SCN_OSGEMM_DEPTH(0) }
 #undef SCN_OSGEMM_DEPTH
 #undef SCN_OSGEMM_LAUNCH
   prof_end(PROF_GEMM, s, prof_bytes, prof_flops);
@@ -1780,9 +1647,8 @@ int dw_partial_tc(const float *X, const float *dY, const int32_t *pairs, const D
   using namespace tc;
   auto al = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
   // bf16 mode: the weight gradient runs on the single-pass tf32 kernel (both operands are gathered fp32 rows)
-  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16 &&
-      precision != SCN_PRECISION_FP32_SPLIT) return 1;
-  const bool x3 = precision == SCN_PRECISION_FP32_3XTF32 || precision == SCN_PRECISION_FP32_SPLIT;   // (both: 3xTF32 weight gradient)
+  if (precision != SCN_PRECISION_TF32 && precision != SCN_PRECISION_FP32_3XTF32 && precision != SCN_PRECISION_BF16) return 1;
+  const bool x3 = precision == SCN_PRECISION_FP32_3XTF32;
   if (Cin < 32 || Cin % 32 || (Cin > 128 && Cin != 256) || Cout < 32 || Cout % 32 || Cout > 256) return 1;
   if (((Cin >> 5) & ((Cin >> 5) - 1)) || ((Cout >> 5) & ((Cout >> 5) - 1))) return 1;   // 32-channel atoms: power of two
   if (!al(X) || !al(dY) || !al(partial)) return 1;

@@ -24,9 +24,7 @@ lib = ctypes.CDLL(LIB_PATH)
 # cores (hi/lo operand split, fp32 accumulation, error ~2^-20 relative - inside the 1e-4 parity bound),
 # with the exact FFMA tiles for the shapes the tensor path does not take (Cin = 9 stem).
 # "bf16": forward / input-gradient contractions with bf16 operands (fp32 accumulation), weight gradient in tf32.
-# "fp32_split": like "fp32" with the two correction terms of the operand split as bf16 MMAs (8 instead of 12 tensor-pipe
-# slots per step, error <= ~4 * 2^-20 per product); 3xTF32 weight gradient.
-PRECISIONS = {"fp32_ffma": 0, "tf32": 1, "fp32": 2, "bf16": 3, "fp32_split": 4}
+PRECISIONS = {"fp32_ffma": 0, "tf32": 1, "fp32": 2, "bf16": 3}
 _precision = PRECISIONS[os.environ.get("SCN_B200_PRECISION", "fp32")]
 
 

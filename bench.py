@@ -1,7 +1,7 @@
 """bench.py - the sparse3d backbone (FPN_Net) forward+backward on synthetic SUNCG-shaped buildings.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode train|infer]
-                    [--batch B] [--precision fp32|fp32_split|fp32_ffma|tf32|bf16]
+                    [--batch B] [--precision fp32|fp32_ffma|tf32|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 --mode infer times the evaluation forward (no_grad, batch statistics as every shipped config has
@@ -430,9 +430,7 @@ def run_b200(args, rank, local_rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32 (3xTF32 on tcgen05, fp32 accumulate)", "fp32_ffma": "f32", "tf32": "tf32",
-                      "bf16": "bf16 (operands; fp32 accumulate, tf32 weight gradient)",
-                      "fp32_split": "f32 (operand split on tcgen05: tf32 main term + bf16 correction terms in forward / dX, "
-                                    "3xTF32 weight gradient; fp32 accumulate)"}[args.precision],
+                      "bf16": "bf16 (operands; fp32 accumulate, tf32 weight gradient)"}[args.precision],
             "data": "synthetic",
             "buildings_per_sec": args.batch * world / sec, "active_voxels_per_building": na_local / args.batch,
             "config": workload_config(args),
@@ -547,7 +545,7 @@ def main():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--floors", type=int, default=None)
     ap.add_argument("--precision", default=os.environ.get("SCN_B200_PRECISION", "fp32"),
-                    choices=["fp32", "fp32_split", "fp32_ffma", "tf32", "bf16"])
+                    choices=["fp32", "fp32_ffma", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

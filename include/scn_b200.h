@@ -40,13 +40,9 @@ enum {
   SCN_PRECISION_FP32_3XTF32 = 2, /* fp32 accuracy on the tensor cores: x = hi + lo, w = whi + wlo in tf32,
                                    hi*whi + lo*whi + hi*wlo accumulated in fp32 (error ~2^-20 relative);
                                    shapes the tensor path does not take use the exact FFMA tiles           */
-  SCN_PRECISION_BF16 = 3,      /* forward / input-gradient contractions with bf16 operands (features rounded to
+  SCN_PRECISION_BF16 = 3       /* forward / input-gradient contractions with bf16 operands (features rounded to
                                    nearest, kind::f16 MMAs, A operand from tensor memory), fp32 accumulation;
                                    the weight gradient runs in single-pass tf32                              */
-  SCN_PRECISION_FP32_SPLIT = 4 /* fp32 accuracy with 8 instead of 12 tensor-pipe slots per step: x = hi + lo, w = whi + wlo
-                                   with hi / whi ROUNDED to tf32 (|lo| <= 2^-12 |x|); hi*whi as tf32 MMAs, the two
-                                   correction terms lo*w and hi*wlo as bf16 MMAs (error <= ~4 * 2^-20 per product),
-                                   fp32 accumulation; the weight gradient runs in 3xTF32                        */
 };
 
 /* ---- library ---------------------------------------------------------------------- */
