@@ -112,6 +112,14 @@ class FPN_Net(torch.nn.Module):
 
     # ---- one-call execution of the whole graph (sparseconvnet/graph.py) ----------------------
     use_layer_graph = os.environ.get("SCN_B200_LAYER_GRAPH", "1") != "0"
+    # B200 extension, OFF by default: skip the layers no returned map depends on (the finer half of the top-down path,
+    # which the reference computes and drops - fpn_net.py:186-203).  Outputs and gradients are unchanged bit for bit;
+    # with tracked running statistics the BN buffers of the skipped layers are no longer updated.  Set the attribute
+    # before the first forward pass (or call `invalidate_graph()` after changing it).
+    prune_dead_branches = os.environ.get("SCN_B200_PRUNE_DEAD", "0") == "1"
+
+    def invalidate_graph(self):
+        self._graph_cache = None
 
     def _apply(self, fn, *args, **kwargs):
         self._graph_cache = None          # .to() / .cuda() replace the BN buffers the compiled graph points at
@@ -145,7 +153,7 @@ class FPN_Net(torch.nn.Module):
                 both = rpn3d + rpn2d
                 self._graph_rpn = [both[i] for i in self.rpn_3d_2d_selector]
                 self._graph_roi = [ups[i] for i in self.roi_scales_from_top]
-                g.finalize(self._graph_rpn + self._graph_roi)
+                g.finalize(self._graph_rpn + self._graph_roi, prune_dead=self.prune_dead_branches)
             except _graph.Unsupported:
                 g = False
             self._graph_cache = g

@@ -145,9 +145,23 @@ class LayerGraph(object):
             return cur
         raise Unsupported(type(mod).__name__)
 
-    def finalize(self, outputs):
+    def finalize(self, outputs, prune_dead=False):
+        """prune_dead: drop the ops no output depends on.  The reference computes them (fpn_net.py:186-203 runs the whole
+        top-down path and returns only the maps of `fpn_scales_from_top`: 61 % of the forward MACs at the BASELINE
+        config) and so does this library by default; nothing observable depends on them except the running statistics
+        of their BN layers when those are tracked - outputs and gradients are bit-identical with and without."""
         self.outputs = list(dict.fromkeys(outputs))          # unique, order kept
         assert 0 not in self.outputs
+        live = set(self.outputs)
+        for o in reversed(self.ops):
+            if o.out in live:
+                live.add(o.in0)
+                if o.kind == ADD:
+                    live.add(o.in1)
+        self.n_dead_ops = sum(1 for o in self.ops if o.out not in live)
+        self.live_values = live
+        if prune_dead:
+            self.ops = [o for o in self.ops if o.out in live]
         self._c_ops = (GraphOp * len(self.ops))(*self.ops)
         self.grad_params = [t for t in self.params if isinstance(t, torch.nn.Parameter)]
         self._grad_slot = [self._slot[id(t)] for t in self.grad_params]
@@ -213,8 +227,9 @@ class GraphFunction(Function):
             raise RuntimeError("input features have %d rows, the input grid %d" % (x0.size(0), rows[0]))
         is_out = set(graph.outputs)
         off, total = [0] * nv, 0
+        written = set(o.out for o in graph.ops)
         for v in range(1, nv):
-            if v not in is_out:
+            if v not in is_out and v in written:                              # (pruned graphs: dead values get no room)
                 off[v] = total
                 total += (rows[v] * graph.values[v][0] + 63) // 64 * 64       # 256-byte aligned
         arena = x0.new_empty(max(total, 1))

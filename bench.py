@@ -14,6 +14,7 @@ BASELINE.json configs[1]: one 300k-point building, batch 1 (SURVEY.md section 8d
 Metric: active voxels/s (sum over samples of nActive at scale 0 / time), whole job over all GPUs.
 
   value     inputs resident in HBM when the timed region starts
+  value_pruned  (extra, not the headline) the step with FPN_Net.prune_dead_branches = True
   value_inline  the same step through the reference's own call net([coords, feats]) - no prefetcher, voxel
             hashing and all rulebooks built inside the step
   e2e       same step through the public API from pinned HOST buffers (coords + features H2D and a
@@ -383,6 +384,23 @@ def run_b200(args, rank, local_rank, world):
         return float(t.item())
     ms_inline = timed_inline(args.steps)
 
+    # B200 extension, reported beside the headline and NOT part of it: FPN_Net.prune_dead_branches skips the layers no
+    # returned map depends on (the reference computes them and drops the results, fpn_net.py:186-203; outputs and
+    # gradients are bit-identical - tests/test_full_parity.py::test_pruned_dead_branches_change_nothing)
+    net.prune_dead_branches = True
+    net.invalidate_graph()
+    if train:
+        bucket = scn.GradBucket(net.parameters(), module=net)     # (its ranges follow the compiled graph's op order)
+    for _ in range(args.warmup):
+        step(locs_dev, feats_dev)
+    ms_pruned, launches_pruned = timed(args.steps, False)
+    dead_ops, live_ops = net._layer_graph().n_dead_ops, len(net._layer_graph().ops)
+    net.prune_dead_branches = False
+    net.invalidate_graph()
+    if train:
+        bucket = scn.GradBucket(net.parameters(), module=net)
+    step(locs_dev, feats_dev)
+
     na_t = torch.tensor([na_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(na_t)
@@ -445,6 +463,13 @@ def run_b200(args, rank, local_rank, world):
             "value_inline": {"value": na_total / (ms_inline * 1e-3 / args.steps), "unit": "active voxels/s",
                              "ms_per_step": ms_inline / args.steps,
                              "what": "plain net([coords, feats]) - no prefetcher, rulebook builds inside the step"},
+            "value_pruned": {"value": na_total / (ms_pruned * 1e-3 / args.steps), "unit": "active voxels/s",
+                             "ms_per_step": ms_pruned / args.steps, "gpu_launches": int(launches_pruned),
+                             "ops_skipped": int(dead_ops), "ops_run": int(live_ops),
+                             "what": "NOT the headline: the same step with FPN_Net.prune_dead_branches = True (B200 extension, "
+                                     "off by default) - the layers no returned map depends on are skipped; the reference "
+                                     "computes them (fpn_net.py:186-203) and so does every other number of this line; "
+                                     "outputs and gradients are bit-identical"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "conv gather-GEMM (fwd + dX), all launches of a step",

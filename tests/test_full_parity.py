@@ -217,3 +217,33 @@ def test_full_size_reduced_precision_within_stated_tolerance(precision, full_siz
         assert (num / den) ** 0.5 <= l2tol
     finally:
         scn.set_conv_precision("fp32")
+
+
+def test_pruned_dead_branches_change_nothing(wide):
+    """FPN_Net.prune_dead_branches (B200 extension, off by default): the layers no returned map depends on are skipped -
+    the 8 output maps and every parameter gradient stay bit-identical, and fewer kernels run"""
+    import sparseconvnet as scn
+    g, sd, locs, feats, _, _ = wide
+    scn.set_conv_precision("fp32")
+    res = []
+    for prune in (False, True):
+        net = _fpn(scn, WIDE_CFG, 32)
+        net.load_state_dict(sd)
+        net.prune_dead_branches = prune
+        net = net.cuda().train()
+        k0 = scn.SCN.launch_count()
+        rpn, roi = net([locs, feats.cuda()])
+        sum((m.features ** 2).sum() for m in list(rpn) + list(roi)).backward()
+        torch.cuda.synchronize()
+        res.append((scn.SCN.launch_count() - k0, [m.features.detach().clone() for m in list(rpn) + list(roi)],
+                    {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in net.named_parameters()},
+                    net._graph_cache.n_dead_ops, len(net._graph_cache.ops)))
+    (l0, f0, g0, dead0, ops0), (l1, f1, g1, dead1, ops1) = res
+    assert dead0 == dead1 > 0 and ops1 == ops0 - dead0
+    assert l1 < l0
+    assert all(torch.equal(a, b) for a, b in zip(f0, f1))
+    for k in g0:
+        if g0[k] is None or float(g0[k].abs().max()) == 0.0:
+            assert g1[k] is None or float(g1[k].abs().max()) == 0.0, k
+        else:
+            assert torch.equal(g0[k], g1[k]), k
