@@ -11,6 +11,7 @@ print("${name}", d["n_gpus"], "ms/step", round(d["ms_per_step"], 3), "e2e", roun
       "buildings/s", d.get("buildings_per_sec"))
 PY
 }
+run scale_fp32_b1 --steps 30 --warmup 3 --no-cpu-baseline
 run cfg3_bf16_b2 --steps 20 --warmup 3 --batch 2 --precision bf16 --no-cpu-baseline
 run cfg4_fp32_b4 --steps 10 --warmup 3 --batch 4 --no-cpu-baseline
 run cfg5_infer_2M --steps 10 --warmup 3 --mode infer --no-cpu-baseline
