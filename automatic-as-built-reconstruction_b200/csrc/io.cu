@@ -336,6 +336,43 @@ int scn_sparse_to_dense_forward(scn_metadata_t *m, const int64_t *ss, const floa
   return 0;
 }
 
+// the same into the CROPPED volume [batch, C, ext0, ext1, ext2] = dense[:, :, :ext0, :ext1, :ext2] of the full tensor
+// (what tools_3d_2d.py:28 slices out after densifying all of [X, Y, Z]: 1.07 GB zero-filled for a [256,256,32] ROI map
+// of which the benchmark building occupies 16 MB)
+int scn_sparse_to_dense_cropped_forward(scn_metadata_t *m, const int64_t *ss, const int64_t *ext, const float *in,
+                                        float *out, int64_t C, int64_t batch, void *stream) {
+  SCN_CHECK(m && ss && ext && out, "null argument");
+  SCN_CHECK(ext[0] >= 0 && ext[1] >= 0 && ext[2] >= 0 && ext[0] <= ss[0] && ext[1] <= ss[1] && ext[2] <= ss[2],
+            "SparseToDense: extent [%lld,%lld,%lld] outside the spatial size", (long long)ext[0], (long long)ext[1],
+            (long long)ext[2]);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long V = ext[0] * ext[1] * ext[2];
+  if (batch * C * V == 0) return 0;
+  SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)batch * C * V * 4, s));
+  Grid *g = find_grid(m, ss);
+  if (!g || g->n_active == 0) return 0;
+  SCN_CHECK(in, "null feature pointer");
+  const long long total = g->n_active * C;
+  SCN_LAUNCH(k_s2d_fwd, cdiv(total, 256), 256, 0, s, in, out, g->coords, g->n_active, (int)C, ext[1], ext[2], V);
+  SCN_LAUNCHED();
+  return 0;
+}
+
+int scn_sparse_to_dense_cropped_backward(scn_metadata_t *m, const int64_t *ss, const int64_t *ext, float *d_in,
+                                         const float *d_out, int64_t C, int64_t batch, void *stream) {
+  SCN_CHECK(m && ss && ext, "null argument");
+  (void)batch;
+  Grid *g = find_grid(m, ss);
+  if (!g || g->n_active == 0) return 0;
+  SCN_CHECK(d_in && d_out, "null feature pointer");
+  const long long V = ext[0] * ext[1] * ext[2];
+  const long long total = g->n_active * C;
+  SCN_LAUNCH(k_s2d_bwd, cdiv(total, 256), 256, 0, (cudaStream_t)stream, d_in, d_out, g->coords, g->n_active,
+             (int)C, ext[1], ext[2], V);
+  SCN_LAUNCHED();
+  return 0;
+}
+
 int scn_sparse_to_dense_backward(scn_metadata_t *m, const int64_t *ss, float *d_in,
                                  const float *d_out, int64_t C, int64_t batch, void *stream) {
   SCN_CHECK(m && ss, "null argument");

@@ -228,6 +228,30 @@ static int roi_setup(scn_metadata_t *m, const int64_t *ss, const float *rois, in
   return 0;
 }
 
+// ext[0..2] = max active coordinate + 1 per axis, ext[3] = max batch index + 1 of the grid at `ss` - what
+// tools_3d_2d.py:16-18 derives on the host from a copy of every location; here one 16-byte read-back
+int scn_grid_extent(scn_metadata_t *m, const int64_t *ss, int64_t ext_out[4], void *stream) {
+  SCN_CHECK(m && ss && ext_out, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ext_out[0] = ext_out[1] = ext_out[2] = ext_out[3] = 0;
+  Grid *g = find_grid(m, ss);
+  if (!g || g->n_active == 0) return 0;
+  int32_t *ext = nullptr;
+  SCN_TRY(dev_alloc_t(&ext, 4, s));
+  SCN_CUDA(cudaMemsetAsync(ext, 0, 16, s));
+  int blocks = cdiv(g->n_active, 256);
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  SCN_LAUNCH(k_coord_extent, blocks, 256, 0, s, g->coords, g->n_active, ext);
+  SCN_LAUNCHED();
+  int32_t *h = (int32_t *)host_scratch(2);
+  SCN_CHECK(h, "pinned host scratch unavailable");
+  SCN_CUDA(cudaMemcpyAsync(h, ext, 16, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < 4; ++i) ext_out[i] = h[i];
+  dev_free(ext, s);
+  return 0;
+}
+
 int scn_roi_align_rotated_3d_forward(scn_metadata_t *m, const int64_t *ss, const float *feats, int64_t n_planes,
                                      const float *rois, int64_t n_rois, float spatial_scale, const int64_t *pooled,
                                      int sampling_ratio, float *out, void *stream) {

@@ -398,6 +398,32 @@ def SparseToDense_updateGradInput(spatial_size, m, input_features, d_input_featu
                                            input_features.size(1), dy.size(0), stream()))
 
 
+# B200 extension: the occupied extent of a grid and SparseToDense into the cropped volume (tools_3d_2d.py:7-48)
+def grid_extent(m, spatial_size):
+    """[max x + 1, max y + 1, max z + 1, max batch index + 1] of the active sites at `spatial_size`"""
+    ext = (c_int64 * 4)()
+    check(lib.scn_grid_extent(m._h, i64x3(spatial_size), ext, stream()))
+    return [int(v) for v in ext]
+
+
+def SparseToDense_cropped_updateOutput(spatial_size, extent, m, input_features, output_features, n_planes):
+    x = require_cuda_f32(input_features, "input_features")
+    batch = m.getBatchSize()
+    output_features.resize_(batch, int(n_planes), int(extent[0]), int(extent[1]), int(extent[2]))
+    check(lib.scn_sparse_to_dense_cropped_forward(m._h, i64x3(spatial_size), i64x3(extent), ptr(x) if x.dim() == 2 else None,
+                                                  ptr(output_features), int(n_planes), batch, stream()))
+
+
+def SparseToDense_cropped_updateGradInput(spatial_size, extent, m, input_features, d_input_features, d_output_features):
+    dy = require_cuda_f32(d_output_features, "d_output_features")
+    d_input_features.resize_as_(input_features)
+    d_input_features.zero_()
+    if input_features.dim() != 2:
+        return
+    check(lib.scn_sparse_to_dense_cropped_backward(m._h, i64x3(spatial_size), i64x3(extent), ptr(d_input_features), ptr(dy),
+                                                   input_features.size(1), dy.size(0), stream()))
+
+
 # ---- instrumentation -----------------------------------------------------------------------
 def launch_count():
     """kernels launched by libscn_b200 since load (bench.py `gpu_launches`)"""

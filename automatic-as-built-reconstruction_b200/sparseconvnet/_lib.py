@@ -112,6 +112,9 @@ _sig = {
     "scn_stream_wait_event": (c_int, [c_void_p, c_void_p]),
     "scn_sparse_to_dense_forward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                             c_void_p]),
+    "scn_grid_extent": (c_int, [c_void_p, I64P, I64P, c_void_p]),
+    "scn_sparse_to_dense_cropped_forward": (c_int, [c_void_p, I64P, I64P, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "scn_sparse_to_dense_cropped_backward": (c_int, [c_void_p, I64P, I64P, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "scn_sparse_to_dense_backward": (c_int, [c_void_p, I64P, c_void_p, c_void_p, c_int64, c_int64,
                                              c_void_p]),
     "scn_scale_inplace": (c_int, [c_void_p, c_float, c_int64, c_void_p]),

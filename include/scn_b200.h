@@ -253,6 +253,17 @@ int scn_sparse_to_dense_backward(scn_metadata_t *m, const int64_t *spatial_size,
                                  const float *d_out, int64_t n_planes, int64_t batch_size,
                                  void *stream);
 
+/* B200 extension for tools_3d_2d.py:7-48 (sparse_3d_to_dense_2d densifies all of [X, Y, Z] and slices out the occupied
+ * extent): scn_grid_extent returns ext = [max x + 1, max y + 1, max z + 1, max batch index + 1] of the grid (one 16-byte
+ * read-back instead of a host copy of every location), the _cropped_ calls densify straight into
+ * [batch, n_planes, ext0, ext1, ext2] = dense[:, :, :ext0, :ext1, :ext2] of the full tensor. */
+int scn_grid_extent(scn_metadata_t *m, const int64_t *spatial_size, int64_t ext_out[4], void *stream);
+int scn_sparse_to_dense_cropped_forward(scn_metadata_t *m, const int64_t *spatial_size, const int64_t *ext,
+                                        const float *in, float *out, int64_t n_planes, int64_t batch_size, void *stream);
+int scn_sparse_to_dense_cropped_backward(scn_metadata_t *m, const int64_t *spatial_size, const int64_t *ext,
+                                         float *d_in, const float *d_out, int64_t n_planes, int64_t batch_size,
+                                         void *stream);
+
 /* ---- layer-graph executor (B200 extension) -------------------------------------------
  * The reference runs the backbone as ~130 Python autograd Functions per direction
  * (sparseconvnet/{submanifoldConvolution,convolution,deconvolution,batchNormalization}.py, fpn_net.py:168-265);

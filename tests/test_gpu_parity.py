@@ -494,6 +494,41 @@ def test_sparse_to_dense(scn):
     d2 = scn.tools_3d_2d.sparse_3d_to_dense_2d(t)
     mx = (loc.max(0) + 1).tolist()
     assert list(d2.shape) == [2, 16, mx[0], mx[1], mx[2]]
+    assert torch.equal(d2, d[:, :, :mx[0], :mx[1], :mx[2]])        # the reference's slice of the full tensor
+
+
+def test_sparse_3d_to_dense_2d_cropped(scn):
+    """sparse_3d_to_dense_2d at the size of the ROI maps ([256,256,32], 128 planes, ~10k sites in a corner of the volume):
+    the cropped densify equals the reference's route (SparseToDense of the whole volume - 1.07 GB - then the slice to the
+    occupied extent, tools_3d_2d.py:25-28) bit for bit, forward and backward; both are timed"""
+    if scn.PREC != "fp32":
+        pytest.skip("precision-independent")
+    ss, C = [256, 256, 32], 128
+    rng = np.random.RandomState(3)
+    c = np.unique(np.stack([rng.randint(0, 60, 12000), rng.randint(0, 51, 12000), rng.randint(0, 10, 12000),
+                            np.zeros(12000, dtype=np.int64)], 1), axis=0)
+    t, _ = make_input(scn, c, ss, C=C)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    full = scn.SparseToDense(4, C)(t)                        # warm both paths once
+    crop = scn.tools_3d_2d.sparse_3d_to_dense_2d(t)
+    torch.cuda.synchronize()
+    ev[0].record()
+    full = scn.SparseToDense(4, C)(t)
+    ev[1].record()
+    crop = scn.tools_3d_2d.sparse_3d_to_dense_2d(t)
+    ev[2].record()
+    torch.cuda.synchronize()
+    mx = (c.max(0) + 1).tolist()
+    assert list(full.shape) == [1, C] + ss and list(crop.shape) == [1, C, mx[0], mx[1], mx[2]]
+    assert crop.is_contiguous() and torch.equal(crop, full[:, :, :mx[0], :mx[1], :mx[2]])
+    g = torch.randn_like(crop)
+    (gc,) = torch.autograd.grad(crop, t.features, g)
+    gfull = torch.zeros_like(full)
+    gfull[:, :, :mx[0], :mx[1], :mx[2]] = g
+    (gf,) = torch.autograd.grad(full, t.features, gfull)
+    assert torch.equal(gc, gf)
+    print("sparse_3d_to_dense_2d [1,128,256,256,32]: whole volume %.3f ms, cropped %.3f ms (incl. the extent read-back)"
+          % (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
 
 
 # ---------------------------------------------------------------------------------------------
