@@ -1,11 +1,11 @@
-"""Developer tool (GPU box, needs tools/libscn_exp_TRACE.so): clock64 timeline of CTA 0's roles in one
+"""Developer tool (GPU box, needs tools/_exp/libscn_TRACE.so: `tools/build_exp.sh TRACE`): clock64 timeline of CTA 0's roles in one
 gather-GEMM launch - where does a tile's time go?"""
 import ctypes
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["SCN_B200_LIB_PATH"] = os.path.join(ROOT, "tools", "libscn_exp_TRACE.so")
+os.environ["SCN_B200_LIB_PATH"] = os.path.join(ROOT, "tools", "_exp", "libscn_TRACE.so")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "automatic-as-built-reconstruction_b200"))
 import numpy as np  # noqa: E402
