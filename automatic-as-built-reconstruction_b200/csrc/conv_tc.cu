@@ -414,7 +414,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       if (use > 0) MBWS(bar_mempty + slot * 8, (use - 1) & 1, 0);
       int q = 0;
       if (lane == 0) SCN_TRACE(0, 1);
-      if (lane == 0) q = atomicAdd(sched, 1);
+      // a CTA's FIRST item is its block index (grid <= n_items; no atomic round trip - 0.5 us - before the kernel's first
+      // gather), the following ones come off the counter, which therefore counts from gridDim.x
+      if (lane == 0) q = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(sched, 1);
       q = __shfl_sync(0xffffffffu, q, 0);
       if (lane == 0) SCN_TRACE(0, 2);
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
