@@ -215,7 +215,7 @@ TileView make_view(const TileBook &tb, int k_flip) {
   v.perm = tb.perm;
   v.tile_mask = tb.tile_mask;
   v.tile_off = tb.tile_off;
-  v.order = tb.identity ? nullptr : tb.order;
+  v.order = tb.identity ? nullptr : reinterpret_cast<const int4 *>(tb.order);
   v.entries = tb.entries;
   return v;
 }

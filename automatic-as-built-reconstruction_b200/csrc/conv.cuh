@@ -12,7 +12,8 @@ struct TileView {            // device view of a TileBook, passed by value to ke
   const int32_t *perm;
   const uint32_t *tile_mask;
   const int32_t *tile_off;
-  const int32_t *order;      // tiles heaviest first (null: identity books)
+  const int4 *order;         // work-item order, tiles heaviest first: {tile, its offset mask, its first entry, 0} - ONE load
+                             // per work item instead of order -> (mask, offset) (null: identity books)
   const int32_t *entries;
 };
 

@@ -426,7 +426,9 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         break;
       }
       // heaviest tiles first: by the tile book's order (descending number of active offsets)
-      const int tile = tb.order ? tb.order[q % n_tiles] : n_tiles - 1 - q % n_tiles;
+      int4 rec = make_int4(n_tiles - 1 - q % n_tiles, 0, 0, -1);
+      if (tb.order) rec = tb.order[q % n_tiles];
+      const int tile = rec.x;
       if (lane == 0) hdr[1] = q - q % n_tiles + tile;
       if (tb.identity) {
 #pragma unroll
@@ -443,8 +445,8 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
         // the tile's row permutation (512 B) and its nE gather lists (nE x 512 B, contiguous in the tile
         // book) come in as two bulk copies that complete the slot's barrier - the loader never waits for
         // them (a per-list load loop cost ~2 us per list and paced the whole CTA)
-        const uint32_t mask = tb.tile_mask[tile];
-        const int e0 = tb.tile_off[tile];
+        const uint32_t mask = rec.w < 0 ? tb.tile_mask[tile] : (uint32_t)rec.y;
+        const int e0 = rec.w < 0 ? tb.tile_off[tile] : rec.z;
         const int nE = __popc(mask);
         if (mask & (1u << lane)) reinterpret_cast<int8_t *>(hdr + 2)[__popc(mask & ((1u << lane) - 1u))] = (int8_t)lane;
         if (lane == 0) hdr[0] = nE;

@@ -446,8 +446,8 @@ k_tile_masks(const uint32_t *__restrict__ row_mask, const int32_t *__restrict__ 
 // its work items out in this order - longest first, so the last wave consists of the shortest items.  The same block
 // also writes tile_off = exclusive scan of the per-tile offset counts (n_tiles + 1 entries; a few thousand tiles).
 __global__ void __launch_bounds__(1024)
-k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restrict__ order,
-             int32_t *__restrict__ n_entries, int32_t *__restrict__ tile_off) {
+k_tile_order(const int32_t *__restrict__ tile_pop, const uint32_t *__restrict__ tile_mask, int n_tiles,
+             int32_t *__restrict__ order, int32_t *__restrict__ n_entries, int32_t *__restrict__ tile_off) {
   pdl_sync();
   __shared__ int cnt[40], base[40];
   __shared__ int wsum[32];
@@ -463,7 +463,7 @@ k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restr
     *n_entries = entries;                         // the entry total the host reads back (= tile_off[n_tiles])
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) order[atomicAdd(&base[min(tile_pop[t], 39)], 1)] = t;
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) order[4 * atomicAdd(&base[min(tile_pop[t], 39)], 1)] = t;
   // exclusive scan, 1024 tiles per round
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int t0 = 0; t0 <= n_tiles; t0 += 1024) {
@@ -493,6 +493,14 @@ k_tile_order(const int32_t *__restrict__ tile_pop, int n_tiles, int32_t *__restr
     __syncthreads();
     if (threadIdx.x == 1023) carry = c + wsum[wid] + inc;
     __syncthreads();
+  }
+  // the work-item records: {tile, mask, first entry, 0} (one 16-byte load per work item in the gather-GEMM's loader)
+  __syncthreads();
+  for (int p = threadIdx.x; p < n_tiles; p += blockDim.x) {
+    const int t = order[4 * p];
+    order[4 * p + 1] = (int32_t)tile_mask[t];
+    order[4 * p + 2] = tile_off[t];
+    order[4 * p + 3] = 0;
   }
 }
 
@@ -543,8 +551,8 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   SCN_TRY(dev_alloc_t(&pop, (size_t)tb.n_tiles + 1, s));
   SCN_LAUNCH(k_tile_masks, tb.n_tiles, TILE_M, 0, s, mask, idx, n_rows, tb.perm, tb.tile_mask, pop);
   SCN_LAUNCHED();
-  SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles, s));
-  SCN_LAUNCH(k_tile_order, 1, 1024, 0, s, pop, tb.n_tiles, tb.order, meta_slot, tb.tile_off);
+  SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles * 4, s));
+  SCN_LAUNCH(k_tile_order, 1, 1024, 0, s, pop, tb.tile_mask, tb.n_tiles, tb.order, meta_slot, tb.tile_off);
   SCN_LAUNCHED();
   dev_free(mask, s);
   dev_free(key, s);

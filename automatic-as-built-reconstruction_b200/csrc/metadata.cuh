@@ -71,7 +71,8 @@ struct TileBook {
   int32_t *perm = nullptr;        // [n_tiles*TILE_M] stationary row per slot (-1 pad)
   uint32_t *tile_mask = nullptr;  // [n_tiles] union of active offsets
   int32_t *tile_off = nullptr;    // [n_tiles+1] first entry of the tile
-  int32_t *order = nullptr;       // [n_tiles] tiles by descending number of active offsets (work-item order of the gather-GEMM)
+  int32_t *order = nullptr;       // [n_tiles][4] work-item order of the gather-GEMM: tiles by descending number of active
+                                  // offsets, each with its mask and first entry {tile, mask, tile_off[tile], 0}
   int32_t *entries = nullptr;     // [n_entries*TILE_M] partner rows
 };
 
