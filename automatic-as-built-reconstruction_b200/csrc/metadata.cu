@@ -504,6 +504,109 @@ k_tile_order(const int32_t *__restrict__ tile_pop, const uint32_t *__restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The whole of tilebook_phase1 in ONE block for books of at most SMALL_ROWS rows (the five smallest scales of the
+// backbone: their books went through ~14 launches of 3 - 5 us each - masks, three radix passes of histogram / scan /
+// scatter, tile masks, tile order - i.e. launch latency, not work).  Same results as the separate kernels: the stable
+// radix sort by key equals a sort by (key, row), done here as a bitonic sort of 64-bit words in shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int SMALL_ROWS = 8192;          // (16384 - the backbone's scale 4 - was measured: one block is then SLOWER than the
+                                          // parallel kernels, build 3.86 -> 4.46 ms)
+constexpr int SMALL_SMEM = SMALL_ROWS * 8 + SMALL_ROWS * 4;       // sort words + masks
+
+__global__ void __launch_bounds__(1024)
+k_tilebook_small(const int32_t *__restrict__ T, int n, int K, int key_shift, const int32_t *__restrict__ pair_off,
+                 int grouping, int n_tiles, int32_t *__restrict__ perm, uint32_t *__restrict__ tile_mask,
+                 int32_t *__restrict__ tile_off, int32_t *__restrict__ order, int32_t *__restrict__ n_entries) {
+  pdl_sync();
+  extern __shared__ __align__(16) uint8_t small_smem[];
+  unsigned long long *sk = reinterpret_cast<unsigned long long *>(small_smem);      // [P] (key << 32 | row)
+  uint32_t *sm = reinterpret_cast<uint32_t *>(small_smem + (size_t)SMALL_ROWS * 8);   // [n] mask of row r
+  __shared__ int s_cnt[MAX_K], s_rank[MAX_K];
+  __shared__ int cnt[40], base[40];
+  __shared__ int s_pop[SMALL_ROWS / TILE_M + 1], s_off[SMALL_ROWS / TILE_M + 2];
+  const int tid = threadIdx.x;
+  if (pair_off) {
+    if (tid < K) s_cnt[tid] = pair_off[tid + 1] - pair_off[tid];
+    __syncthreads();
+    if (tid < K) {
+      int rk = 0;
+      const int c = s_cnt[tid];
+      for (int j = 0; j < K; ++j) rk += (s_cnt[j] > c || (s_cnt[j] == c && j < tid)) ? 1 : 0;
+      s_rank[tid] = rk;
+    }
+  }
+  if (tid < 40) cnt[tid] = 0;
+  __syncthreads();
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int r = tid; r < P; r += 1024) {
+    uint32_t m = 0, km = 0;
+    if (r < n) {
+      for (int k = 0; k < K; ++k)
+        if (T[(long long)k * n + r] >= 0) {
+          m |= (1u << k);
+          km |= (1u << (pair_off ? s_rank[k] : k));
+        }
+      sm[r] = m;
+      sk[r] = ((unsigned long long)(km >> key_shift) << 32) | (unsigned)r;
+    } else {
+      sk[r] = ~0ull;                                   // padding sorts to the end
+    }
+  }
+  __syncthreads();
+  if (grouping) {
+    for (int k2 = 2; k2 <= P; k2 <<= 1)
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P; i += 1024) {
+          const int l = i ^ j;
+          if (l > i) {
+            const unsigned long long a = sk[i], b = sk[l];
+            const bool up = (i & k2) == 0;
+            if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+  }
+  // permutation (padded with -1), per-tile union masks and offset counts: one warp per tile
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int t = wid; t < n_tiles; t += 32) {
+    uint32_t u = 0;
+#pragma unroll
+    for (int q = 0; q < TILE_M / 32; ++q) {
+      const int slot = t * TILE_M + q * 32 + lane;
+      int row = -1;
+      if (slot < n) { row = (int)(unsigned)sk[slot]; u |= sm[row]; }
+      perm[slot] = row;
+    }
+    u = __reduce_or_sync(0xffffffffu, u);
+    if (lane == 0) {
+      tile_mask[t] = u;
+      s_pop[t] = __popc(u);
+      atomicAdd(&cnt[min(__popc(u), 39)], 1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0, entries = 0;
+    for (int p = 39; p >= 0; --p) { base[p] = run; run += cnt[p]; entries += p * cnt[p]; }
+    *n_entries = entries;
+    int acc = 0;                                       // (at most 64 tiles)
+    for (int t = 0; t < n_tiles; ++t) { s_off[t] = acc; acc += s_pop[t]; }
+    s_off[n_tiles] = acc;
+  }
+  __syncthreads();
+  for (int t = tid; t <= n_tiles; t += 1024) tile_off[t] = s_off[t];
+  for (int t = tid; t < n_tiles; t += 1024) {
+    const int p = atomicAdd(&base[min(s_pop[t], 39)], 1);
+    order[4 * p] = t;
+    order[4 * p + 1] = (int32_t)tile_mask[t];
+    order[4 * p + 2] = s_off[t];
+    order[4 * p + 3] = 0;
+  }
+}
+
 __global__ void __launch_bounds__(TILE_M)
 k_fill_entries(const int32_t *__restrict__ T, long long n, const int32_t *__restrict__ perm,
                const uint32_t *__restrict__ tile_mask, const int32_t *__restrict__ tile_off,
@@ -530,6 +633,25 @@ static int tilebook_phase1(TileBook &tb, const int32_t *T, int K, int64_t n_rows
   tb.n_tiles = cdiv(n_rows, TILE_M);
   if (tb.n_tiles == 0) {
     SCN_CUDA(cudaMemsetAsync(meta_slot, 0, 4, s));
+    return 0;
+  }
+  static const int sort_bits_small = getenv("SCN_B200_SORT_BITS") ? atoi(getenv("SCN_B200_SORT_BITS")) : 27;
+  static const bool small_path = !(getenv("SCN_B200_SMALL_BOOKS") && atoi(getenv("SCN_B200_SMALL_BOOKS")) == 0);
+  if (small_path && n_rows <= SMALL_ROWS) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      SCN_CUDA(cudaFuncSetAttribute((const void *)k_tilebook_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+      attr_set = true;
+    }
+    const int kb = K < sort_bits_small ? K : sort_bits_small;
+    SCN_TRY(dev_alloc_t(&tb.perm, (size_t)tb.n_tiles * TILE_M, s));
+    SCN_TRY(dev_alloc_t(&tb.tile_mask, (size_t)tb.n_tiles, s));
+    SCN_TRY(dev_alloc_t(&tb.tile_off, (size_t)tb.n_tiles + 1, s));
+    SCN_TRY(dev_alloc_t(&tb.order, (size_t)tb.n_tiles * 4, s));
+    SCN_LAUNCH(k_tilebook_small, 1, 1024, (size_t)SMALL_SMEM, s, T, (int)n_rows, K, K - kb, pair_off,
+               (g_tile_grouping && K > 1 && n_rows > 4 * TILE_M) ? 1 : 0, tb.n_tiles, tb.perm, tb.tile_mask, tb.tile_off,
+               tb.order, meta_slot);
+    SCN_LAUNCHED();
     return 0;
   }
   uint32_t *mask = nullptr, *key = nullptr;
