@@ -35,7 +35,8 @@ class GradBucket(object):
     GradBucket(params, module=net) with a module that runs through the layer-graph executor (FPN_Net): the bucket
     is laid out in the order the reverse sweep finishes the gradients and attached to the graph as its gradient
     SINK - `scn_graph_backward_marked` writes every weight / BN gradient straight into its bucket range (no
-    AccumulateGrad pass) and records an event when each of `n_chunks` ranges is final.  `allreduce_mean()` then
+    AccumulateGrad pass) and records an event when each of `n_chunks` ranges is final (range ends at 1/2, 3/4, 7/8 ...
+    of the bytes: the last range - the one collective nothing hides - is small).  `allreduce_mean()` then
     issues one NCCL all-reduce per range on a side stream behind those events, so the collective of the deep layers
     runs under the rest of the backward pass (DistributedDataParallel's overlapped buckets,
     tools/train_net_sparse3d.py:64-69); the main stream joins at the end.  Dead-branch parameters are never
@@ -43,7 +44,7 @@ class GradBucket(object):
     Direct writes OVERWRITE: call `zero()` (or nothing) between steps, not gradient accumulation over several
     backward passes - for that, build the bucket without `module`."""
 
-    def __init__(self, params, module=None, n_chunks=4):
+    def __init__(self, params, module=None, n_chunks=6):
         params = [p for p in params if p.requires_grad]
         assert params, "no trainable parameters"
         graph = module._layer_graph() if (module is not None and hasattr(module, "_layer_graph")) else None
@@ -54,12 +55,18 @@ class GradBucket(object):
             outside = [p for p in params if id(p) not in last]
             params = inside + outside
             total_in = sum(_pad4(p.numel()) for p in inside)
-            target, off, start, k = (total_in + n_chunks - 1) // max(n_chunks, 1), 0, 0, 1
+            # range ends at 1/2, 3/4, 7/8, ... of the bytes: the reverse sweep finishes the deep layers - most of the
+            # bytes - first and the small shallow weights last, so the LAST range (the only collective nothing hides)
+            # carries ~3 % of the bucket instead of a quarter
+            bounds = [total_in - (total_in >> k) for k in range(1, max(n_chunks, 1))] + [total_in]
+            off, start, k = 0, 0, 0
             for p in inside:
                 off += _pad4(p.numel())
-                if off >= min(k * target, total_in) or p is inside[-1]:
+                if off >= bounds[k] or p is inside[-1]:
                     self.chunks.append((start, off, last[id(p)]))
-                    start, k = off, k + 1
+                    start = off
+                    while k < len(bounds) - 1 and off >= bounds[k]:
+                        k += 1
         self.params = params
         dev, dt = params[0].device, params[0].dtype
         n = sum(_pad4(p.numel()) for p in params)       # every range starts 16-byte aligned (vector stores)
@@ -124,6 +131,9 @@ class GradBucket(object):
         if world == 1:
             return None
         self.check_views()
+        # NCCL averages inside the collective (no pass over the bucket afterwards); other backends: sum, then scale
+        avg = self.flat.is_cuda and dist.get_backend(group) == "nccl"
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         if fired and self._events and not async_op:
             # overlapped: one collective per finished range, each behind its event, on a side stream
             if self._side is None:
@@ -132,18 +142,20 @@ class GradBucket(object):
             for (a, b, _), ev in zip(self.chunks, self._events):
                 _lib.check(_lib.lib.scn_stream_wait_event(self._side.cuda_stream, ev))
                 with torch.cuda.stream(self._side):
-                    works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+                    works.append(dist.all_reduce(self.flat[a:b], op=op, group=group, async_op=True))
                 end = b
             if end < self.flat.numel():       # parameters outside the graph: final once the main stream gets here
-                works.append(dist.all_reduce(self.flat[end:], op=dist.ReduceOp.SUM, group=group, async_op=True))
+                works.append(dist.all_reduce(self.flat[end:], op=op, group=group, async_op=True))
             for w in works:
                 w.wait()                      # the current stream waits for the collective (no host block)
-            self._scale(1.0 / world)
+            if not avg:
+                self._scale(1.0 / world)
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        work = dist.all_reduce(self.flat, op=op, group=group, async_op=async_op)
         if async_op:
-            return _Pending(self, work, world)
-        self._scale(1.0 / world)
+            return _Pending(self, work, 1 if avg else world)
+        if not avg:
+            self._scale(1.0 / world)
         return None
 
     def _scale(self, alpha):
@@ -159,7 +171,8 @@ class _Pending(object):
 
     def wait(self):
         self.work.wait()
-        self.bucket._scale(1.0 / self.world)
+        if self.world != 1:
+            self.bucket._scale(1.0 / self.world)
 
 
 def broadcast_parameters(module, src=0, group=None):
