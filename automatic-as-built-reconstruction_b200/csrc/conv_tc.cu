@@ -330,7 +330,7 @@ template <int DEPTH, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
               float *__restrict__ Y, int Kd, int N, int ldn, int K, long long n_rows, TileView tb, uint32_t acc_cols,
-              float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched, int ms) {
+              float *__restrict__ Ypart, int n_items, int splits, int NSB, int *__restrict__ sched, int ms, int static_first) {
   // DEPTH + 2 stages of gathered rows (16 KB each)
   constexpr int NSA = DEPTH + 2;
   pdl_trigger();
@@ -416,7 +416,7 @@ k_osgemm_tf32(const float *__restrict__ X, const float *__restrict__ Wp, const f
       if (lane == 0) SCN_TRACE(0, 1);
       // a CTA's FIRST item is its block index (grid <= n_items; no atomic round trip - 0.5 us - before the kernel's first
       // gather), the following ones come off the counter, which therefore counts from gridDim.x
-      if (lane == 0) q = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(sched, 1);
+      if (lane == 0) q = (it == 0 && static_first) ? (int)blockIdx.x : (static_first ? (int)gridDim.x : 0) + atomicAdd(sched, 1);
       q = __shfl_sync(0xffffffffu, q, 0);
       if (lane == 0) SCN_TRACE(0, 2);
       int32_t(*sIdx)[TILE_M] = meta_idx(slot);
@@ -1258,10 +1258,11 @@ int osgemm_tc(const float *X, const float *W, const float *bias, float *Y, int K
   if (g_gemm_grid_limit > 0 && grid > g_gemm_grid_limit) grid = g_gemm_grid_limit;
   int *sched = nullptr;
   if (sched_counters(&sched, s)) return -1;
+  static const int static_first = getenv("SCN_B200_GEMM_STATIC_FIRST") ? atoi(getenv("SCN_B200_GEMM_STATIC_FIRST")) : 1;
   prof_begin(PROF_GEMM, s);
 #define SCN_OSGEMM_LAUNCH(D, T3)                                                                              \
   SCN_LAUNCH_GEMM((k_osgemm_tf32<D, T3>), grid, gemm_threads(T3), L.total, s, X, wp, bias, Y, Kd, NW, N, Kb, n_rows, tv, cols, ypart, \
-                                                                n_items, splits, nsb, sched, ms)
+                                                                n_items, splits, nsb, sched, ms, static_first)
 #define SCN_OSGEMM_DEPTH(T3)                                                                                  \
   switch (depth) {                                                                                            \
     case 6: SCN_OSGEMM_LAUNCH(6, T3); break;                                                                  \
