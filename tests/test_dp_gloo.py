@@ -53,3 +53,28 @@ def test_grad_bucket_allreduce_world2():
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert out[0][0] and out[1][0]
         assert out[0][1] == [0, 2, 4] and out[1][1] == [1, 3]
+
+
+def test_gradient_ranges_end_at_geometric_fractions():
+    """GradBucket(module=net): the ranges the reverse sweep finishes end at 1/2, 3/4, 7/8 ... of the graph's gradient
+    bytes (the last, un-hidden collective is small), cover them contiguously and finish in bucket order (host logic
+    only: no GPU needed)"""
+    import torch
+    import sparseconvnet as scn
+    torch.manual_seed(0)
+    net = scn.FPN_Net([512] * 3, 3, ["xyz", "color", "normal"], 1, [32, 64, 64, 128, 128, 128, 256, 256, 256],
+                      nPlaneM=128, residual_blocks=True, fpn_scales_from_top=[4, 3, 2, 1], roi_scales_from_top=(4, 3),
+                      downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8],
+                      rpn_map_sizes=[[32] * 3, [16] * 3, [8] * 3, [4] * 3], voxel_scale=50,
+                      rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6], bn_momentum=0.95, track_running_stats=False)
+    bucket = scn.GradBucket(net.parameters(), module=net)
+    ch = bucket.chunks
+    assert 2 <= len(ch) <= 6
+    assert ch[0][0] == 0 and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+    ops = [c[2] for c in ch]
+    assert ops == sorted(ops, reverse=True)
+    total = ch[-1][1]
+    assert ch[0][1] >= total // 2                                  # the first range: at least half of the bytes
+    assert ch[-1][1] - ch[-1][0] <= total // 8                     # the last one: a small tail
+    inside = set(id(p) for p in net._layer_graph().grad_params)
+    assert total == sum((p.numel() + 3) // 4 * 4 for p in net.parameters() if id(p) in inside)
