@@ -210,9 +210,8 @@ k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (VEC) {
     const long long nq = total >> 2;
-    for (; i < nq; i += st) {
-      const int c = (int)((i << 2) % C);
-      const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + i);
+    auto apply4 = [&](long long q, const float4 x) {
+      const int c = (int)((q << 2) % C);
       const float4 w = *reinterpret_cast<const float4 *>(coef + c);
       const float4 b = *reinterpret_cast<const float4 *>(coef + C + c);
       float4 y;
@@ -220,8 +219,17 @@ k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, 
       y.y = lrelu(fmaf(x.y, w.y, b.y), leak);
       y.z = lrelu(fmaf(x.z, w.z, b.z), leak);
       y.w = lrelu(fmaf(x.w, w.w, b.w), leak);
-      reinterpret_cast<float4 *>(Y)[i] = y;
+      reinterpret_cast<float4 *>(Y)[q] = y;
+    };
+    // four independent 128-bit loads in flight per thread (one per iteration left a full grid at 32 KB in flight per SM)
+    for (; i + 3 * st < nq; i += 4 * st) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4 *>(X) + i);
+      const float4 x1 = __ldg(reinterpret_cast<const float4 *>(X) + i + st);
+      const float4 x2 = __ldg(reinterpret_cast<const float4 *>(X) + i + 2 * st);
+      const float4 x3 = __ldg(reinterpret_cast<const float4 *>(X) + i + 3 * st);
+      apply4(i, x0); apply4(i + st, x1); apply4(i + 2 * st, x2); apply4(i + 3 * st, x3);
     }
+    for (; i < nq; i += st) apply4(i, __ldg(reinterpret_cast<const float4 *>(X) + i));
   } else {
     for (; i < total; i += st) {
       const int c = (int)(i % C);
@@ -256,18 +264,14 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (VEC) {
     const long long nq = total >> 2;
-    for (; i < nq; i += st) {
-      const int c = (int)((i << 2) % C);
-      const float4 x = __ldg(reinterpret_cast<const float4 *>(X) + i);
-      float4 y;
+    auto bwd4 = [&](long long q, const float4 x, const float4 yo, const float4 d, const float4 r) {
+      const int c = (int)((q << 2) % C);
+      float4 y = yo;
       if (recompute) {
         const float4 w = *reinterpret_cast<const float4 *>(aff + c);
         const float4 b = *reinterpret_cast<const float4 *>(aff + C + c);
         y = make_float4(fmaf(x.x, w.x, b.x), fmaf(x.y, w.y, b.y), fmaf(x.z, w.z, b.z), fmaf(x.w, w.w, b.w));
-      } else {
-        y = __ldg(reinterpret_cast<const float4 *>(Yo) + i);
       }
-      const float4 d = __ldg(reinterpret_cast<const float4 *>(dY) + i);
       const float4 mu = *reinterpret_cast<const float4 *>(smean + c);
       const float4 gm = *reinterpret_cast<const float4 *>(coef + c);
       const float4 kk = *reinterpret_cast<const float4 *>(coef + C + c);
@@ -277,12 +281,22 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
       o.y = (d.y * (y.y > 0.f ? 1.f : leak) - gm.y - (x.y - mu.y) * kk.y) * sc.y;
       o.z = (d.z * (y.z > 0.f ? 1.f : leak) - gm.z - (x.z - mu.z) * kk.z) * sc.z;
       o.w = (d.w * (y.w > 0.f ? 1.f : leak) - gm.w - (x.w - mu.w) * kk.w) * sc.w;
-      if (R) {   // second gradient of the same value (skip connection), may alias dX
-        const float4 r = reinterpret_cast<const float4 *>(R)[i];
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
-      reinterpret_cast<float4 *>(dX)[i] = o;
+      if (R) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }   // second gradient of the same value (skip connection), may alias dX
+      reinterpret_cast<float4 *>(dX)[q] = o;
+    };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld = [&](const float *p, long long q) { return p ? __ldg(reinterpret_cast<const float4 *>(p) + q) : z4; };
+    auto ldr = [&](long long q) { return R ? reinterpret_cast<const float4 *>(R)[q] : z4; };   // (R may alias dX: plain load)
+    // two elements per iteration: 4 - 8 independent 128-bit loads in flight per thread
+    for (; i + st < nq; i += 2 * st) {
+      const float4 xa = ld(X, i), xb = ld(X, i + st);
+      const float4 ya = ld(recompute ? nullptr : Yo, i), yb = ld(recompute ? nullptr : Yo, i + st);
+      const float4 da = ld(dY, i), db = ld(dY, i + st);
+      const float4 ra = ldr(i), rb = ldr(i + st);
+      bwd4(i, xa, ya, da, ra);
+      bwd4(i + st, xb, yb, db, rb);
     }
+    for (; i < nq; i += st) bwd4(i, ld(X, i), ld(recompute ? nullptr : Yo, i), ld(dY, i), ldr(i));
   } else {
     for (; i < total; i += st) {
       const int c = (int)(i % C);
