@@ -325,14 +325,14 @@ static int stats_grid(long long n, int rows_per_iter) {
 // memset is launched per call.
 struct BnState { double *buf[2]; int used[2]; int k; };
 static std::mutex g_bn_mu;
-static std::vector<std::pair<cudaStream_t, BnState *>> g_bn;
+static std::vector<std::pair<StreamKey, BnState *>> g_bn;
 constexpr int BN_MAX_C = 4096;
 
 static int bn_buffers(cudaStream_t s, int C, double **cur, double **other, int *other_used) {
   std::lock_guard<std::mutex> lk(g_bn_mu);
   BnState *st = nullptr;
   for (auto &e : g_bn)
-    if (e.first == s) { st = e.second; break; }
+    if (e.first == stream_key(s)) { st = e.second; break; }
   if (!st) {
     st = new BnState();
     for (int i = 0; i < 2; ++i) {
@@ -341,7 +341,7 @@ static int bn_buffers(cudaStream_t s, int C, double **cur, double **other, int *
       st->used[i] = 0;
     }
     st->k = 0;
-    g_bn.emplace_back(s, st);
+    g_bn.emplace_back(stream_key(s), st);
   }
   const int a = st->k & 1, b = a ^ 1;
   *cur = st->buf[a];

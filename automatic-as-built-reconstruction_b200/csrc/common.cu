@@ -48,7 +48,6 @@ void prof_end_(int cls, cudaStream_t s, double bytes, double flops) {
   g_prof_segs.push_back(sg);
 }
 
-static std::once_flag g_pool_once;
 static int g_num_sms = 0;
 
 static void init_pool() {
@@ -81,13 +80,21 @@ static void init_pool() {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
+// once per DEVICE (a process may drive several): the pool attributes and the pre-sizing belong to the current device's pool
+static std::once_flag g_pool_once_dev[64];
+static void ensure_pool() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(g_pool_once_dev[dev & 63], init_pool);
+}
+
 int num_sms() {
-  std::call_once(g_pool_once, init_pool);
+  ensure_pool();
   return g_num_sms > 0 ? g_num_sms : 148;
 }
 
 int dev_alloc(void **p, size_t bytes, cudaStream_t s) {
-  std::call_once(g_pool_once, init_pool);
+  ensure_pool();
   *p = nullptr;
   SCN_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, s));
   return 0;
@@ -99,16 +106,16 @@ void dev_free(void *p, cudaStream_t s) {
 
 struct WsBuf { void *p = nullptr; size_t cap = 0; };
 static std::mutex g_ws_mu;
-static std::vector<std::pair<cudaStream_t, WsBuf *>> g_ws;   // a handful of streams: linear search
+static std::vector<std::pair<StreamKey, WsBuf *>> g_ws;   // a handful of streams: linear search
 
 int workspace(void **p, int slot, size_t bytes, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
   WsBuf *bufs = nullptr;
   for (auto &e : g_ws)
-    if (e.first == s) { bufs = e.second; break; }
+    if (e.first == stream_key(s)) { bufs = e.second; break; }
   if (!bufs) {
     bufs = new WsBuf[WS_SLOTS];
-    g_ws.emplace_back(s, bufs);
+    g_ws.emplace_back(stream_key(s), bufs);
   }
   WsBuf &b = bufs[slot];
   if (b.cap < bytes) {
@@ -124,32 +131,32 @@ int workspace(void **p, int slot, size_t bytes, cudaStream_t s) {
   return 0;
 }
 
-static std::vector<std::pair<cudaStream_t, int *>> g_sched;
+static std::vector<std::pair<StreamKey, int *>> g_sched;
 
 int sched_counters(int **p, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
   for (auto &e : g_sched)
-    if (e.first == s) { *p = e.second; return 0; }
+    if (e.first == stream_key(s)) { *p = e.second; return 0; }
   int *d = nullptr;
   SCN_CUDA(cudaMalloc((void **)&d, 64));
   SCN_CUDA(cudaMemset(d, 0, 64));          // synchronous: visible to every stream that follows
-  g_sched.emplace_back(s, d);
+  g_sched.emplace_back(stream_key(s), d);
   *p = d;
   return 0;
 }
 
 static std::mutex g_side_mu;
-static std::vector<std::pair<cudaStream_t, SideStream *>> g_side;
+static std::vector<std::pair<StreamKey, SideStream *>> g_side;
 
 int side_stream(cudaStream_t s, SideStream **out) {
   std::lock_guard<std::mutex> lk(g_side_mu);
   for (auto &e : g_side)
-    if (e.first == s) { *out = e.second; return 0; }
+    if (e.first == stream_key(s)) { *out = e.second; return 0; }
   SideStream *ss = new SideStream();
   SCN_CUDA(cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking));
   SCN_CUDA(cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming));
   SCN_CUDA(cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming));
-  g_side.emplace_back(s, ss);
+  g_side.emplace_back(stream_key(s), ss);
   *out = ss;
   return 0;
 }
@@ -282,7 +289,7 @@ struct ScanState {
   unsigned long long epoch = 0;
 };
 static std::mutex g_scan_mu;
-static std::vector<std::pair<cudaStream_t, ScanState *>> g_scan;
+static std::vector<std::pair<StreamKey, ScanState *>> g_scan;
 
 static int scan_launch(const int32_t *in, int32_t *out, long long n, bool flags, cudaStream_t s) {
   const long long n_out = n + 1;
@@ -291,10 +298,10 @@ static int scan_launch(const int32_t *in, int32_t *out, long long n, bool flags,
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     for (auto &e : g_scan)
-      if (e.first == s) { st = e.second; break; }
+      if (e.first == stream_key(s)) { st = e.second; break; }
     if (!st) {
       st = new ScanState();
-      g_scan.emplace_back(s, st);
+      g_scan.emplace_back(stream_key(s), st);
     }
   }
   // (a stream's calls are made by one host thread at a time: the state below is only touched by that thread)

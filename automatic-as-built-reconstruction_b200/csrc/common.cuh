@@ -80,6 +80,20 @@ int side_stream(cudaStream_t s, SideStream **out);
 int side_fork(cudaStream_t s, SideStream *ss);
 int side_join(cudaStream_t s, SideStream *ss);
 
+// Key of all per-stream state (workspaces, scheduler counters, companion streams, scan descriptors, BN sum buffers):
+// the stream handle AND the current device - the default-stream handle is the same value on every device, so two
+// devices driven from one process must not share (or free) each other's buffers.
+struct StreamKey {
+  int dev;
+  cudaStream_t s;
+  bool operator==(const StreamKey &o) const { return dev == o.dev && s == o.s; }
+};
+inline StreamKey stream_key(cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return StreamKey{dev, s};
+}
+
 // pinned host scratch for count read-backs (per thread)
 int64_t *host_scratch(size_t n_int64);
 

@@ -588,14 +588,28 @@ static int conv_backward_common(RuleBook *rb, bool dx_stationary_out, const floa
     SCN_TRY(side_stream(s, &ss));
     SCN_TRY(side_fork(s, ss));
   }
+  // the caller's stream must never run ahead of a forked companion stream, also when a launch below fails: the guard
+  // joins on every exit path unless the join was done (or handed to the sweep's marks) explicitly
+  struct JoinGuard {
+    cudaStream_t s;
+    SideStream *ss;
+    bool armed;
+    ~JoinGuard() { if (armed) side_join(s, ss); }
+  } join_guard{s, ss, fork};
   if (d_in)
     SCN_TRY(osgemm(d_out, weight, nullptr, d_in, Cout, Cin, tb, precision, /*transpose_w=*/1, s, mirror ? rb->K - 1 : -1,
                    weight_tag));
   if (d_weight) SCN_TRY(weight_grad(in, d_out, d_weight, Cin, Cout, rb, xcol, ycol, precision, fork ? ss->stream : s));
   // (layer-graph reverse sweep: the join is deferred to the sweep's progress marks / its end, so the weight
   // gradients of the latency-bound coarse scales run under the following layers instead of holding them up)
-  if (fork && !g_defer_dw_join) SCN_TRY(side_join(s, ss));
-  if (fork && g_defer_dw_join) g_dw_join_pending = true;
+  if (fork && !g_defer_dw_join) {
+    join_guard.armed = false;
+    SCN_TRY(side_join(s, ss));
+  }
+  if (fork && g_defer_dw_join) {
+    join_guard.armed = false;
+    g_dw_join_pending = true;
+  }
   SCN_TRY(bias_grad(d_out, d_bias, n_dout_rows, Cout, s));
   return 0;
 }
