@@ -247,6 +247,9 @@ class GraphFunction(Function):
                                               ctypes.byref(macs)))
         sparseconvnet.forward_pass_multiplyAdd_count += macs.value
         ctx.graph, ctx.metadata_, ctx.keep = graph, metadata, (x0, arena, bn_save, outs)
+        # the backward pass re-reads the live Parameters (not saved copies): remember their version counters so that an
+        # in-place edit between forward and backward is an error, as it is for tensors saved by autograd
+        ctx.param_versions = [t._version for t in graph.grad_params]
         ctx.rows, ctx.vals, ctx.off, ctx.total = rows, vals, off, total
         ctx.set_materialize_grads(False)
         return tuple(outs[v] for v in graph.outputs)
@@ -259,6 +262,10 @@ class GraphFunction(Function):
                                "after the first backward (retain_graph=True is not supported; set use_layer_graph = False "
                                "on the network for that)")
         x0, arena, bn_save, outs = ctx.keep
+        for t, v in zip(graph.grad_params, ctx.param_versions):
+            if t._version != v:
+                raise RuntimeError("sparseconvnet layer graph: a parameter was modified in place between the forward and "
+                                   "the backward pass (its gradient would be computed with the new values)")
         rows, nv = ctx.rows, len(graph.values)
         # gradient buffers: one arena laid out like the value arena, separate buffers for the outputs
         garena = x0.new_empty(max(ctx.total, 1))

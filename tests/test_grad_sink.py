@@ -91,3 +91,21 @@ def test_shared_parameter_falls_back_to_per_layer_path():
     v = g.emit(seq, 0)
     with pytest.raises(G.Unsupported):
         g.finalize([v])
+
+
+def test_layer_graph_guards_its_backward():
+    """the one-call backward re-reads live Parameters and releases the step's arena: an in-place parameter edit between
+    forward and backward, and a second backward, are errors (not silently wrong gradients)"""
+    import sparseconvnet as scn
+    net, locs, feats = _net_and_batch(scn)
+    rpn, roi = net([locs, feats])
+    loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
+    with torch.no_grad():
+        net.layers_in[1].weight.mul_(1.0)                              # in place: bumps the version counter
+    with pytest.raises(RuntimeError, match="modified in place"):
+        loss.backward()
+    rpn, roi = net([locs, feats])
+    loss = sum((m.features ** 2).sum() for m in list(rpn) + list(roi))
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
