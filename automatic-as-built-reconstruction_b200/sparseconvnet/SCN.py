@@ -445,3 +445,22 @@ def prof_read():
         check(lib.scn_prof_read(i, v))
         out[name] = {"regions": int(v[0]), "ms": v[1], "bytes": v[2], "flops": v[3]}
     return out
+
+
+# ---- extension entry points off the sparse3d path --------------------------------------------
+_OP_SUFFIXES = ("_updateOutput", "_updateGradInput", "_backward", "_accGradParameters")
+
+
+def __getattr__(name):
+    """The reference's extension also exports the pooling / full / randomized-stride / permutohedral /
+    BL-layer entry points (pybind.cpp:34-235).  None of them is on the sparse3d path; a
+    layer file that reaches for one gets a loud NotImplementedError at call time instead of an AttributeError
+    at some unrelated line."""
+    if name.endswith(_OP_SUFFIXES) and not name.startswith("_"):
+        def _off_path(*a, **k):
+            raise NotImplementedError("sparseconvnet.SCN.%s is not on the sparse3d backbone path (SURVEY.md "
+                                      "section 8) and is not implemented in the B200 build" % name)
+        _off_path.__name__ = name
+        _off_path.off_path = True
+        return _off_path
+    raise AttributeError("module 'sparseconvnet.SCN' has no attribute %r" % name)

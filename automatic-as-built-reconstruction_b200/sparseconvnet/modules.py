@@ -364,7 +364,9 @@ class _StridedBase(Module):
         if len(set(self.filter_size.tolist())) == 1 and len(set(self.filter_stride.tolist())) == 1:
             s = "%d/%d" % (self.filter_size[0].item(), self.filter_stride[0].item())
         else:
-            s = "%s/%s" % (_size_repr(self.filter_size), _size_repr(self.filter_stride))
+            # the reference prints both tuples in full here, e.g. "C(1,1,8)/(1,1,1)" (convolution.py:57-64)
+            s = "(%s)/(%s)" % (",".join(str(i) for i in self.filter_size.tolist()),
+                               ",".join(str(i) for i in self.filter_stride.tolist()))
         return "%s %d->%d C%s" % (self._name, self.nIn, self.nOut, s)
 
 

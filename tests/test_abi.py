@@ -56,3 +56,72 @@ def test_reference_import_paths_resolve():
     import SparseConvNet.sparseconvnet as scn2
     assert scn2 is scn and callable(sparse_3d_to_dense_2d)
     assert scn2.FPN_Net is scn.FPN_Net
+
+
+def test_reference_call_sites_bind():
+    """every call the reference's own Python layer files make into `sparseconvnet.SCN` (tests/golden/
+    scn_callsites.json, extracted from the reference tree by oracle/make_callsites.py: name, positional argument
+    count, file:line) binds to this repo's module: on-path entry points exist, are real (not stubs) and accept
+    exactly that many positional arguments; off-path ones exist and raise NotImplementedError loudly"""
+    import inspect
+    import json
+    import pytest
+    import sparseconvnet.SCN as SCN
+    doc = json.load(open(os.path.join(ROOT, "tests", "golden", "scn_callsites.json")))
+    on = [c for c in doc["scn_calls"] if c["on_path"]]
+    off = [c for c in doc["scn_calls"] if not c["on_path"]]
+    assert len(on) >= 17 and len(off) >= 10
+    for c in on:
+        where = "%s:%d" % (c["file"], c["line"])
+        fn = getattr(SCN, c["name"], None)
+        assert callable(fn) and not getattr(fn, "off_path", False), c["name"] + " missing (" + where + ")"
+        sig = inspect.signature(fn)
+        try:
+            sig.bind(*([None] * c["nargs"]), **{k: None for k in c["kwargs"]})
+        except TypeError as e:
+            raise AssertionError("%s called with %d positional arguments at %s does not bind: %s"
+                                 % (c["name"], c["nargs"], where, e))
+        # ... and not with one argument less (no silently defaulted tensors)
+        required = [p for p in sig.parameters.values()
+                    if p.default is inspect.Parameter.empty and p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert len(required) == c["nargs"], "%s: %d required parameters, the reference passes %d (%s)" % (
+            c["name"], len(required), c["nargs"], where)
+    on_names = {c["name"] for c in on}
+    for c in off:
+        fn = getattr(SCN, c["name"])
+        if c["name"] in on_names:      # an off-path layer file (shapeContext.py) reusing an on-path entry point
+            inspect.signature(fn).bind(*([None] * c["nargs"]))
+            continue
+        with pytest.raises(NotImplementedError):
+            fn(*([None] * c["nargs"]))
+    # Metadata(dim) resolves the class by name (metadata.py:16-17) and the on-path Python calls these methods
+    M = getattr(SCN, doc["metadata_factory"])
+    for c in doc["method_calls"]:
+        if c["name"] == "getSpatialLocations":
+            inspect.signature(M.getSpatialLocations).bind(None, *([None] * c["nargs"]))
+        else:
+            import sparseconvnet as scn
+            inspect.signature(getattr(scn.SparseConvNetTensor, c["name"])).bind(None, *([None] * c["nargs"]))
+    with pytest.raises(AttributeError):
+        SCN.no_such_name
+
+
+def test_module_surface_equals_reference():
+    """constructor parameter names / order / defaults, __repr__ strings and parameter / buffer names and shapes of
+    the on-path module classes equal the reference's (tests/golden/scn_callsites.json `module_surface`: recorded by
+    oracle/make_callsites.py from the reference's own Python package)"""
+    import inspect
+    import json
+    import sparseconvnet as scn
+    doc = json.load(open(os.path.join(ROOT, "tests", "golden", "scn_callsites.json")))
+    assert len(doc["module_surface"]) >= 19
+    for case in doc["module_surface"]:
+        C = getattr(scn, case["class"])
+        tag = "%s%r" % (case["class"], tuple(case["args"]))
+        ours = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                for p in list(inspect.signature(C.__init__).parameters.values())[1:]]
+        assert ours == case["init_params"], "%s: constructor %r, reference %r" % (tag, ours, case["init_params"])
+        m = C(*case["args"], **case["kwargs"])
+        assert repr(m) == case["repr"], tag
+        assert {k: list(v.shape) for k, v in m.named_parameters()} == case["parameters"], tag
+        assert {k: list(v.shape) for k, v in m.named_buffers()} == case["buffers"], tag
