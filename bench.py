@@ -304,12 +304,20 @@ def run_b200(args, rank, local_rank, world):
     loss_seen = []
     e2e_host_ms = []           # host time between consecutive batches of the e2e loop (diagnostic: stalls show here)
 
+    cuprof_done = []
+
     def timed(n_steps, host_inputs):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = scn.SCN.launch_count()
+        # SCN_BENCH_CUPROF=1: the device-resident timed region is a cudaProfilerStart / Stop range, so that
+        # `ncu --profile-from-start off` lists exactly the launches of the timed steps (profiles/README.md)
+        cuprof = os.environ.get("SCN_BENCH_CUPROF") == "1" and not host_inputs and not cuprof_done
+        if cuprof:
+            cuprof_done.append(True)                           # the headline region only, not value_pruned's
+            torch.cuda.cudart().cudaProfilerStart()
         a.record()
         if host_inputs:
             # end to end from HOST buffers through the public API: scn.VoxelLoader uploads the raw float32 points
@@ -349,6 +357,8 @@ def run_b200(args, rank, local_rank, world):
                 step(prepared, feats_dev)
         b.record()
         torch.cuda.synchronize()
+        if cuprof:
+            torch.cuda.cudart().cudaProfilerStop()
         if world > 1:
             dist.barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
