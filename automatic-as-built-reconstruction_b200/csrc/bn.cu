@@ -7,12 +7,27 @@
 // the per-channel coefficients themselves (no separate finalize launch).
 #include "common.cuh"
 #include "../../include/scn_b200.h"
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
 namespace scn {
 
 constexpr int BN_T = 256;
+// The 2C fp64 column sums exist in G replicas, [G][2C]: block b of a statistics kernel adds into replica
+// b % G and every apply block sums the replicas (fixed order) when it derives the coefficients.  With one copy, the
+// <= 4 blocks per SM x 2C atomics of a launch all land on the 2C x 8 bytes of a few 128-byte lines and drain through
+// the L2 slices that own them one at a time: ncu showed the SMs of a statistics kernel idle for 7 us (C = 32) to 11 us
+// (C = 64) of a 14 - 42 us launch, growing with C and with the number of blocks (tools/bn_probe.py).
+constexpr int BN_G_MAX = 32;
+static int bn_replicas() {            // SCN_B200_BN_REPLICAS (1 ... 32, default 16)
+  static const int g = [] {
+    const char *e = getenv("SCN_B200_BN_REPLICAS");
+    int v = e ? atoi(e) : 16;
+    return v < 1 ? 1 : (v > BN_G_MAX ? BN_G_MAX : v);
+  }();
+  return g;
+}
 
 // y = lrelu(fmaf(x, w, b)) with w = invstd * gamma, b = fma(-mean, w, beta): ONE definition for the forward apply and
 // for the backward pass, which recomputes the sign of the pre-activation from x instead of reading y back (the
@@ -45,7 +60,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(BN_T)
 k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
-               long long n, int C, double *__restrict__ acc, const float *__restrict__ invstd = nullptr,
+               long long n, int C, double *__restrict__ acc, int G, const float *__restrict__ invstd = nullptr,
                const float *__restrict__ gamma = nullptr, const float *__restrict__ beta = nullptr) {
   pdl_sync();
   __shared__ double red[2][BN_T * 4];
@@ -89,11 +104,12 @@ k_bn_stats_vec(const float *__restrict__ X, const float *__restrict__ Yo,
   red[1][t4] = s1.x; red[1][t4 + 1] = s1.y; red[1][t4 + 2] = s1.z; red[1][t4 + 3] = s1.w;
   __syncthreads();
   // thread c (< C) sums the rpb row-slots of channel c: element index = rs*C + c
+  double *__restrict__ mine = acc + (size_t)(blockIdx.x % G) * 2 * C;
   for (int c = threadIdx.x; c < C; c += BN_T) {
     double a = 0, b = 0;
     for (int j = 0; j < rpb; ++j) { a += red[0][j * C + c]; b += red[1][j * C + c]; }
-    atomicAdd(&acc[c], a);        // fp64: the order of the <= 2*SMs block sums is immaterial
-    atomicAdd(&acc[C + c], b);
+    atomicAdd(&mine[c], a);        // fp64: the order of the block sums inside a replica is immaterial
+    atomicAdd(&mine[C + c], b);
   }
 }
 
@@ -102,7 +118,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(BN_T)
 k_bn_stats_gen(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ dY, const float *__restrict__ mean, float leak,
-               long long n, int C, double *__restrict__ acc) {
+               long long n, int C, double *__restrict__ acc, int G) {
   pdl_sync();
   __shared__ double red[2][8][33];
   const int c = blockIdx.y * 32 + threadIdx.x;
@@ -123,23 +139,32 @@ k_bn_stats_gen(const float *__restrict__ X, const float *__restrict__ Yo,
   if (threadIdx.y == 0 && c < C) {
     double a = 0, b = 0;
     for (int j = 0; j < 8; ++j) { a += red[0][j][threadIdx.x]; b += red[1][j][threadIdx.x]; }
-    atomicAdd(&acc[c], a);        // fp64: the order of the <= 2*SMs block sums is immaterial
-    atomicAdd(&acc[C + c], b);
+    double *__restrict__ mine = acc + (size_t)(blockIdx.x % G) * 2 * C;
+    atomicAdd(&mine[c], a);        // fp64: the order of the block sums inside a replica is immaterial
+    atomicAdd(&mine[C + c], b);
   }
+}
+
+// column sum c (s = 0) / second sum (s = 1) over the replicas, in replica order
+__device__ __forceinline__ double bn_acc(const double *__restrict__ acc, int G, int C, int c, int s) {
+  double v = 0;
+#pragma unroll 8
+  for (int g = 0; g < G; ++g) v += acc[(size_t)g * 2 * C + s * C + c];
+  return v;
 }
 
 // ---- coefficients -------------------------------------------------------------------------
 // Every apply block derives the per-channel coefficients from the fp64 sums itself (2C loads);
 // block 0 also publishes the saved / running statistics or the parameter gradients.
 // forward train (CPU/BatchNormalization.cpp:19-40): coef = [scale, shift]
-__device__ __forceinline__ void bn_fwd_coef(const double *__restrict__ acc, long long n, int C, int c,
+__device__ __forceinline__ void bn_fwd_coef(const double *__restrict__ acc, int G, long long n, int C, int c,
                                             float *save_mean, float *save_invstd, float *running_mean,
                                             float *running_var, const float *weight, const float *bias,
                                             float eps, float momentum, int train, bool publish,
                                             float *coef) {
   float mean, invstd;
   if (train) {
-    const double sum = acc[c], sq = acc[C + c];
+    const double sum = bn_acc(acc, G, C, c, 0), sq = bn_acc(acc, G, C, c, 1);
     const double dmean = sum / (double)n;
     const double s = sq - dmean * dmean * (double)n;  // sum of squared deviations
     mean = (float)dmean;
@@ -166,10 +191,10 @@ __device__ __forceinline__ void bn_fwd_coef(const double *__restrict__ acc, long
 }
 
 // backward (:86-106): coef = [gradMean, k, invstd*gamma]
-__device__ __forceinline__ void bn_bwd_coef(const double *__restrict__ acc, long long n, int C, int c,
+__device__ __forceinline__ void bn_bwd_coef(const double *__restrict__ acc, int G, long long n, int C, int c,
                                             const float *save_invstd, const float *weight,
                                             float *d_weight, float *d_bias, bool publish, float *coef) {
-  const double gsum = acc[c], dotp = acc[C + c];
+  const double gsum = bn_acc(acc, G, C, c, 0), dotp = bn_acc(acc, G, C, c, 1);
   const float invstd = save_invstd[c];
   if (publish) {
     if (d_bias) d_bias[c] = (float)gsum;
@@ -187,6 +212,7 @@ struct BnFwdArgs {
   double *zero_buf;   // the OTHER ping-pong sum buffer: block 0 clears it for the next BN call
   int zero_n;
   const double *acc;
+  int replicas;
   float *save_mean, *save_invstd, *running_mean, *running_var;
   const float *weight, *bias;
   float eps, momentum;
@@ -202,7 +228,7 @@ k_bn_fwd_apply(const float *__restrict__ X, float *__restrict__ Y, BnFwdArgs a, 
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < a.zero_n; i += BN_T) a.zero_buf[i] = 0.0;
   for (int c = threadIdx.x; c < C; c += BN_T)
-    bn_fwd_coef(a.acc, n, C, c, a.save_mean, a.save_invstd, a.running_mean, a.running_var, a.weight,
+    bn_fwd_coef(a.acc, a.replicas, n, C, c, a.save_mean, a.save_invstd, a.running_mean, a.running_var, a.weight,
                 a.bias, a.eps, a.momentum, a.train, blockIdx.x == 0, coef);
   __syncthreads();
   const long long total = n * C;
@@ -245,7 +271,7 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
                const float *__restrict__ mean, const double *__restrict__ acc,
                const float *__restrict__ save_invstd, const float *__restrict__ weight,
                float *d_weight, float *d_bias, float leak, long long n, int C, double *zero_buf, int zero_n,
-               const float *R, const float *__restrict__ beta) {
+               const float *R, const float *__restrict__ beta, int G) {
   pdl_sync();
   extern __shared__ float coef[];  // [3C] then mean [C], then (Yo == nullptr) the forward's [w, b] [2C]
   float *smean = coef + 3 * C;
@@ -254,7 +280,7 @@ k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Yo,
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < zero_n; i += BN_T) zero_buf[i] = 0.0;
   for (int c = threadIdx.x; c < C; c += BN_T) {
-    bn_bwd_coef(acc, n, C, c, save_invstd, weight, d_weight, d_bias, blockIdx.x == 0, coef);
+    bn_bwd_coef(acc, G, n, C, c, save_invstd, weight, d_weight, d_bias, blockIdx.x == 0, coef);
     smean[c] = mean[c];
     if (recompute) bn_affine(mean[c], save_invstd[c], weight ? weight[c] : 1.f, beta ? beta[c] : 0.f, aff[c], aff[C + c]);
   }
@@ -336,8 +362,8 @@ static int bn_buffers(cudaStream_t s, int C, double **cur, double **other, int *
   if (!st) {
     st = new BnState();
     for (int i = 0; i < 2; ++i) {
-      SCN_CUDA(cudaMalloc((void **)&st->buf[i], (size_t)2 * BN_MAX_C * sizeof(double)));
-      SCN_CUDA(cudaMemset(st->buf[i], 0, (size_t)2 * BN_MAX_C * sizeof(double)));
+      SCN_CUDA(cudaMalloc((void **)&st->buf[i], (size_t)BN_G_MAX * 2 * BN_MAX_C * sizeof(double)));
+      SCN_CUDA(cudaMemset(st->buf[i], 0, (size_t)BN_G_MAX * 2 * BN_MAX_C * sizeof(double)));
       st->used[i] = 0;
     }
     st->k = 0;
@@ -347,7 +373,7 @@ static int bn_buffers(cudaStream_t s, int C, double **cur, double **other, int *
   *cur = st->buf[a];
   *other = st->buf[b];
   *other_used = st->used[b];
-  st->used[a] = 2 * C;
+  st->used[a] = bn_replicas() * 2 * C;
   st->used[b] = 0;
   st->k++;
   return 0;
@@ -385,13 +411,13 @@ int scn_batchnorm_forward(const float *in, float *out, float *save_mean, float *
     SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
     if (vec)
       SCN_LAUNCH((k_bn_stats_vec<false>), stats_grid(n, BN_T / (C / 4)), BN_T, 0, s, in, nullptr, nullptr, nullptr, 0.f, n, C, acc,
-                 nullptr, nullptr, nullptr);
+                 bn_replicas(), nullptr, nullptr, nullptr);
     else
       SCN_LAUNCH((k_bn_stats_gen<false>), dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s, in, nullptr, nullptr, nullptr,
-                                                                                     0.f, n, C, acc);
+                                                                                     0.f, n, C, acc, bn_replicas());
     SCN_LAUNCHED();
   }
-  BnFwdArgs a{other, other_used, acc, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train};
+  BnFwdArgs a{other, other_used, acc, bn_replicas(), save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, train};
   const long long total = (long long)n * C;
   const size_t sm = (size_t)2 * C * sizeof(float);
   if (vec) SCN_LAUNCH((k_bn_fwd_apply<true>), apply_grid(total / 4), BN_T, sm, s, in, out, a, leakiness, n, C);
@@ -443,21 +469,21 @@ int scn_batchnorm_backward_fused(const float *in, float *d_in, const float *out,
   SCN_TRY(bn_buffers(s, C, &acc, &other, &other_used));
   if (vec)
     SCN_LAUNCH((k_bn_stats_vec<true>), stats_grid(n, BN_T / (C / 4)), BN_T, 0, s, in, out, d_out, save_mean, leakiness, n, C, acc,
-                                                                        save_invstd, weight, bias);
+                                                                        bn_replicas(), save_invstd, weight, bias);
   else
     SCN_LAUNCH((k_bn_stats_gen<true>), dim3(stats_grid(n, 8), cdiv(C, 32)), dim3(32, 8), 0, s, in, out, d_out, save_mean,
-                                                                                   leakiness, n, C, acc);
+                                                                                   leakiness, n, C, acc, bn_replicas());
   SCN_LAUNCHED();
   const long long total = (long long)n * C;
   const size_t sm = (size_t)6 * C * sizeof(float);
   if (vec)
     SCN_LAUNCH((k_bn_bwd_apply<true>), apply_grid(total / 4), BN_T, sm, s, in, out, d_out, d_in, save_mean, acc, save_invstd,
                                                               weight, d_weight, d_bias, leakiness, n, C, other, other_used,
-                                                              residual, bias);
+                                                              residual, bias, bn_replicas());
   else
     SCN_LAUNCH((k_bn_bwd_apply<false>), apply_grid(total), BN_T, sm, s, in, out, d_out, d_in, save_mean, acc, save_invstd,
                                                            weight, d_weight, d_bias, leakiness, n, C, other, other_used,
-                                                           residual, bias);
+                                                           residual, bias, bn_replicas());
   SCN_LAUNCHED();
   prof_end(PROF_BN, s, 5.0 * 4.0 * (double)n * C, 0);  // 5 n C s
   return 0;
