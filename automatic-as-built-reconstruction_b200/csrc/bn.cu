@@ -14,16 +14,16 @@
 namespace scn {
 
 constexpr int BN_T = 256;
-// The 2C fp64 column sums exist in G replicas, [G][2C]: block b of a statistics kernel adds into replica
+// The 2C fp64 column sums exist in G = 8 replicas, [G][2C]: block b of a statistics kernel adds into replica
 // b % G and every apply block sums the replicas (fixed order) when it derives the coefficients.  With one copy, the
 // <= 4 blocks per SM x 2C atomics of a launch all land on the 2C x 8 bytes of a few 128-byte lines and drain through
 // the L2 slices that own them one at a time: ncu showed the SMs of a statistics kernel idle for 7 us (C = 32) to 11 us
 // (C = 64) of a 14 - 42 us launch, growing with C and with the number of blocks (tools/bn_probe.py).
 constexpr int BN_G_MAX = 32;
-static int bn_replicas() {            // SCN_B200_BN_REPLICAS (1 ... 32, default 16)
+static int bn_replicas() {            // SCN_B200_BN_REPLICAS (1 ... 32, default 8: one unrolled batch of loads in bn_acc)
   static const int g = [] {
     const char *e = getenv("SCN_B200_BN_REPLICAS");
-    int v = e ? atoi(e) : 16;
+    int v = e ? atoi(e) : 8;
     return v < 1 ? 1 : (v > BN_G_MAX ? BN_G_MAX : v);
   }();
   return g;
