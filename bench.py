@@ -202,6 +202,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count()
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank): the reference's own
+    # OpenMP loops (per-sample rule building) read the variable when its extension is loaded, ATen follows torch
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     torch.set_num_threads(cores)
     # one reference step of the full 300k-point workload takes ~4.2 s on the box's host cores: up to 30 steps
     # (~2 minutes) run the workload itself, longer runs a bounded 60k-point sample of it
