@@ -1,0 +1,120 @@
+"""GPU parity sweep (fp32 mode) over the clouds and layer geometries of tests/test_oracle_vs_ref_sweep.py - the oracle is
+pinned there against the compiled reference on exactly these cases; here the library meets the oracle on them through
+the C ABI: ragged batches with an empty and a single-point sample, heavy duplication, anisotropic and even submanifold
+filters, overlapping / anisotropic strides with backward, deconvolution and SparseToDense.  Rulebooks bit-exact as
+canonical pair sets, features and gradients at the fp32 bound."""
+import numpy as np
+import pytest
+import torch
+
+import scn_oracle as O
+from test_oracle_vs_ref_sweep import CLOUDS, GEOM, _cloud
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def scn():
+    import sparseconvnet
+    sparseconvnet.set_conv_precision("fp32")
+    return sparseconvnet
+
+
+def _input(scn, coords, ss, C, batch, seed):
+    torch.manual_seed(seed)
+    feats = torch.randn(len(coords), C)
+    leaf = feats.cuda().requires_grad_(True)
+    t = scn.InputLayer(3, ss, 4)([torch.as_tensor(coords), leaf, batch])
+    return t, leaf, feats
+
+
+def _point_grad(coords, dx_sites):
+    loc, prow, header, table = O.input_layer_rules(coords, 4)
+    f = torch.zeros(len(coords), dx_sites.shape[1], requires_grad=True)
+    O.input_layer_forward(f, header, table).backward(dx_sites)
+    return f.grad
+
+
+def _canon(pairs, rin, rout):
+    return O.canonical_pairs(pairs.numpy() if torch.is_tensor(pairs) else pairs, rin, rout)
+
+
+@pytest.mark.parametrize("ci", range(len(CLOUDS)))
+@pytest.mark.parametrize("fs", [[3, 3, 3], [3, 1, 3], [2, 2, 2], [1, 3, 5]])
+def test_submanifold_sweep(scn, ci, fs):
+    sizes, ss, dup = CLOUDS[ci]
+    ss = list(ss)
+    coords = _cloud(sizes, ss, 20 + ci, dup)
+    t, leaf, feats = _input(scn, coords, ss, 32, len(sizes), ci)
+    loc = t.get_spatial_locations().numpy()
+    oloc, _, header, table = O.input_layer_rules(coords, 4)
+    assert np.array_equal(loc, oloc)                                 # first-occurrence order, exactly
+    x = t.features.detach().cpu()
+    assert rel(x, O.input_layer_forward(feats, header, table)) <= 1e-6
+    conv = scn.SubmanifoldConvolution(3, 32, 64, fs, False).cuda()
+    y = conv(t)
+    rules = O.submanifold_rules(loc, ss, fs)
+    r0 = O.canonical_rank(loc, ss)
+    got = t.metadata.getSubmanifoldRuleBook(ss, fs)
+    assert len(got) == len(rules)
+    for k in range(len(rules)):
+        assert np.array_equal(_canon(got[k], r0, r0), _canon(rules[k], r0, r0)), k
+    w = conv.weight.detach().cpu()
+    assert rel(y.features, O.conv_forward(x, w, rules, len(loc))) <= TOL
+    dy = torch.randn_like(y.features)
+    y.features.backward(dy)
+    dx, dw, _ = O.conv_backward(x, dy.cpu(), w, rules)
+    assert rel(conv.weight.grad, dw) <= TOL
+    assert rel(leaf.grad, _point_grad(coords, dx)) <= TOL
+
+
+@pytest.mark.parametrize("ci", range(len(CLOUDS)))
+@pytest.mark.parametrize("gi", range(len(GEOM)))
+def test_strided_sweep(scn, ci, gi):
+    sizes, ss, dup = CLOUDS[ci]
+    fs, st = [list(v) for v in GEOM[gi]]
+    if fs[2] == 0:
+        fs[2] = ss[2]
+    out_ss = [(s - f) // t + 1 for s, f, t in zip(ss, fs, st)]
+    ss = [(o - 1) * t + f for o, t, f in zip(out_ss, st, fs)]
+    coords = _cloud(sizes, ss, 30 + ci, dup)
+    t, leaf, feats = _input(scn, coords, ss, 32, len(sizes), ci + gi)
+    loc0 = t.get_spatial_locations().numpy()
+    conv = scn.Convolution(3, 32, 64, fs, st, False).cuda()
+    dec = scn.Deconvolution(3, 64, 32, fs, st, False).cuda()
+    y = conv(t)
+    z = dec(y)
+    assert y.spatial_size.tolist() == out_ss and z.spatial_size.tolist() == ss
+    gloc1 = y.get_spatial_locations().numpy()
+    oloc1, rules = O.conv_rules(loc0, ss, fs, st, out_ss)
+    pg, po = np.argsort(O.canonical_rank(gloc1, out_ss)), np.argsort(O.canonical_rank(oloc1, out_ss))
+    assert np.array_equal(gloc1[pg], oloc1[po])                       # the same sites
+    assert (np.diff(gloc1[:, 3]) >= 0).all()                          # batch-contiguous ascending
+    r0, r1g, r1o = O.canonical_rank(loc0, ss), O.canonical_rank(gloc1, out_ss), O.canonical_rank(oloc1, out_ss)
+    got = t.metadata.getRuleBook(ss, out_ss, fs, st)
+    assert len(got) == len(rules)
+    for k in range(len(rules)):
+        assert np.array_equal(_canon(got[k], r0, r1g), _canon(rules[k], r0, r1o)), k
+    x, w, w2 = t.features.detach().cpu(), conv.weight.detach().cpu(), dec.weight.detach().cpu()
+    oy = O.conv_forward(x, w, rules, len(oloc1))
+    assert rel(y.features[pg], oy[po]) <= TOL
+    oz = O.conv_forward(oy, w2, rules, len(loc0), swap=True)
+    assert rel(z.features, oz) <= TOL
+    dense = scn.SparseToDense(3, 64)(y)
+    assert rel(dense, O.sparse_to_dense(oy, oloc1, out_ss, len(sizes))) <= TOL
+    dz = torch.randn_like(z.features)
+    z.features.backward(dz)
+    ody, odw2, _ = O.conv_backward(oy, dz.cpu(), w2, rules, swap=True)
+    assert rel(dec.weight.grad, odw2) <= TOL
+    odx, odw, _ = O.conv_backward(x, ody, w, rules)
+    assert rel(conv.weight.grad, odw) <= TOL
+    assert rel(leaf.grad, _point_grad(coords, odx)) <= TOL
