@@ -48,7 +48,7 @@ def _worker(rank, world, port, out):
 
 def test_grad_bucket_allreduce_world2():
     world = 2
-    with mp.Manager() as mgr:
+    with mp.get_context("spawn").Manager() as mgr:       # (no fork() of the multi-threaded test process)
         out = mgr.dict()
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert out[0][0] and out[1][0]
