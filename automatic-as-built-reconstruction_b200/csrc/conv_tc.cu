@@ -28,7 +28,6 @@ namespace tc {
 constexpr int KC = 32;                      // reduction elements per pipeline step
 constexpr int NCORE = KC / 4;               // 16-byte pieces (4 tf32) per row and step
 constexpr int A_STAGE = TILE_M * 128;       // 128 rows x 128 bytes, K-major SWIZZLE_128B
-constexpr int NT = 256;                     // threads of the weight-gradient kernel
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
