@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the knob this script flips exists only with profiles/experiments/r02_bn_reverse_traversal.patch.txt applied (the experiment was
+# measured and not kept - profiles/experiments/README.md); on the shipped tree both arms run the same code.
 # GPU box: A/B of the BN traversal order (SCN_B200_BN_REVERSE=0: statistics and apply both front to back; 1: the
 # statistics pass walks the rows back to front), two interleaved runs each; the BN parity tests run on the default.
 out=gpurun_out; mkdir -p $out

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the knob this script flips exists only with profiles/experiments/r02_fused_residual_add_v2.patch.txt applied (the experiment was
+# measured and not kept - profiles/experiments/README.md); on the shipped tree both arms run the same code.
 # GPU box: the fused conv -> add epilogue (SCN_B200_FUSE_ADD=1, default) against separate k_add launches (=0):
 # bit-identity / parity tests first, then two interleaved bench runs each.
 out=gpurun_out; mkdir -p $out

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the knob this script flips exists only with profiles/experiments/r02_spatial_sort_scale1.patch.txt applied (the experiment was
+# measured and not kept - profiles/experiments/README.md); on the shipped tree both arms run the same code.
 # GPU box: Morton renumbering of the first large conv-created scale (SCN_B200_SPATIAL_SORT=1, default) against
 # first-touch order (=0): parity tests on the default first, then two interleaved bench runs each.
 out=gpurun_out; mkdir -p $out
