@@ -1,8 +1,8 @@
 #!/bin/bash
-# GPU box: replicated fp64 BN accumulators (SCN_B200_BN_REPLICAS: 1 = one copy of the 2C column sums, 16 default)
+# GPU box: replicated fp64 BN accumulators (SCN_B200_BN_REPLICAS: 1 = one copy of the 2C column sums, 8 default)
 out=gpurun_out; mkdir -p $out
 for g in 1 4 16 32; do
-  SCN_B200_BN_REPLICAS=$g timeout 120 python tools/bn_probe.py 10 2>&1 | sed "s/^cap=4 unroll=4/replicas=$g/" | tee -a $out/bn_replicas_probe.log | tail -8
+  SCN_B200_BN_REPLICAS=$g timeout 120 python tools/bn_probe.py 10 2>&1 | tee -a $out/bn_replicas_probe.log | tail -8
 done
 timeout 300 python -m pytest tests -m gpu -x -q -k "batchnorm or backbone or layer_graph or dense_equivalence or wide or pruned or full_size" > $out/ab_bnrep_tests.log 2>&1
 echo "tests rc=$? $(tail -1 $out/ab_bnrep_tests.log)"

@@ -15,7 +15,7 @@ SHAPES = [(278639, 32), (227288, 64), (123489, 64), (38672, 128), (9544, 128), (
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-tag = "cap=%s unroll=%s" % (os.environ.get("SCN_B200_BN_STATS_CAP", "4"), os.environ.get("SCN_B200_BN_STATS_UNROLL", "4"))
+tag = "replicas=%s" % os.environ.get("SCN_B200_BN_REPLICAS", "8")
 tot_f = tot_b = 0.0
 for n, C in SHAPES:
     x = torch.randn(n, C, device=dev)

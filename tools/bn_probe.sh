@@ -1,4 +1,7 @@
 #!/bin/bash
+# NOTE: SCN_B200_BN_STATS_CAP / _UNROLL were knobs of an experimental build of bn.cu (statistics blocks per SM, row slots
+# unrolled; results in profiles/experiments/r02_bn_probe_grid_unroll.txt: the shipped 4 / 4 is the best pair) - the shipped
+# library ignores them; tools/bn_probe.py itself and SCN_B200_BN_REPLICAS (tools/ab_bn_replicas*.sh) work on the shipped tree.
 out=gpurun_out; mkdir -p $out
 for cfg in "4 4" "6 4" "8 4" "4 8" "8 8" "2 4"; do set -- $cfg
   SCN_B200_BN_STATS_CAP=$1 SCN_B200_BN_STATS_UNROLL=$2 timeout 120 python tools/bn_probe.py 10 2>&1 | tee -a $out/bn_probe.log | tail -8
